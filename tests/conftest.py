@@ -1,0 +1,57 @@
+import glob
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def golden_case_names():
+    return sorted(os.path.basename(p)[len("case_"):-len(".npz")]
+                  for p in glob.glob(os.path.join(GOLDEN, "case_*.npz")))
+
+
+def load_case(name):
+    from fiat_b200 import description
+    case = description.load(os.path.join(GOLDEN, f"case_{name}.npz"))
+    ent = case["entity"]
+    if ent == "none":
+        case["entity"] = None
+    else:
+        dim, eid = ent
+        case["entity"] = (tuple(dim) if isinstance(dim, list) else dim, eid)
+    case["ref"] = {tuple(k): v for k, v in zip(case["keys"], case["values"])}
+    return case
+
+
+def load_desc(name):
+    from fiat_b200 import description
+    return description.load(os.path.join(GOLDEN, f"desc_{name}.npz"))
+
+
+def tolerance(desc, alpha):
+    """north_star: 1e-12 * max|ref| per derivative component; 1e-10 for order >= 2 at degree >= 8."""
+    def degree(d):
+        if d["kind"] == "simplex":
+            return int(d["degree"])
+        if d["kind"] == "flattened":
+            return degree(d["element"])
+        return max(degree(d["A"]), degree(d["B"]))
+    return 1e-10 if (sum(alpha) >= 2 and degree(desc) >= 8) else 1e-12
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")

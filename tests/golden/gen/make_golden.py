@@ -1,0 +1,214 @@
+"""Generate the golden fixtures under tests/golden/ by running the *reference* itself.
+
+Run in the build container only (needs /root/reference; the GPU box never runs this):
+
+    python tests/golden/gen/make_golden.py
+
+The reference is imported from /root/reference with the `recursivenodes` stand-in that sits next
+to this script (the real package is not installed here; it is only used at element-construction
+time).  For every case we store
+  * the element description (`fiat_b200.extract.describe_element`),
+  * the evaluation points, derivative order and entity,
+  * the reference's `element.tabulate(order, points, entity)` result,
+  * for split-cell elements, the reference's `compute_cell_point_map` membership matrices.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", "..", ".."))
+sys.path.insert(0, HERE)
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+import numpy  # noqa: E402
+import FIAT  # noqa: E402
+from FIAT import expansions, polynomial_set  # noqa: E402
+from FIAT.reference_element import ufc_simplex, UFCInterval  # noqa: E402
+from FIAT.tensor_product import FlattenedDimensions  # noqa: E402
+
+from fiat_b200 import description  # noqa: E402
+from fiat_b200.extract import describe_element  # noqa: E402
+
+OUT = os.path.abspath(os.path.join(HERE, ".."))
+
+
+def simplex_points(rng, n, sd):
+    u = numpy.sort(rng.random((n, sd)), axis=1)
+    return numpy.diff(numpy.concatenate([numpy.zeros((n, 1)), u], axis=1), axis=1)
+
+
+def adversarial_triangle_points(complex_):
+    """Vertices, edge midpoints, barycentres of every subcell, offsets across interior facets,
+    and a ring of exterior points."""
+    top = complex_.get_topology()
+    verts = numpy.array(complex_.get_vertices())
+    pts = [v for v in verts]
+    for e in top[1].values():
+        a, b = verts[list(e)]
+        mid = 0.5 * (a + b)
+        nrm = numpy.array([-(b - a)[1], (b - a)[0]])
+        nrm = nrm / numpy.linalg.norm(nrm)
+        pts.append(mid)
+        pts.append(0.25 * a + 0.75 * b)
+        for eps in (2e-16, 1e-15, 1e-13, 1e-11, 1e-9):
+            pts.append(mid + eps * nrm)
+            pts.append(mid - eps * nrm)
+    for c in top[2].values():
+        pts.append(verts[list(c)].mean(axis=0))
+    pts.append(numpy.array([1.0 / 3.0, 1.0 / 3.0]))
+    for t in numpy.linspace(0, 2 * numpy.pi, 13)[:-1]:
+        pts.append(numpy.array([1 / 3 + 0.9 * numpy.cos(t), 1 / 3 + 0.9 * numpy.sin(t)]))
+    pts.append(numpy.array([0.2, 0.2 + 1e-13]))
+    pts.append(numpy.array([0.2, 0.2 + 1e-11]))
+    pts.append(numpy.array([-1e-14, 0.5]))
+    pts.append(numpy.array([0.5, -1e-10]))
+    return numpy.array(pts)
+
+
+class CiarletElement:
+    """Holder that presents a bare PolynomialSet through the element interface
+    (used to pin expansion variants that no shipped element family exposes directly)."""
+
+    def __init__(self, poly_set):
+        self.poly_set = poly_set
+        self.ref_el = poly_set.get_reference_element()
+
+    def get_nodal_basis(self):
+        return self.poly_set
+
+    def get_reference_element(self):
+        ref_el = self.ref_el
+        return ref_el.get_parent() or ref_el
+
+    def tabulate(self, order, points, entity=None):
+        return self.poly_set.tabulate(numpy.asarray(points), order)
+
+
+def membership(complex_, pts, unique):
+    cpm = expansions.compute_cell_point_map(complex_, pts, unique=unique)
+    ncells = len(complex_.get_topology()[complex_.get_spatial_dimension()])
+    near = numpy.zeros((ncells, len(pts)), dtype=bool)
+    for c, ipts in cpm.items():
+        near[c, ipts] = True
+    return near
+
+
+def write_case(name, element, order, pts, entity=None, with_cells=False):
+    desc = describe_element(element)
+    ref = element.tabulate(order, pts, entity)
+    case = {
+        "name": name,
+        "desc": desc,
+        "order": order,
+        "points": numpy.asarray(pts, dtype=float),
+        "entity": "none" if entity is None else [entity[0] if not isinstance(entity[0], tuple) else list(entity[0]), int(entity[1])],
+        "keys": [list(k) for k in ref.keys()],
+        "values": [numpy.asarray(v, dtype=float) for v in ref.values()],
+    }
+    if with_cells:
+        complex_ = element.get_nodal_basis().get_expansion_set().ref_el
+        case["near_unique"] = membership(complex_, numpy.asarray(pts), True)
+        case["near_all"] = membership(complex_, numpy.asarray(pts), False)
+    path = os.path.join(OUT, f"case_{name}.npz")
+    description.save(path, case)
+    print(f"{name:32s} {os.path.getsize(path) / 1024:8.1f} KiB  keys={len(ref)}  shape={next(iter(ref.values())).shape}")
+
+
+def main():
+    rng = numpy.random.default_rng(20261018)
+    T1, T2, T3 = UFCInterval(), ufc_simplex(2), ufc_simplex(3)
+
+    # --- BASELINE configs at fixture sizes ---
+    write_case("p3_tri_o1", FIAT.Lagrange(T2, 3), 1, simplex_points(rng, 200, 2))
+    write_case("p8_tet_o2", FIAT.Lagrange(T3, 8), 2, simplex_points(rng, 32, 3))
+    write_case("n2curl4_tet_o1", FIAT.NedelecSecondKind(T3, 4), 1, simplex_points(rng, 32, 3))
+    for nm, el in (("hct", FIAT.HsiehCloughTocher(T2)),
+                   ("ps6", FIAT.QuadraticPowellSabin6(T2)),
+                   ("ps12", FIAT.QuadraticPowellSabin12(T2))):
+        complex_ = el.get_nodal_basis().get_expansion_set().ref_el
+        pts = numpy.concatenate([simplex_points(rng, 150, 2), adversarial_triangle_points(complex_)])
+        write_case(f"{nm}_o2", el, 2, pts, with_cells=True)
+        write_case(f"{nm}_o0", el, 0, pts, with_cells=True)
+    G = FIAT.GaussLobattoLegendre(T1, 10)
+    quad = FlattenedDimensions(FIAT.TensorProductElement(G, G))
+    hexa = FlattenedDimensions(FIAT.TensorProductElement(quad, G))
+    hpts = rng.random((8, 3))
+    nodes = numpy.array([list(nd.get_point_dict().keys())[0][0] for nd in G.dual_basis()])
+    hpts[0] = (nodes[3], 0.3, nodes[7])        # coordinates that coincide with GLL nodes
+    hpts[1] = (0.0, 1.0, nodes[5])
+    write_case("gll_q10_hex_o1", hexa, 1, hpts)
+
+    # --- wider coverage of the same path ---
+    write_case("p1_tri_o2", FIAT.Lagrange(T2, 1), 2, simplex_points(rng, 40, 2))
+    write_case("p2_tri_facet1_o1", FIAT.Lagrange(T2, 2), 1, rng.random((17, 1)), entity=(1, 1))
+    write_case("p2_tet_vertex_o1", FIAT.Lagrange(T3, 2), 1, numpy.zeros((1, 0)), entity=(0, 2))
+    write_case("p4_tet_face2_o2", FIAT.Lagrange(T3, 4), 2, simplex_points(rng, 20, 2), entity=(2, 2))
+    write_case("p5_tet_o3", FIAT.Lagrange(T3, 5), 3, simplex_points(rng, 24, 3))
+    write_case("p6_tri_o4", FIAT.Lagrange(T2, 6), 4, simplex_points(rng, 24, 2))
+    write_case("p4_line_o2", FIAT.Lagrange(T1, 4), 2, rng.random((33, 1)))
+    write_case("gll7_line_o3", FIAT.GaussLobattoLegendre(T1, 7), 3,
+               numpy.concatenate([rng.random((20, 1)), [[0.0], [1.0], [0.5]]]))
+    write_case("legendre5_line_o3", FIAT.Legendre(T1, 5), 3, rng.random((25, 1)))
+    write_case("dg3_tri_o1", FIAT.DiscontinuousLagrange(T2, 3), 1, simplex_points(rng, 30, 2))
+    write_case("dp0_tet_o1", FIAT.DiscontinuousLagrange(T3, 0), 1, simplex_points(rng, 9, 3))
+    write_case("cr_tri_o1", FIAT.CrouzeixRaviart(T2, 1), 1, simplex_points(rng, 30, 2))
+    write_case("rt3_tri_o1", FIAT.RaviartThomas(T2, 3), 1, simplex_points(rng, 30, 2))
+    write_case("bdm2_tet_o1", FIAT.BrezziDouglasMarini(T3, 2), 1, simplex_points(rng, 30, 3))
+    write_case("ned2_tet_o2", FIAT.Nedelec(T3, 2), 2, simplex_points(rng, 30, 3))
+    write_case("regge1_tri_o1", FIAT.Regge(T2, 1), 1, simplex_points(rng, 30, 2))
+    write_case("argyris_tri_o2", FIAT.Argyris(T2, 5), 2, simplex_points(rng, 30, 2))
+    write_case("morley_tri_o2", FIAT.Morley(T2), 2, simplex_points(rng, 30, 2))
+    write_case("bubble4_tet_o1", FIAT.Bubble(T3, 4), 1, simplex_points(rng, 30, 3))
+    write_case("intleg4_tri_o2", FIAT.IntegratedLegendre(T2, 4), 2, simplex_points(rng, 30, 2))
+
+    for nm, el in (("p2_alfeld_tri", FIAT.Lagrange(T2, 2, variant="alfeld")),
+                   ("p1_iso_tri", FIAT.Lagrange(T2, 1, variant="iso")),
+                   ("p2_iso_line", FIAT.Lagrange(T1, 2, variant="iso"))):
+        complex_ = el.get_nodal_basis().get_expansion_set().ref_el
+        if complex_.get_spatial_dimension() == 2:
+            pts = numpy.concatenate([simplex_points(rng, 60, 2), adversarial_triangle_points(complex_)])
+        else:
+            pts = numpy.concatenate([rng.random((30, 1)), [[0.5], [0.5 + 1e-13], [0.5 - 1e-11], [0.0], [1.0], [-0.1], [1.2]]])
+        write_case(f"{nm}_o1", el, 1, pts, with_cells=True)
+        write_case(f"{nm}_o0", el, 0, pts, with_cells=True)
+    al3 = FIAT.Lagrange(T3, 2, variant="alfeld")
+    write_case("p2_alfeld_tet_o2", al3, 2,
+               numpy.concatenate([simplex_points(rng, 40, 3), [[0.25, 0.25, 0.25], [0.1, 0.1, 0.1], [0.2, 0.2, 0.3]]]),
+               with_cells=True)
+
+    # expansion variants with identity coefficients ("dual" is not exposed by an element family)
+    for variant in (None, "bubble", "dual"):
+        for sd, cell in ((1, T1), (2, T2), (3, T3)):
+            P = polynomial_set.ONPolynomialSet(cell, 4, variant=variant)
+            pts = rng.random((12, 1)) if sd == 1 else simplex_points(rng, 12, sd)
+            write_case(f"on4_{variant or 'none'}_{sd}d_o2", CiarletElement(P), 2, pts)
+
+    # tensor-product elements: quad with entities, prism, hex facet
+    Q2 = FlattenedDimensions(FIAT.TensorProductElement(FIAT.Lagrange(T1, 2), FIAT.Lagrange(T1, 2)))
+    write_case("q2_quad_o2", Q2, 2, rng.random((15, 2)))
+    write_case("q2_quad_edge2_o1", Q2, 1, rng.random((9, 1)), entity=(1, 2))
+    write_case("q2_quad_vertex3_o1", Q2, 1, numpy.zeros((1, 0)), entity=(0, 3))
+    prism = FIAT.TensorProductElement(FIAT.Lagrange(T2, 2), FIAT.Lagrange(T1, 1))
+    write_case("p2xp1_prism_o1", prism, 1, numpy.concatenate([simplex_points(rng, 11, 2), rng.random((11, 1))], axis=1))
+    write_case("p2xp1_prism_facet_o1", prism, 1, numpy.concatenate([rng.random((7, 1)), rng.random((7, 1))], axis=1),
+               entity=((1, 1), 2))
+    G3 = FIAT.GaussLobattoLegendre(T1, 3)
+    hex3 = FlattenedDimensions(FIAT.TensorProductElement(
+        FlattenedDimensions(FIAT.TensorProductElement(G3, G3)), G3))
+    write_case("gll_q3_hex_face4_o2", hex3, 2, rng.random((10, 2)), entity=(2, 4))
+    dq = FlattenedDimensions(FIAT.TensorProductElement(FIAT.GaussLegendre(T1, 3), FIAT.GaussLegendre(T1, 2)))
+    write_case("dq32_quad_o2", dq, 2, rng.random((10, 2)))
+
+    # element descriptions alone, for bench.py and full-size GPU tests
+    for nm, el in (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),
+                   ("hct", FIAT.HsiehCloughTocher(T2)), ("ps6", FIAT.QuadraticPowellSabin6(T2)),
+                   ("ps12", FIAT.QuadraticPowellSabin12(T2)), ("gll_q10_hex", hexa),
+                   ("p3_tri", FIAT.Lagrange(T2, 3))):
+        path = os.path.join(OUT, f"desc_{nm}.npz")
+        description.save(path, describe_element(el))
+        print(f"desc {nm:27s} {os.path.getsize(path) / 1024:8.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/case_*.npz)."""
+import numpy
+import pytest
+
+from conftest import golden_case_names, load_case, tolerance
+from oracle import fiat_oracle
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_oracle_matches_reference(name):
+    case = load_case(name)
+    got = fiat_oracle.tabulate(case["desc"], case["order"], case["points"], case["entity"])
+    ref = case["ref"]
+    assert list(got.keys()) == list(ref.keys())          # same keys in the same (mis) order
+    for alpha, expect in ref.items():
+        assert got[alpha].shape == expect.shape
+        scale = max(abs(expect).max(), 1e-300) if expect.size else 1.0
+        err = abs(got[alpha] - expect).max() if expect.size else 0.0
+        assert err <= tolerance(case["desc"], alpha) * scale, (alpha, err / scale)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_case_names()])
+def test_oracle_subcell_assignment_bit_exact(name):
+    case = load_case(name)
+    if "near_all" not in case:
+        pytest.skip("single-cell element")
+    desc, pts = case["desc"], case["points"]
+    assert numpy.array_equal(fiat_oracle.locate_cells(desc, pts, unique=False), case["near_all"])
+    assert numpy.array_equal(fiat_oracle.locate_cells(desc, pts, unique=True), case["near_unique"])
