@@ -1,0 +1,135 @@
+"""ctypes binding of the C ABI declared in include/fiat_b200.h.
+
+The library is built in-tree (fiat_b200/csrc/libfiat_b200.so).  There is no fallback: if the
+library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfiat_b200.so")
+
+c_i32, c_i64, c_u32, c_dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_double
+p_i32, p_dbl, p_void = ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), ctypes.c_void_p
+
+
+class SimplexProgramStruct(ctypes.Structure):
+    _fields_ = [
+        ("sd", c_i32), ("degree", c_i32), ("order", c_i32), ("na", c_i32), ("expansion", c_i32),
+        ("ncells", c_i32), ("nslots", c_i32), ("nrows", c_i32), ("unique", c_i32),
+        ("nsteps", c_i32), ("nchains", c_i32), ("nfix", c_i32), ("line_n", c_i32),
+        ("chain_ptr", c_i32 * 4),
+        ("step_idx", p_i32), ("step_dat", p_dbl), ("chains", p_i32), ("fix_idx", p_i32), ("fix_w", p_dbl),
+        ("geom", p_dbl), ("bary", p_dbl), ("ccell", p_dbl),
+        ("low1", p_i32), ("mul1", p_dbl), ("low2", p_i32), ("mul2", p_dbl),
+        ("line_tab", p_dbl), ("line_tab_len", c_i64),
+        ("nrb", c_i32), ("kpad", c_i32), ("nblk", c_i32),
+        ("blk_ptr", p_i32), ("blk_kb", p_i32), ("blk_frag", p_dbl), ("rb_order", p_i32),
+    ]
+
+
+class EntityMapStruct(ctypes.Structure):
+    _fields_ = [("dim", c_i32), ("identity", c_i32), ("C", c_dbl * 9), ("offset", c_dbl * 3)]
+
+
+class TensorLeafStruct(ctypes.Structure):
+    _fields_ = [("plan", p_void), ("entity", EntityMapStruct), ("point_offset", c_i32)]
+
+
+class LibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = [
+    "fiatb200_version", "fiatb200_last_error", "fiatb200_simplex_plan_create", "fiatb200_tensor_plan_create",
+    "fiatb200_plan_destroy", "fiatb200_plan_shape", "fiatb200_tabulate", "fiatb200_locate_subcells",
+    "fiatb200_tabulate_host", "fiatb200_launch_count",
+]
+
+
+def load():
+    """Load libfiat_b200.so (once).  Raises if it has not been built -- no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryError(f"{LIB_PATH} is missing: build it with fiat_b200/csrc/build.sh "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.fiatb200_version.restype = ctypes.c_int
+    lib.fiatb200_last_error.restype = ctypes.c_char_p
+    lib.fiatb200_launch_count.restype = c_i64
+    lib.fiatb200_simplex_plan_create.argtypes = [ctypes.POINTER(SimplexProgramStruct), ctypes.POINTER(p_void)]
+    lib.fiatb200_tensor_plan_create.argtypes = [ctypes.POINTER(TensorLeafStruct), c_i32, c_i32, ctypes.POINTER(p_void)]
+    lib.fiatb200_plan_destroy.argtypes = [p_void]
+    lib.fiatb200_plan_shape.argtypes = [p_void, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    lib.fiatb200_tabulate.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, p_void, c_i64,
+                                      c_u32, p_void]
+    lib.fiatb200_locate_subcells.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, c_i32,
+                                             p_void, p_void]
+    lib.fiatb200_tabulate_host.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, p_void,
+                                           c_i64, c_u32]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().fiatb200_last_error()
+        raise LibraryError(f"fiat_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def _ptr(arr, ctype):
+    return arr.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def simplex_struct(prog):
+    """ctypes view of a plan.SimplexProgram; returns (struct, keepalive list)."""
+    keep = []
+
+    def f64(a):
+        a = numpy.ascontiguousarray(a, dtype=numpy.float64)
+        keep.append(a)
+        return _ptr(a, c_dbl)
+
+    def i32(a):
+        a = numpy.ascontiguousarray(a, dtype=numpy.int32)
+        keep.append(a)
+        return _ptr(a, c_i32)
+
+    s = SimplexProgramStruct()
+    s.sd, s.degree, s.order, s.na, s.expansion = prog.sd, prog.degree, prog.order, prog.na, prog.expansion
+    s.ncells, s.nslots, s.nrows, s.unique = prog.ncells, prog.nslots, prog.nrows, prog.unique
+    s.nsteps, s.nchains, s.nfix, s.line_n = len(prog.step_idx), len(prog.chains), len(prog.fix_idx), prog.line_n
+    cp = list(prog.chain_ptr) + [int(prog.chain_ptr[-1])] * (4 - len(prog.chain_ptr))
+    s.chain_ptr = (c_i32 * 4)(*[int(v) for v in cp])
+    s.step_idx, s.step_dat, s.chains = i32(prog.step_idx), f64(prog.step_dat), i32(prog.chains)
+    s.fix_idx, s.fix_w = i32(prog.fix_idx), f64(prog.fix_w)
+    s.geom, s.bary, s.ccell = f64(prog.geom), f64(prog.bary), f64(prog.ccell)
+    s.low1, s.mul1, s.low2, s.mul2 = i32(prog.low1), f64(prog.mul1), i32(prog.low2), f64(prog.mul2)
+    s.line_tab, s.line_tab_len = f64(prog.line_tab), int(numpy.size(prog.line_tab))
+    s.nrb, s.kpad, s.nblk = len(prog.blk_ptr) - 1, prog.kpad, len(prog.blk_kb)
+    s.blk_ptr, s.blk_kb, s.blk_frag, s.rb_order = i32(prog.blk_ptr), i32(prog.blk_kb), f64(prog.blk_frag), i32(prog.rb_order)
+    return s, keep
+
+
+def entity_struct(sd, transform):
+    """transform: None (identity) or (C (dim x sd), offset (sd,))."""
+    e = EntityMapStruct()
+    if transform is None:
+        e.dim, e.identity = sd, 1
+        return e
+    C, off = transform
+    C = numpy.asarray(C, dtype=float).reshape(-1, sd)
+    e.dim, e.identity = C.shape[0], 0
+    flat = numpy.zeros(9)
+    flat[:C.size] = C.reshape(-1)
+    e.C = (c_dbl * 9)(*flat)
+    o = numpy.zeros(3)
+    o[:sd] = off
+    e.offset = (c_dbl * 3)(*o)
+    return e

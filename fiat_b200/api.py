@@ -1,0 +1,271 @@
+"""Public API: a drop-in for `FiniteElement.tabulate(order, points, entity=None)`
+(FIAT/finite_element.py:98-109,181-197; TensorProductElement / FlattenedDimensions:
+FIAT/tensor_product.py:231-336,396-407) that runs on the B200.
+
+    from fiat_b200 import tabulate
+    tab = tabulate(element, order, points)          # element built by FIAT itself
+    tab[(1, 0, 0)]                                   # torch.float64 cuda tensor (ndofs, *value_shape, npts)
+
+The result is the same dict as the reference's: keys are derivative multi-indices in the order
+mis(sd,0), ..., mis(sd,order); values have shape (ndofs, *value_shape, npoints), float64.  The
+values are views of ONE device allocation `(nalpha, ndofs, *value_shape, npoints)`.
+
+`element` may also be an element description (`fiat_b200.extract.describe_element`, possibly
+loaded from a file), which is how the GPU box runs without FIAT installed.  Plans (device tables)
+are cached per element and order.  There is no CPU fallback: unsupported elements raise
+`NotImplementedError`, a missing CUDA library or device raises.
+"""
+import ctypes
+import threading
+import weakref
+
+import numpy
+import torch
+
+from . import _lib, plan as planmod
+from .extract import describe_element, UnsupportedElement
+
+__all__ = ["tabulate", "tabulate_into", "tabulate_host", "locate_subcells", "Tabulator", "get_tabulator"]
+
+FORCE_THREAD_PER_POINT = 1
+FORCE_DMMA = 2
+
+
+def _resolve_simplex_entity(desc, entity):
+    sd = int(desc["sd"])
+    if entity is None:
+        entity = (sd, 0)
+    dim, ent = int(entity[0]), int(entity[1])
+    keys = numpy.asarray(desc["ent_keys"]).reshape(-1, 2)
+    hit = numpy.where((keys[:, 0] == dim) & (keys[:, 1] == ent))[0]
+    if len(hit) == 0:
+        if dim == sd and ent == 0:
+            return sd, None
+        raise KeyError(f"no entity {(dim, ent)} on this reference cell")
+    j = int(hit[0])
+    C = numpy.asarray(desc["ent_C"][j][:dim], dtype=float)
+    off = numpy.asarray(desc["ent_off"][j], dtype=float)
+    if dim == sd and numpy.array_equal(C, numpy.eye(sd)) and not off.any():
+        return sd, None
+    return dim, (C, off)
+
+
+class _Plan:
+    """Owns one device plan handle."""
+
+    def __init__(self, handle, keep):
+        self.handle = handle
+        self.keep = keep
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().fiatb200_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class Tabulator:
+    """Device tabulation of one element (description) on one CUDA device."""
+
+    def __init__(self, desc, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fiat_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.desc = desc
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.kind = desc["kind"]
+        self._plans = {}
+        self._lock = threading.Lock()
+
+    # -- shapes -------------------------------------------------------------------------------
+    def cell_dimension(self):
+        return planmod._cell_dim(self.desc)
+
+    def value_shape(self):
+        d = self.desc
+        while d["kind"] == "flattened":
+            d = d["element"]
+        return tuple(int(s) for s in d["value_shape"]) if d["kind"] == "simplex" else ()
+
+    def alphas(self, order):
+        return planmod.alpha_list(self.cell_dimension(), order)
+
+    # -- plans --------------------------------------------------------------------------------
+    def _simplex_plan(self, desc, order):
+        key = ("simplex", id(desc), order)
+        with self._lock:
+            if key not in self._plans:
+                prog = planmod.compile_simplex(desc, order)
+                struct, keep = _lib.simplex_struct(prog)
+                handle = ctypes.c_void_p()
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.fiatb200_simplex_plan_create(ctypes.byref(struct), ctypes.byref(handle)))
+                self._plans[key] = (_Plan(handle, keep), prog)
+            return self._plans[key]
+
+    def _tensor_plan(self, order, entity):
+        ekey = None if entity is None else (tuple(entity[0]) if isinstance(entity[0], (list, tuple)) else entity[0], entity[1])
+        key = ("tensor", order, ekey)
+        with self._lock:
+            cached = self._plans.get(key)
+        if cached is not None:
+            return cached
+        leaves = planmod.flatten_tensor(self.desc, entity)
+        if len(leaves) > 4:
+            raise UnsupportedElement("tensor-product elements with more than 4 factors")
+        arr = (_lib.TensorLeafStruct * len(leaves))()
+        keep, nrows, npdim = [], 1, 0
+        for i, lf in enumerate(leaves):
+            if len(lf.desc["value_shape"]):
+                raise UnsupportedElement("vector-valued tensor-product factors")
+            p, prog = self._simplex_plan(lf.desc, order)
+            dim, tr = _resolve_simplex_entity(lf.desc, lf.entity)
+            arr[i].plan = p.handle
+            arr[i].entity = _lib.entity_struct(lf.sd, tr)
+            if tr is None:
+                arr[i].entity.dim = dim
+            arr[i].point_offset = lf.point_offset
+            keep.append(p)
+            nrows *= prog.nrows
+            npdim = max(npdim, lf.point_offset + lf.point_dim)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fiatb200_tensor_plan_create(arr, len(leaves), order, ctypes.byref(handle)))
+        out = (_Plan(handle, keep), nrows, npdim)
+        with self._lock:
+            self._plans[key] = out
+        return out
+
+    def _resolve(self, order, entity):
+        """(plan handle, entity struct or None, nrows, point dimension, result shape prefix)."""
+        if order < 0:
+            raise ValueError("order must be non-negative")
+        if self.kind == "simplex":
+            p, prog = self._simplex_plan(self.desc, order)
+            dim, tr = _resolve_simplex_entity(self.desc, entity)
+            ent = _lib.entity_struct(prog.sd, tr)
+            return p, ent, prog.nrows, dim, (prog.ndofs,) + prog.value_shape
+        p, nrows, npdim = self._tensor_plan(order, entity)
+        return p, None, nrows, npdim, (nrows,)
+
+    # -- calls --------------------------------------------------------------------------------
+    def _points(self, points, pdim):
+        if isinstance(points, torch.Tensor):
+            pts = points.to(device=self.device, dtype=torch.float64)
+        else:
+            arr = numpy.asarray(points)
+            if arr.dtype == object:
+                raise NotImplementedError("symbolic points are not tabulated on the device")
+            pts = torch.as_tensor(numpy.ascontiguousarray(arr, dtype=numpy.float64), device=self.device)
+        pts = pts.reshape(-1, pdim) if pts.numel() or pts.ndim < 2 else pts.reshape(pts.shape[0], pdim)
+        return pts.contiguous()
+
+    def tabulate(self, order, points, entity=None, flags=0):
+        p, ent, nrows, pdim, prefix = self._resolve(order, entity)
+        pts = self._points(points, pdim)
+        npts = pts.shape[0]
+        alphas = self.alphas(order)
+        out = torch.empty((len(alphas), nrows, npts), dtype=torch.float64, device=self.device)
+        self._launch(p, ent, pts, out, npts, flags)
+        return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
+
+    def tabulate_into(self, out, order, points, entity=None, flags=0):
+        """Streaming form: write into a caller-owned (nalpha, nrows, >=npts) float64 cuda tensor
+        (row stride = out.stride(1)); returns the number of points written."""
+        p, ent, nrows, pdim, _ = self._resolve(order, entity)
+        pts = self._points(points, pdim)
+        npts = pts.shape[0]
+        na = len(self.alphas(order))
+        if out.dtype != torch.float64 or out.device != self.device or out.ndim != 3 or out.shape[0] != na \
+                or out.shape[1] != nrows or out.shape[2] < npts or out.stride(2) != 1 \
+                or out.stride(0) != nrows * out.stride(1):
+            raise ValueError("out must be a float64 cuda tensor (nalpha, nrows, >=npts) with unit point stride")
+        self._launch(p, ent, pts, out, npts, flags, row_stride=out.stride(1))
+        return npts
+
+    def _launch(self, p, ent, pts, out, npts, flags, row_stride=None):
+        if npts == 0:
+            return
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ld = pts.stride(0) if pts.shape[1] else 0
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fiatb200_tabulate(
+                p.handle, ctypes.byref(ent) if ent is not None else None, pts.data_ptr(), npts, ld,
+                out.data_ptr(), npts if row_stride is None else row_stride, flags, stream))
+
+    def tabulate_host(self, order, points, entity=None, chunk_pts=1 << 16, flags=0, out=None):
+        """End-to-end with host (numpy) buffers: returns a dict of numpy arrays, like the reference."""
+        p, ent, nrows, pdim, prefix = self._resolve(order, entity)
+        pts = numpy.ascontiguousarray(numpy.asarray(points, dtype=numpy.float64)).reshape(-1, pdim)
+        npts = pts.shape[0]
+        alphas = self.alphas(order)
+        if out is None:
+            out = numpy.empty((len(alphas), nrows, npts))
+        if npts:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fiatb200_tabulate_host(
+                    p.handle, ctypes.byref(ent) if ent is not None else None, pts.ctypes.data, npts, pdim,
+                    out.ctypes.data, chunk_pts, flags))
+        return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
+
+    def locate_subcells(self, points, unique, entity=None):
+        """Bitmask (uint32 as int64 tensor) of the subcells each point is binned to."""
+        if self.kind != "simplex":
+            raise UnsupportedElement("subcell location is defined for simplicial complexes")
+        p, prog = self._simplex_plan(self.desc, 0)
+        dim, tr = _resolve_simplex_entity(self.desc, entity)
+        ent = _lib.entity_struct(prog.sd, tr)
+        pts = self._points(points, dim)
+        mask = torch.zeros(pts.shape[0], dtype=torch.int32, device=self.device)
+        if pts.shape[0]:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fiatb200_locate_subcells(p.handle, ctypes.byref(ent), pts.data_ptr(), pts.shape[0],
+                                                             pts.stride(0) if dim else 0, int(bool(unique)),
+                                                             mask.data_ptr(), stream))
+        return mask
+
+
+_cache_lock = threading.Lock()
+_by_element = weakref.WeakKeyDictionary()
+_by_desc = {}
+
+
+def get_tabulator(element, device=None):
+    """Cached Tabulator of a FIAT element object or of an element description dict."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if isinstance(element, dict):
+        key = (id(element), str(dev))
+        with _cache_lock:
+            hit = _by_desc.get(key)
+            if hit is None or hit[0] is not element:
+                hit = (element, Tabulator(element, dev))
+                _by_desc[key] = hit
+            return hit[1]
+    with _cache_lock:
+        try:
+            per_dev = _by_element.setdefault(element, {})
+        except TypeError:          # not weak-referenceable
+            per_dev = element.__dict__.setdefault("_fiat_b200_tabulators", {})
+        tab = per_dev.get(str(dev))
+        if tab is None:
+            tab = per_dev[str(dev)] = Tabulator(describe_element(element), dev)
+        return tab
+
+
+def tabulate(element, order, points, entity=None, device=None):
+    """Device drop-in for `element.tabulate(order, points, entity)`."""
+    return get_tabulator(element, device).tabulate(order, points, entity)
+
+
+def tabulate_into(out, element, order, points, entity=None, device=None):
+    return get_tabulator(element, device).tabulate_into(out, order, points, entity)
+
+
+def tabulate_host(element, order, points, entity=None, device=None, chunk_pts=1 << 16):
+    return get_tabulator(element, device).tabulate_host(order, points, entity, chunk_pts=chunk_pts)
+
+
+def locate_subcells(element, points, unique, device=None):
+    return get_tabulator(element, device).locate_subcells(points, unique)

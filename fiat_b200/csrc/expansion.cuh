@@ -1,0 +1,353 @@
+// Per-point expansion arithmetic shared by all kernels: entity transform, split-cell location,
+// Dubiner / integrated-Jacobi recurrence with derivative jets, C0 fix-ups, 1-D sets.
+//
+// Follows the reference's arithmetic (paths relative to the FIAT source tree):
+//   entity transform            FIAT/reference_element.py:570-609
+//   l1 distance / binning       FIAT/reference_element.py:616-644,779-780; FIAT/expansions.py:771-811
+//   recurrence factors          FIAT/expansions.py:54-63
+//   three-term recurrence       FIAT/expansions.py:202-249 (Leibniz rule: :66-137)
+//   C0 fix-ups                  FIAT/expansions.py:281-295
+//   Legendre line set           FIAT/expansions.py:659-678, FIAT/jacobi.py:47-74
+//   Lagrange line set           FIAT/barycentric_interpolation.py:22-47
+// The per-pass normalisation (:251-266) and the C0 reordering (:297-322) are folded into the
+// coefficient matrix on the host (fiat_b200/plan.py).
+#pragma once
+#include "device_plan.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// entity transform: x_cell = x_entity * C + offset
+// ---------------------------------------------------------------------------------------------
+template <int SD>
+__device__ __forceinline__ void apply_entity(const DevEntity& E, const double* __restrict__ pt, double (&x)[3]) {
+    x[0] = x[1] = x[2] = 0.0;
+    if (E.identity) {
+#pragma unroll
+        for (int j = 0; j < SD; ++j) x[j] = pt[j];
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < SD; ++j) {
+        double s = 0.0;
+        for (int d = 0; d < E.dim; ++d) s = fma(pt[d], E.C[d * SD + j], s);
+        x[j] = s + E.off[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// split-cell location.  No FMA contraction here: the comparison against best + 1e-12 must bin
+// points exactly like the reference does.
+// ---------------------------------------------------------------------------------------------
+template <int SD>
+__device__ __forceinline__ double l1_distance(const double* __restrict__ rows, const double (&x)[3]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i <= SD; ++i) {
+        const double* r = rows + 4 * i;
+        double lam = __dmul_rn(x[0], r[0]);
+#pragma unroll
+        for (int d = 1; d < SD; ++d) lam = __dadd_rn(lam, __dmul_rn(x[d], r[d]));
+        lam = __dadd_rn(lam, r[3]);
+        const double t = __dadd_rn(fabs(lam), -lam);
+        s = (i == 0) ? t : __dadd_rn(s, t);
+    }
+    return __dmul_rn(0.5, fabs(s));
+}
+
+template <int SD>
+__device__ __forceinline__ unsigned locate_cells(const double* __restrict__ bary, int ncells, int unique,
+                                                 const double (&x)[3]) {
+    if (ncells == 1) return 1u;
+    const double best = l1_distance<SD>(bary + 16 * ncells, x);
+    const double tol = __dadd_rn(best, 1e-12);
+    unsigned mask = 0;
+    for (int c = 0; c < ncells; ++c) {
+        if (l1_distance<SD>(bary + 16 * c, x) < tol) {
+            mask |= 1u << c;
+            if (unique) break;
+        }
+    }
+    return mask;
+}
+
+// ---------------------------------------------------------------------------------------------
+// derivative jets.  Component order = mis(SD,0), mis(SD,1), mis(SD,2): value, gradient, then the
+// upper triangle of the Hessian row by row.  ORDER = -1 selects the table-driven generic path.
+// ---------------------------------------------------------------------------------------------
+template <int SD, int ORDER>
+struct Jet {
+    static constexpr int NA = fb_binom(SD + ORDER, ORDER);
+    static constexpr int CAP = NA;
+
+    __device__ __forceinline__ static void first(const DevSimplex&, int, double* __restrict__ nx,
+                                                 const double* __restrict__ cu, double F,
+                                                 const double* __restrict__ dF) {
+        nx[0] = F * cu[0];
+        if (ORDER >= 1) {
+#pragma unroll
+            for (int d = 0; d < SD; ++d) nx[1 + d] = fma(F, cu[1 + d], dF[d] * cu[0]);
+        }
+        if (ORDER >= 2) {
+            int k = 0;
+#pragma unroll
+            for (int d1 = 0; d1 < SD; ++d1) {
+#pragma unroll
+                for (int d2 = d1; d2 < SD; ++d2) {
+                    const int j = 1 + SD + k;
+                    double v = F * cu[j];
+                    if (d1 == d2) {
+                        v = fma(2.0 * dF[d1], cu[1 + d1], v);
+                    } else {
+                        v = fma(dF[d1], cu[1 + d2], v);
+                        v = fma(dF[d2], cu[1 + d1], v);
+                    }
+                    nx[j] = v;
+                    ++k;
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ static void three(const DevSimplex& P, int na, double* __restrict__ nx,
+                                                 const double* __restrict__ cu, const double* __restrict__ pv,
+                                                 double F, const double* __restrict__ dF, double G,
+                                                 const double* __restrict__ dG, const double* __restrict__ ddG) {
+        first(P, na, nx, cu, F, dF);
+        nx[0] = fma(G, pv[0], nx[0]);
+        if (ORDER >= 1) {
+#pragma unroll
+            for (int d = 0; d < SD; ++d) nx[1 + d] = fma(G, pv[1 + d], fma(dG[d], pv[0], nx[1 + d]));
+        }
+        if (ORDER >= 2) {
+            int k = 0;
+#pragma unroll
+            for (int d1 = 0; d1 < SD; ++d1) {
+#pragma unroll
+                for (int d2 = d1; d2 < SD; ++d2) {
+                    const int j = 1 + SD + k;
+                    double v = fma(G, pv[j], nx[j]);
+                    if (d1 == d2) {
+                        v = fma(2.0 * dG[d1], pv[1 + d1], v);
+                    } else {
+                        v = fma(dG[d1], pv[1 + d2], v);
+                        v = fma(dG[d2], pv[1 + d1], v);
+                    }
+                    nx[j] = fma(ddG[k], pv[0], v);
+                    ++k;
+                }
+            }
+        }
+    }
+};
+
+template <int SD>
+struct Jet<SD, -1> {
+    static constexpr int NA = -1;
+    static constexpr int CAP = FB_NA_MAX;
+    static constexpr int NPAIR = SD * (SD + 1) / 2;
+
+    __device__ static void first(const DevSimplex& P, int na, double* __restrict__ nx,
+                                 const double* __restrict__ cu, double F, const double* __restrict__ dF) {
+        for (int j = 0; j < na; ++j) {
+            double v = F * cu[j];
+            for (int d = 0; d < SD; ++d) {
+                const int lo = __ldg(P.low1 + 3 * j + d);
+                if (lo >= 0) v = fma(__ldg(P.mul1 + 3 * j + d) * dF[d], cu[lo], v);
+            }
+            nx[j] = v;
+        }
+    }
+
+    __device__ static void three(const DevSimplex& P, int na, double* __restrict__ nx,
+                                 const double* __restrict__ cu, const double* __restrict__ pv, double F,
+                                 const double* __restrict__ dF, double G, const double* __restrict__ dG,
+                                 const double* __restrict__ ddG) {
+        for (int j = 0; j < na; ++j) {
+            double v = fma(F, cu[j], G * pv[j]);
+            for (int d = 0; d < SD; ++d) {
+                const int lo = __ldg(P.low1 + 3 * j + d);
+                if (lo >= 0) {
+                    const double m = __ldg(P.mul1 + 3 * j + d);
+                    v = fma(m * dF[d], cu[lo], v);
+                    v = fma(m * dG[d], pv[lo], v);
+                }
+            }
+            for (int k = 0; k < NPAIR; ++k) {
+                const int lo = __ldg(P.low2 + 6 * j + k);
+                if (lo >= 0) v = fma(__ldg(P.mul2 + 6 * j + k) * ddG[k], pv[lo], v);
+            }
+            nx[j] = v;
+        }
+    }
+};
+
+// Recurrence factors of the three collapsing passes at one point: X = (x, -1, -1),
+// fb = (X[c+1] + X[c+2]) / 2, fa = X[c] + (fb + 1).
+template <int SD>
+__device__ __forceinline__ void recurrence_factors(const double (&x)[3], double (&fa)[3], double (&fb)[3]) {
+    double X[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
+#pragma unroll
+    for (int i = 0; i < SD; ++i) X[i] = x[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        fb[c] = 0.5 * (X[c + 1] + X[c + 2]);
+        fa[c] = X[c] + (fb[c] + 1.0);
+    }
+}
+
+__device__ __forceinline__ double pick3(const double (&v)[3], int i) {
+    return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]);
+}
+
+// Run one chain of the recurrence program for one point.  T addresses member slot s, jet
+// component a at T[s * slot_stride + a * comp_stride]; the chain start is read from T.
+template <int SD, int ORDER>
+__device__ __forceinline__ void run_chain(const DevSimplex& P, const double* __restrict__ step_dat_cell,
+                                          int step0, int nst, const double (&fa)[3], const double (&fb)[3],
+                                          double* __restrict__ T, int slot_stride, int comp_stride, int na) {
+    typedef Jet<SD, ORDER> J;
+    double cur[J::CAP], prv[J::CAP], nxt[J::CAP];
+    const int4 s0 = __ldg(P.step_idx + step0);
+    const int codim = s0.w;
+    const double fav = pick3(fa, codim), fbv = pick3(fb, codim);
+    const double fcv = fbv * fbv;
+    {
+        const double* src = T + (size_t)s0.y * slot_stride;
+#pragma unroll
+        for (int a = 0; a < (J::NA > 0 ? J::NA : FB_NA_MAX); ++a)
+            if (J::NA > 0 || a < na) cur[a] = src[a * comp_stride];
+    }
+    for (int s = 0; s < nst; ++s) {
+        const int4 idx = __ldg(P.step_idx + step0 + s);
+        const double* rec = step_dat_cell + (size_t)(step0 + s) * FB_STEP_DOUBLES;
+        const double a = __ldg(rec + 0), b = __ldg(rec + 1), c = __ldg(rec + 2);
+        const double F = a * fav - b * fbv;
+        double dF[3], dG[3], ddG[6];
+#pragma unroll
+        for (int d = 0; d < SD; ++d) dF[d] = __ldg(rec + 3 + d);
+        if (s == 0) {
+            J::first(P, na, nxt, cur, F, dF);
+        } else {
+            const double G = -c * fcv;
+#pragma unroll
+            for (int d = 0; d < SD; ++d) dG[d] = fbv * __ldg(rec + 6 + d);
+#pragma unroll
+            for (int k = 0; k < SD * (SD + 1) / 2; ++k) ddG[k] = __ldg(rec + 9 + k);
+            J::three(P, na, nxt, cur, prv, F, dF, G, dG, ddG);
+        }
+        double* dst = T + (size_t)idx.x * slot_stride;
+#pragma unroll
+        for (int a2 = 0; a2 < (J::NA > 0 ? J::NA : FB_NA_MAX); ++a2) {
+            if (J::NA > 0 || a2 < na) {
+                dst[a2 * comp_stride] = nxt[a2];
+                prv[a2] = cur[a2];
+                cur[a2] = nxt[a2];
+            }
+        }
+    }
+}
+
+// Whole Dubiner expansion of one cell at one point, thread-private column of T.
+template <int SD, int ORDER>
+__device__ __forceinline__ void dubiner_point(const DevSimplex& P, int cell, double start, const double (&xref)[3],
+                                              double* __restrict__ T, int slot_stride, int comp_stride, int na) {
+    double fa[3], fb[3];
+    recurrence_factors<SD>(xref, fa, fb);
+    T[0] = start;
+    for (int a = 1; a < na; ++a) T[a * comp_stride] = 0.0;
+    const double* sd_cell = P.step_dat + (size_t)cell * P.nsteps * FB_STEP_DOUBLES;
+    for (int ch = 0; ch < P.nchains; ++ch) {
+        const int2 c = __ldg(P.chains + ch);
+        run_chain<SD, ORDER>(P, sd_cell, c.x, c.y, fa, fb, T, slot_stride, comp_stride, na);
+    }
+    for (int f = 0; f < P.nfix; ++f) {
+        const int2 ts = __ldg(P.fix_idx + f);
+        const double w = __ldg(P.fix_w + f);
+        double* t = T + (size_t)ts.x * slot_stride;
+        const double* s = T + (size_t)ts.y * slot_stride;
+        for (int a = 0; a < na; ++a) t[a * comp_stride] = fma(-w, s[a * comp_stride], t[a * comp_stride]);
+    }
+}
+
+// Legendre set on a line (variant None): k-th derivative = Jacobi(k,k) times a running scale.
+__device__ __forceinline__ void legendre_line_point(const DevSimplex& P, int cell, double inv_mult, double xin,
+                                                    double* __restrict__ T, int slot_stride, int comp_stride) {
+    const int n = P.line_n, order = P.order;
+    const double* geom = P.geom + cell * FB_GEOM_DOUBLES;
+    const double x = fma(xin, __ldg(geom + 0), __ldg(geom + 9));
+    const double* rec = P.line_tab;
+    const double* scales = P.line_tab + (size_t)(order + 1) * (n + 1) * 4 + (size_t)cell * (order + 1) * (n + 1);
+    for (int k = 0; k <= order; ++k) {
+        const double* rk = rec + (size_t)k * (n + 1) * 4;
+        const double* sk = scales + (size_t)k * (n + 1);
+        for (int p = 0; p < k && p <= n; ++p) T[(size_t)p * slot_stride + k * comp_stride] = 0.0;
+        double pm2 = 0.0, pm1 = 1.0;
+        for (int j = 0; j + k <= n; ++j) {
+            double v;
+            if (j == 0) {
+                v = 1.0;
+            } else if (j == 1) {
+                v = __ldg(rk + 4) + __ldg(rk + 5) * x;
+            } else {
+                v = (__ldg(rk + 4 * j) + __ldg(rk + 4 * j + 1) * x) * pm1 - __ldg(rk + 4 * j + 2) * pm2;
+            }
+            pm2 = pm1;
+            pm1 = v;
+            T[(size_t)(j + k) * slot_stride + k * comp_stride] = v * __ldg(sk + j + k) * inv_mult;
+        }
+    }
+}
+
+// Lagrange set on a line through arbitrary nodes: second barycentric formula, NaN -> 1 at nodes,
+// r-th derivative = dmat^r phi.
+__device__ __forceinline__ void lagrange_line_point(const DevSimplex& P, int cell, double inv_mult, double x,
+                                                    double* __restrict__ T, int slot_stride, int comp_stride) {
+    const int nn = P.line_n, order = P.order;
+    const double* nodes = P.line_tab + (size_t)cell * (2 * nn + nn * nn);
+    const double* wts = nodes + nn;
+    const double* dmat = wts + nn;
+    double sum = 0.0;
+    for (int i = 0; i < nn; ++i) {
+        const double t = (1.0 / (x - __ldg(nodes + i))) * __ldg(wts + i);
+        T[(size_t)i * slot_stride] = t;
+        sum += t;
+    }
+    const double inv = 1.0 / sum;
+    for (int i = 0; i < nn; ++i) {
+        double v = inv * T[(size_t)i * slot_stride];
+        if (v != v) v = 1.0;
+        T[(size_t)i * slot_stride] = v;
+    }
+    for (int r = 1; r <= order; ++r) {
+        for (int i = 0; i < nn; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < nn; ++j)
+                s = fma(__ldg(dmat + i * nn + j), T[(size_t)j * slot_stride + (r - 1) * comp_stride], s);
+            T[(size_t)i * slot_stride + r * comp_stride] = s;
+        }
+    }
+    if (inv_mult != 1.0) {
+        for (int i = 0; i < nn; ++i)
+            for (int r = 0; r <= order; ++r) T[(size_t)i * slot_stride + r * comp_stride] *= inv_mult;
+    }
+}
+
+// Expansion table of one (sub)cell at one point into the thread's column of T.
+template <int SD, int ORDER>
+__device__ __forceinline__ void expansion_point(const DevSimplex& P, int cell, double inv_mult, const double (&x)[3],
+                                                double* __restrict__ T, int slot_stride, int comp_stride, int na) {
+    if (P.expansion == 0) {
+        const double* geom = P.geom + cell * FB_GEOM_DOUBLES;
+        double xr[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < SD; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < SD; ++d) s = fma(x[d], __ldg(geom + i * SD + d), s);
+            xr[i] = s + __ldg(geom + 9 + i);
+        }
+        dubiner_point<SD, ORDER>(P, cell, __ldg(geom + 12) * inv_mult, xr, T, slot_stride, comp_stride, na);
+    } else if (SD == 1) {
+        if (P.expansion == 1) legendre_line_point(P, cell, inv_mult, x[0], T, slot_stride, comp_stride);
+        else lagrange_line_point(P, cell, inv_mult, x[0], T, slot_stride, comp_stride);
+    }
+}

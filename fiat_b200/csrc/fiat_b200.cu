@@ -1,0 +1,472 @@
+// C ABI of the B200 tabulation library (see include/fiat_b200.h).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+#define FB_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(FIATB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+enum PlanKind { PLAN_SIMPLEX = 1, PLAN_TENSOR = 2 };
+
+}  // namespace
+
+struct fiatb200_plan {
+    int kind;
+    int device;
+    void* blob;             // one device allocation holding every table
+    DevSimplex simplex;
+    DevTensor tensor;
+    int max_smem_optin;
+    int num_sms;
+};
+
+namespace {
+
+// bump allocator over one host staging buffer mirrored to one device allocation
+struct Arena {
+    std::vector<unsigned char> host;
+    size_t add(const void* src, size_t bytes) {
+        size_t off = (host.size() + 255) & ~size_t(255);
+        host.resize(off + bytes);
+        if (bytes) memcpy(host.data() + off, src, bytes);
+        return off;
+    }
+};
+
+template <typename T>
+const T* at(void* base, size_t off) {
+    return reinterpret_cast<const T*>(static_cast<unsigned char*>(base) + off);
+}
+
+DevEntity make_entity(const fiatb200_entity_map* e, int sd) {
+    DevEntity d;
+    memset(&d, 0, sizeof(d));
+    if (!e) {
+        d.dim = sd;
+        d.identity = 1;
+        return d;
+    }
+    d.dim = e->dim;
+    d.identity = e->identity;
+    memcpy(d.C, e->C, sizeof(d.C));
+    memcpy(d.off, e->offset, sizeof(d.off));
+    return d;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return FIATB200_OK;
+}
+
+// ---- thread-per-point launch -----------------------------------------------------------------
+template <int SD, int ORDER>
+int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
+                    double* out, long long ostride, cudaStream_t st) {
+    const DevSimplex& P = plan->simplex;
+    const size_t per_point = (size_t)P.nslots * P.na * sizeof(double);
+    // widest block whose private expansion columns fit; very large elements end up with narrow blocks
+    int bp = 128;
+    while (bp > 32 && per_point * bp > 96 * 1024) bp >>= 1;
+    while (bp > 8 && per_point * bp > (size_t)plan->max_smem_optin) bp >>= 1;
+    const size_t smem = per_point * bp;
+    if (smem > (size_t)plan->max_smem_optin)
+        return fail(FIATB200_ERR_UNSUPPORTED, "expansion table of one point tile does not fit in shared memory");
+    int rc = set_smem(k_cellwise<SD, ORDER>, smem);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((npts + bp - 1) / bp);
+    k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, E, pts, npts, ldp, out, ostride);
+    g_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
+template <int SD>
+int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts,
+                      long long ldp, double* out, long long ostride, cudaStream_t st) {
+    switch (plan->simplex.order) {
+        case 0: return launch_cellwise<SD, 0>(plan, E, pts, npts, ldp, out, ostride, st);
+        case 1: return launch_cellwise<SD, 1>(plan, E, pts, npts, ldp, out, ostride, st);
+        case 2: return launch_cellwise<SD, 2>(plan, E, pts, npts, ldp, out, ostride, st);
+        default: return launch_cellwise<SD, -1>(plan, E, pts, npts, ldp, out, ostride, st);
+    }
+}
+
+// ---- tile / DMMA launch ------------------------------------------------------------------------
+bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
+    const DevSimplex& P = plan->simplex;
+    if (P.ncells != 1 || P.expansion != 0 || P.order > 2 || P.nblk == 0) return false;
+    const size_t budget2 = 100 * 1024;                       // two CTAs per SM
+    const size_t budget1 = (size_t)plan->max_smem_optin - 1024;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int pt = 128; pt >= 8; pt >>= 1) {
+            int ld = P.na * pt;
+            while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
+            const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double);
+            if (bytes <= (pass == 0 ? budget2 : budget1)) {
+                const int ncb = P.na * pt / 8;
+                int ngroups = (ncb + FB_MMA_SMAX - 1) / FB_MMA_SMAX;
+                G->PT = pt;
+                G->ldT = ld;
+                G->ngroups = ngroups;
+                G->S = (ncb + ngroups - 1) / ngroups;
+                *smem_out = bytes;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+template <int SD, int ORDER>
+int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
+               long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
+    int rc = set_smem(k_mma<SD, ORDER>, smem);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
+    k_mma<SD, ORDER><<<grid, FB_MMA_THREADS, smem, st>>>(plan->simplex, E, G, pts, npts, ldp, out, ostride);
+    g_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
+template <int SD>
+int dispatch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
+                 long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
+    switch (plan->simplex.order) {
+        case 0: return launch_mma<SD, 0>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+        case 1: return launch_mma<SD, 1>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+        default: return launch_mma<SD, 2>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+    }
+}
+
+int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts, long long npts,
+                     long long ldp, double* out, long long ostride, uint32_t flags, cudaStream_t st) {
+    const DevSimplex& P = plan->simplex;
+    const DevEntity E = make_entity(entity, P.sd);
+    if (E.dim < 0 || E.dim > 3) return fail(FIATB200_ERR_ARG, "entity dimension out of range");
+    MmaGeom G;
+    size_t smem = 0;
+    bool use_mma = mma_geometry(plan, &G, &smem);
+    // the tensor-pipe path pays off once the contraction dominates; tiny elements stay per-thread
+    if (use_mma && !(flags & 2u) && (long long)P.nrows * P.nslots < 256) use_mma = false;
+    if (flags & 1u) use_mma = false;
+    if ((flags & 2u) && !use_mma) return fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
+    if (use_mma) {
+        switch (P.sd) {
+            case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+            case 2: return dispatch_mma<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+            default: return dispatch_mma<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+        }
+    }
+    switch (P.sd) {
+        case 1: return dispatch_cellwise<1>(plan, E, pts, npts, ldp, out, ostride, st);
+        case 2: return dispatch_cellwise<2>(plan, E, pts, npts, ldp, out, ostride, st);
+        default: return dispatch_cellwise<3>(plan, E, pts, npts, ldp, out, ostride, st);
+    }
+}
+
+int tabulate_tensor(const fiatb200_plan* plan, const double* pts, long long npts, long long ldp, double* out,
+                    long long ostride, cudaStream_t st) {
+    const DevTensor& Q = plan->tensor;
+    int bp = 128;
+    while (bp > 32 && (size_t)Q.total_doubles * bp * sizeof(double) > 96 * 1024) bp >>= 1;
+    const size_t smem = (size_t)Q.total_doubles * bp * sizeof(double);
+    if (smem > (size_t)plan->max_smem_optin)
+        return fail(FIATB200_ERR_UNSUPPORTED, "factor tables of one point tile do not fit in shared memory");
+    int rc = set_smem(k_tensor, smem);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((npts + bp - 1) / bp);
+    k_tensor<<<grid, bp, smem, st>>>(Q, pts, npts, ldp, out, ostride);
+    g_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
+int device_limits(fiatb200_plan* plan) {
+    FB_CUDA(cudaGetDevice(&plan->device));
+    FB_CUDA(cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device));
+    FB_CUDA(cudaDeviceGetAttribute(&plan->num_sms, cudaDevAttrMultiProcessorCount, plan->device));
+    return FIATB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fiatb200_version(void) { return 1; }
+
+const char* fiatb200_last_error(void) { return g_error.c_str(); }
+
+int64_t fiatb200_launch_count(void) { return g_launches.load(); }
+
+int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_plan** out) {
+    if (!h || !out) return fail(FIATB200_ERR_ARG, "null argument");
+    if (h->sd < 1 || h->sd > 3) return fail(FIATB200_ERR_UNSUPPORTED, "spatial dimension must be 1, 2 or 3");
+    if (h->ncells < 1 || h->ncells > 32) return fail(FIATB200_ERR_UNSUPPORTED, "at most 32 subcells are supported");
+    if (h->na < 1 || h->na > FB_NA_MAX) return fail(FIATB200_ERR_UNSUPPORTED, "derivative order too high");
+    if (h->expansion != 0 && h->sd != 1) return fail(FIATB200_ERR_ARG, "line expansion on a non-line cell");
+    fiatb200_plan* plan = new fiatb200_plan();
+    memset(static_cast<void*>(plan), 0, sizeof(*plan));
+    plan->kind = PLAN_SIMPLEX;
+    int rc = device_limits(plan);
+    if (rc) { delete plan; return rc; }
+
+    Arena A;
+    const size_t o_step_idx = A.add(h->step_idx, sizeof(int32_t) * 4 * h->nsteps);
+    const size_t o_step_dat = A.add(h->step_dat, sizeof(double) * FB_STEP_DOUBLES * h->nsteps * h->ncells);
+    const size_t o_chains = A.add(h->chains, sizeof(int32_t) * 2 * h->nchains);
+    const size_t o_fix_idx = A.add(h->fix_idx, sizeof(int32_t) * 2 * h->nfix);
+    const size_t o_fix_w = A.add(h->fix_w, sizeof(double) * h->nfix);
+    const size_t o_geom = A.add(h->geom, sizeof(double) * FB_GEOM_DOUBLES * h->ncells);
+    const size_t o_bary = A.add(h->bary, sizeof(double) * 16 * (h->ncells + 1));
+    const size_t o_ccell = A.add(h->ccell, sizeof(double) * (size_t)h->ncells * h->nrows * h->nslots);
+    const size_t o_low1 = A.add(h->low1, sizeof(int32_t) * 3 * h->na);
+    const size_t o_mul1 = A.add(h->mul1, sizeof(double) * 3 * h->na);
+    const size_t o_low2 = A.add(h->low2, sizeof(int32_t) * 6 * h->na);
+    const size_t o_mul2 = A.add(h->mul2, sizeof(double) * 6 * h->na);
+    const size_t o_line = A.add(h->line_tab, sizeof(double) * h->line_tab_len);
+    const size_t o_blk_ptr = A.add(h->blk_ptr, sizeof(int32_t) * (h->nrb + 1));
+    const size_t o_blk_kb = A.add(h->blk_kb, sizeof(int32_t) * h->nblk);
+    const size_t o_blk_frag = A.add(h->blk_frag, sizeof(double) * 32 * (size_t)h->nblk);
+    const size_t o_rb_order = A.add(h->rb_order, sizeof(int32_t) * h->nrb);
+
+    cudaError_t e = cudaMalloc(&plan->blob, A.host.size() + 256);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->blob, A.host.data(), A.host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (plan->blob) cudaFree(plan->blob);
+        delete plan;
+        return fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+    }
+    DevSimplex& P = plan->simplex;
+    P.sd = h->sd; P.degree = h->degree; P.order = h->order; P.na = h->na; P.expansion = h->expansion;
+    P.ncells = h->ncells; P.nslots = h->nslots; P.nrows = h->nrows; P.unique = h->unique;
+    P.nsteps = h->nsteps; P.nchains = h->nchains; P.nfix = h->nfix; P.line_n = h->line_n;
+    for (int i = 0; i < 4; ++i) P.chain_ptr[i] = h->chain_ptr[i];
+    void* b = plan->blob;
+    P.step_idx = at<int4>(b, o_step_idx);
+    P.step_dat = at<double>(b, o_step_dat);
+    P.chains = at<int2>(b, o_chains);
+    P.fix_idx = at<int2>(b, o_fix_idx);
+    P.fix_w = at<double>(b, o_fix_w);
+    P.geom = at<double>(b, o_geom);
+    P.bary = at<double>(b, o_bary);
+    P.ccell = at<double>(b, o_ccell);
+    P.low1 = at<int>(b, o_low1);
+    P.mul1 = at<double>(b, o_mul1);
+    P.low2 = at<int>(b, o_low2);
+    P.mul2 = at<double>(b, o_mul2);
+    P.line_tab = at<double>(b, o_line);
+    P.nrb = h->nrb; P.kpad = h->kpad; P.nblk = h->nblk;
+    P.blk_ptr = at<int>(b, o_blk_ptr);
+    P.blk_kb = at<int>(b, o_blk_kb);
+    P.blk_frag = at<double>(b, o_blk_frag);
+    P.rb_order = at<int>(b, o_rb_order);
+    *out = plan;
+    return FIATB200_OK;
+}
+
+int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nleaf, int32_t order,
+                                fiatb200_plan** out) {
+    if (!leaves || !out) return fail(FIATB200_ERR_ARG, "null argument");
+    if (nleaf < 1 || nleaf > FB_MAX_LEAVES)
+        return fail(FIATB200_ERR_UNSUPPORTED, "tensor-product elements with 1..4 scalar factors are supported");
+    fiatb200_plan* plan = new fiatb200_plan();
+    memset(static_cast<void*>(plan), 0, sizeof(*plan));
+    plan->kind = PLAN_TENSOR;
+    int rc = device_limits(plan);
+    if (rc) { delete plan; return rc; }
+    DevTensor& Q = plan->tensor;
+    Q.nleaf = nleaf;
+    Q.order = order;
+    Q.nrows = 1;
+    int scratch = 0, off = 0, sd_total = 0;
+    for (int l = 0; l < nleaf; ++l) {
+        const fiatb200_plan* lp = leaves[l].plan;
+        if (!lp || lp->kind != PLAN_SIMPLEX || lp->simplex.order != order) {
+            delete plan;
+            return fail(FIATB200_ERR_ARG, "tensor leaves must be simplex plans of the same derivative order");
+        }
+        Q.leaf[l].prog = lp->simplex;
+        Q.leaf[l].ent = make_entity(&leaves[l].entity, lp->simplex.sd);
+        Q.leaf[l].point_offset = leaves[l].point_offset;
+        scratch = std::max(scratch, lp->simplex.nslots * lp->simplex.na);
+        Q.nrows *= lp->simplex.nrows;
+        sd_total += lp->simplex.sd;
+    }
+    off = scratch;
+    for (int l = 0; l < nleaf; ++l) {
+        Q.leaf[l].table_off = off;
+        off += Q.leaf[l].prog.nrows * Q.leaf[l].prog.na;
+    }
+    Q.scratch_doubles = scratch;
+    Q.total_doubles = off;
+
+    // product multi-indices in mis order, split into per-leaf alpha indices
+    std::vector<std::vector<int>> alphas;
+    for (int k = 0; k <= order; ++k) {
+        // enumerate m-tuples summing to k, first entry descending (mis)
+        std::vector<int> cur(sd_total, 0);
+        struct Rec {
+            static void go(std::vector<std::vector<int>>& outv, std::vector<int>& cur, int pos, int left) {
+                const int m = (int)cur.size();
+                if (pos == m - 1) { cur[pos] = left; outv.push_back(cur); return; }
+                for (int v = left; v >= 0; --v) { cur[pos] = v; go(outv, cur, pos + 1, left - v); }
+            }
+        };
+        Rec::go(alphas, cur, 0, k);
+    }
+    Q.nalpha = (int)alphas.size();
+    auto leaf_alpha_index = [&](const int* a, int sd) {
+        // position of the sd-tuple a within mis(sd,0), mis(sd,1), ..., in mis order
+        int tot = 0;
+        for (int i = 0; i < sd; ++i) tot += a[i];
+        int idx = 0;
+        for (int k = 0; k < tot; ++k) idx += fb_binom(sd + k - 1, k);
+        // rank within mis(sd, tot): first entry descending
+        int left = tot;
+        for (int i = 0; i < sd - 1; ++i) {
+            for (int v = left; v > a[i]; --v) idx += fb_binom((sd - i - 1) + (left - v) - 1, left - v);
+            left -= a[i];
+        }
+        return idx;
+    };
+    std::vector<int> table((size_t)Q.nalpha * FB_MAX_LEAVES, 0);
+    for (int j = 0; j < Q.nalpha; ++j) {
+        int pos = 0;
+        for (int l = 0; l < nleaf; ++l) {
+            const int sd = Q.leaf[l].prog.sd;
+            table[(size_t)j * FB_MAX_LEAVES + l] = leaf_alpha_index(alphas[j].data() + pos, sd);
+            pos += sd;
+        }
+    }
+    cudaError_t e = cudaMalloc(&plan->blob, table.size() * sizeof(int) + 256);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->blob, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (plan->blob) cudaFree(plan->blob);
+        delete plan;
+        return fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+    }
+    Q.alpha_leaf = static_cast<const int*>(plan->blob);
+    *out = plan;
+    return FIATB200_OK;
+}
+
+int fiatb200_plan_destroy(fiatb200_plan* plan) {
+    if (!plan) return FIATB200_OK;
+    if (plan->blob) cudaFree(plan->blob);
+    delete plan;
+    return FIATB200_OK;
+}
+
+int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalpha) {
+    if (!plan) return fail(FIATB200_ERR_ARG, "null plan");
+    if (plan->kind == PLAN_SIMPLEX) {
+        if (nrows) *nrows = plan->simplex.nrows;
+        if (nalpha) *nalpha = plan->simplex.na;
+    } else {
+        if (nrows) *nrows = plan->tensor.nrows;
+        if (nalpha) *nalpha = plan->tensor.nalpha;
+    }
+    return FIATB200_OK;
+}
+
+int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,
+                      int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride, uint32_t flags,
+                      void* stream) {
+    if (!plan) return fail(FIATB200_ERR_ARG, "null plan");
+    if (npts < 0 || out_row_stride < npts) return fail(FIATB200_ERR_ARG, "bad point count / row stride");
+    if (npts == 0) return FIATB200_OK;
+    if (!out_dev || (!pts_dev && pts_ld != 0)) return fail(FIATB200_ERR_ARG, "null device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (plan->kind == PLAN_SIMPLEX)
+        return tabulate_simplex(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, flags, st);
+    return tabulate_tensor(plan, pts_dev, npts, pts_ld, out_dev, out_row_stride, st);
+}
+
+int fiatb200_locate_subcells(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,
+                             int64_t npts, int64_t pts_ld, int32_t unique, uint32_t* mask_out_dev, void* stream) {
+    if (!plan || plan->kind != PLAN_SIMPLEX) return fail(FIATB200_ERR_ARG, "a simplex plan is required");
+    if (npts == 0) return FIATB200_OK;
+    if (!mask_out_dev || (!pts_dev && pts_ld != 0)) return fail(FIATB200_ERR_ARG, "null device pointer");
+    const DevSimplex& P = plan->simplex;
+    const DevEntity E = make_entity(entity, P.sd);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((npts + 127) / 128);
+    switch (P.sd) {
+        case 1: k_locate<1><<<grid, 128, 0, st>>>(P, E, pts_dev, npts, pts_ld, unique, mask_out_dev); break;
+        case 2: k_locate<2><<<grid, 128, 0, st>>>(P, E, pts_dev, npts, pts_ld, unique, mask_out_dev); break;
+        default: k_locate<3><<<grid, 128, 0, st>>>(P, E, pts_dev, npts, pts_ld, unique, mask_out_dev); break;
+    }
+    g_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
+int fiatb200_tabulate_host(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_host,
+                           int64_t npts, int64_t pts_ld, double* out_host, int64_t chunk_pts, uint32_t flags) {
+    if (!plan) return fail(FIATB200_ERR_ARG, "null plan");
+    if (npts == 0) return FIATB200_OK;
+    if ((!pts_host && pts_ld != 0) || !out_host || chunk_pts <= 0)
+        return fail(FIATB200_ERR_ARG, "bad host buffers / chunk size");
+    int64_t nrows = 0, nalpha = 0;
+    fiatb200_plan_shape(plan, &nrows, &nalpha);
+    const int64_t rows = nrows * nalpha;
+    chunk_pts = std::min<int64_t>(chunk_pts, npts);
+    chunk_pts = (chunk_pts + 7) & ~int64_t(7);
+    cudaStream_t st[2];
+    double* d_pts[2] = {nullptr, nullptr};
+    double* d_out[2] = {nullptr, nullptr};
+    int rc = FIATB200_OK;
+    for (int i = 0; i < 2; ++i) {
+        FB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        FB_CUDA(cudaMalloc(&d_pts[i], sizeof(double) * chunk_pts * std::max<int64_t>(pts_ld, 1)));
+        FB_CUDA(cudaMalloc(&d_out[i], sizeof(double) * chunk_pts * rows));
+    }
+    int64_t done = 0;
+    for (int it = 0; done < npts && rc == FIATB200_OK; ++it, done += chunk_pts) {
+        const int b = it & 1;
+        const int64_t n = std::min<int64_t>(chunk_pts, npts - done);
+        if (pts_ld > 0)
+            FB_CUDA(cudaMemcpyAsync(d_pts[b], pts_host + done * pts_ld, sizeof(double) * n * pts_ld,
+                                    cudaMemcpyHostToDevice, st[b]));
+        rc = fiatb200_tabulate(plan, entity, d_pts[b], n, pts_ld, d_out[b], chunk_pts, flags, st[b]);
+        if (rc) break;
+        // rows of the chunk land at column offset `done` of the (rows x npts) host result
+        FB_CUDA(cudaMemcpy2DAsync(out_host + done, sizeof(double) * npts, d_out[b], sizeof(double) * chunk_pts,
+                                  sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st[b]));
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaStreamSynchronize(st[i]);
+        if (e != cudaSuccess && rc == FIATB200_OK) rc = fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
+        cudaFree(d_pts[i]);
+        cudaFree(d_out[i]);
+        cudaStreamDestroy(st[i]);
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// Tabulation kernels (sm_100a).
+//
+//   k_cellwise   thread per point: locate subcell(s) -> expansion in a private shared-memory column
+//                -> contraction with the per-subcell coefficient matrix.  Handles every simplex plan
+//                (split cells, 1-D sets, any order); the only path for split cells.
+//   k_mma        single-cell Dubiner elements: a CTA owns a tile of PT points, runs the recurrence
+//                chain-parallel into a shared expansion table T[member][alpha][point] and contracts
+//                it with the 8x4 block-sparse coefficient matrix on the FP64 tensor pipe
+//                (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), skipping all-zero blocks.
+//   k_tensor     scalar tensor-product elements: factor tables per point in shared memory, then the
+//                fused outer product streamed straight to global memory.
+//   k_locate     subcell bitmasks only.
+//
+// Output: out[(alpha * nrows + row) * ostride + point]; consecutive threads own consecutive points,
+// so every warp store covers 256 contiguous bytes of one row.
+#pragma once
+#include "expansion.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// thread-per-point kernel
+// ---------------------------------------------------------------------------------------------
+template <int SD, int ORDER>
+__global__ void __launch_bounds__(128)
+k_cellwise(const DevSimplex P, const DevEntity E, const double* __restrict__ pts, long long npts, long long ldp,
+           double* __restrict__ out, long long ostride) {
+    extern __shared__ double smem[];
+    const int BP = blockDim.x;
+    const int tid = threadIdx.x;
+    const long long p = (long long)blockIdx.x * BP + tid;
+    if (p >= npts) return;
+    const int na = (ORDER >= 0) ? Jet<SD, ORDER>::CAP : P.na;
+    double* T = smem + tid;
+    const int comp_stride = BP, slot_stride = na * BP;
+
+    double x[3];
+    apply_entity<SD>(E, pts + p * ldp, x);
+    unsigned mask = locate_cells<SD>(P.bary, P.ncells, P.unique, x);
+    const double inv_mult = 1.0 / (double)__popc(mask);
+    bool first = true;
+    while (mask) {
+        const int cell = __ffs(mask) - 1;
+        mask &= mask - 1;
+        expansion_point<SD, ORDER>(P, cell, inv_mult, x, T, slot_stride, comp_stride, na);
+        const double* C = P.ccell + (size_t)cell * P.nrows * P.nslots;
+        for (int r = 0; r < P.nrows; ++r) {
+            const double* Cr = C + (size_t)r * P.nslots;
+            if (ORDER >= 0) {
+                double acc[Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP];
+#pragma unroll
+                for (int a = 0; a < Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP; ++a) acc[a] = 0.0;
+                for (int k = 0; k < P.nslots; ++k) {
+                    const double c = __ldg(Cr + k);
+                    const double* t = T + (size_t)k * slot_stride;
+#pragma unroll
+                    for (int a = 0; a < Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP; ++a)
+                        acc[a] = fma(c, t[a * comp_stride], acc[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP; ++a) {
+                    double* o = out + ((size_t)a * P.nrows + r) * ostride + p;
+                    *o = first ? acc[a] : (*o + acc[a]);
+                }
+            } else {
+                for (int a = 0; a < na; ++a) {
+                    double acc = 0.0;
+                    for (int k = 0; k < P.nslots; ++k)
+                        acc = fma(__ldg(Cr + k), T[(size_t)k * slot_stride + a * comp_stride], acc);
+                    double* o = out + ((size_t)a * P.nrows + r) * ostride + p;
+                    *o = first ? acc : (*o + acc);
+                }
+            }
+        }
+        first = false;
+    }
+}
+
+template <int SD>
+__global__ void __launch_bounds__(128)
+k_locate(const DevSimplex P, const DevEntity E, const double* __restrict__ pts, long long npts, long long ldp,
+         int unique, unsigned* __restrict__ mask_out) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    double x[3];
+    apply_entity<SD>(E, pts + p * ldp, x);
+    mask_out[p] = locate_cells<SD>(P.bary, P.ncells, unique, x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile kernel with FP64 tensor-pipe contraction
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+struct MmaGeom {
+    int PT;        // points per tile (multiple of 8)
+    int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)
+    int S;         // column blocks (8 columns) per work item, <= FB_MMA_SMAX
+    int ngroups;   // work items per row block
+};
+#define FB_MMA_SMAX 8
+#define FB_MMA_THREADS 256
+
+template <int SD, int ORDER>
+__global__ void __launch_bounds__(FB_MMA_THREADS)
+k_mma(const DevSimplex P, const DevEntity E, const MmaGeom G, const double* __restrict__ pts, long long npts,
+      long long ldp, double* __restrict__ out, long long ostride) {
+    constexpr int NA = Jet<SD, ORDER>::NA;
+    extern __shared__ double smem[];
+    double* T = smem;                                   // kpad x ldT
+    double* s_fa = T + (size_t)P.kpad * G.ldT;          // 3 x PT
+    double* s_fb = s_fa + 3 * G.PT;                     // 3 x PT
+    __shared__ int s_next;
+    const int tid = threadIdx.x;
+    const int PT = G.PT;
+    const long long base = (long long)blockIdx.x * PT;
+
+    // phase 0: points of the tile -> recurrence factors; member 0; zero padding rows
+    if (tid == 0) s_next = 0;
+    if (tid < PT) {
+        long long p = base + tid;
+        if (p >= npts) p = npts - 1;                    // tail lanes repeat the last point, never stored
+        double x[3], xr[3] = {0.0, 0.0, 0.0};
+        apply_entity<SD>(E, pts + p * ldp, x);
+#pragma unroll
+        for (int i = 0; i < SD; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < SD; ++d) s = fma(x[d], __ldg(P.geom + i * SD + d), s);
+            xr[i] = s + __ldg(P.geom + 9 + i);
+        }
+        double fa[3], fb[3];
+        recurrence_factors<SD>(xr, fa, fb);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            s_fa[c * PT + tid] = fa[c];
+            s_fb[c * PT + tid] = fb[c];
+        }
+        const double start = __ldg(P.geom + 12);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) T[a * PT + tid] = (a == 0) ? start : 0.0;
+    }
+    for (int i = tid; i < (P.kpad - P.nslots) * G.ldT; i += FB_MMA_THREADS) T[(size_t)P.nslots * G.ldT + i] = 0.0;
+    __syncthreads();
+
+    // phase 1: recurrence, one (chain, point) pair per thread and pass
+    for (int pass = 0; pass < SD; ++pass) {
+        const int c0 = P.chain_ptr[pass];
+        const int items = (P.chain_ptr[pass + 1] - c0) * PT;
+        for (int it = tid; it < items; it += FB_MMA_THREADS) {
+            const int ch = c0 + it / PT, pl = it % PT;
+            const int2 c = __ldg(P.chains + ch);
+            const double fa[3] = {s_fa[pl], s_fa[PT + pl], s_fa[2 * PT + pl]};
+            const double fb[3] = {s_fb[pl], s_fb[PT + pl], s_fb[2 * PT + pl]};
+            run_chain<SD, ORDER>(P, P.step_dat, c.x, c.y, fa, fb, T + pl, G.ldT, PT, NA);
+        }
+        __syncthreads();
+    }
+    // C0 fix-ups: target -= w * source (targets are never sources)
+    if (P.nfix) {
+        const int items = P.nfix * NA * PT;
+        for (int it = tid; it < items; it += FB_MMA_THREADS) {
+            const int f = it / (NA * PT), col = it % (NA * PT);
+            const int2 ts = __ldg(P.fix_idx + f);
+            const double w = __ldg(P.fix_w + f);
+            // several fix-ups may share a target: serialise them per column
+            if (f > 0 && __ldg(P.fix_idx + f - 1).x == ts.x) continue;
+            double v = T[(size_t)ts.x * G.ldT + col];
+            for (int g = f; g < P.nfix; ++g) {
+                const int2 t2 = __ldg(P.fix_idx + g);
+                if (t2.x != ts.x) break;
+                v = fma(-__ldg(P.fix_w + g), T[(size_t)t2.y * G.ldT + col], v);
+            }
+            (void)w;
+            T[(size_t)ts.x * G.ldT + col] = v;
+        }
+        __syncthreads();
+    }
+
+    // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe
+    const int lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int ncb = NA * PT / 8;                         // column blocks of the tile
+    const int nitems = P.nrb * G.ngroups;
+    const bool vec_ok = ((ostride & 1) == 0) && ((base & 1) == 0) && ((((size_t)out) & 15) == 0);
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&s_next, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const int rb = __ldg(P.rb_order + item / G.ngroups);
+        const int cb0 = (item % G.ngroups) * G.S;
+        double acc[FB_MMA_SMAX][2];
+#pragma unroll
+        for (int s = 0; s < FB_MMA_SMAX; ++s) acc[s][0] = acc[s][1] = 0.0;
+        const int q0 = __ldg(P.blk_ptr + rb), q1 = __ldg(P.blk_ptr + rb + 1);
+        double a_next = (q0 < q1) ? __ldg(P.blk_frag + (size_t)q0 * 32 + lane) : 0.0;
+        int kb_next = (q0 < q1) ? __ldg(P.blk_kb + q0) : 0;
+        for (int q = q0; q < q1; ++q) {
+            const double a = a_next;
+            const int kb = kb_next;
+            if (q + 1 < q1) {
+                a_next = __ldg(P.blk_frag + (size_t)(q + 1) * 32 + lane);
+                kb_next = __ldg(P.blk_kb + q + 1);
+            }
+            const double* Tb = T + (size_t)(4 * kb + t) * G.ldT + 8 * cb0 + g;
+#pragma unroll
+            for (int s = 0; s < FB_MMA_SMAX; ++s) {
+                if (s < G.S && cb0 + s < ncb) {
+                    const double b = Tb[8 * s];
+                    dmma_8x8x4(acc[s][0], acc[s][1], a, b);
+                }
+            }
+        }
+        const int row = rb * 8 + g;
+        if (row < P.nrows) {
+#pragma unroll
+            for (int s = 0; s < FB_MMA_SMAX; ++s) {
+                if (s < G.S && cb0 + s < ncb) {
+                    const int col = 8 * (cb0 + s);
+                    const int a = col / PT, pl = col % PT + 2 * t;
+                    const long long p = base + pl;
+                    double* o = out + ((size_t)a * P.nrows + row) * ostride + p;
+                    if (vec_ok && p + 1 < npts) {
+                        *reinterpret_cast<double2*>(o) = make_double2(acc[s][0], acc[s][1]);
+                    } else {
+                        if (p < npts) o[0] = acc[s][0];
+                        if (p + 1 < npts) o[1] = acc[s][1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor-product kernel
+// ---------------------------------------------------------------------------------------------
+template <int SD>
+__device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double* __restrict__ pt, double* scratch,
+                                           double* table, int BP) {
+    const DevSimplex& P = L.prog;
+    double x[3];
+    apply_entity<SD>(L.ent, pt + L.point_offset, x);
+    const int na = P.na;
+    unsigned mask = locate_cells<SD>(P.bary, P.ncells, P.unique, x);
+    const double inv_mult = 1.0 / (double)__popc(mask);
+    bool first = true;
+    while (mask) {
+        const int cell = __ffs(mask) - 1;
+        mask &= mask - 1;
+        expansion_point<SD, -1>(P, cell, inv_mult, x, scratch, na * BP, BP, na);
+        const double* C = P.ccell + (size_t)cell * P.nrows * P.nslots;
+        for (int r = 0; r < P.nrows; ++r) {
+            for (int a = 0; a < na; ++a) {
+                double acc = 0.0;
+                for (int k = 0; k < P.nslots; ++k)
+                    acc = fma(__ldg(C + (size_t)r * P.nslots + k), scratch[((size_t)k * na + a) * BP], acc);
+                double* o = table + ((size_t)a * P.nrows + r) * BP;
+                *o = first ? acc : (*o + acc);
+            }
+        }
+        first = false;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_tensor(const DevTensor Q, const double* __restrict__ pts, long long npts, long long ldp,
+         double* __restrict__ out, long long ostride) {
+    extern __shared__ double smem[];
+    const int BP = blockDim.x;
+    const int tid = threadIdx.x;
+    const long long p = (long long)blockIdx.x * BP + tid;
+    if (p >= npts) return;
+    double* scratch = smem + tid;
+    const double* pt = pts + p * ldp;
+    for (int l = 0; l < Q.nleaf; ++l) {
+        const DevTensorLeaf& L = Q.leaf[l];
+        double* table = smem + (size_t)L.table_off * BP + tid;
+        if (L.prog.sd == 1) leaf_table<1>(L, pt, scratch, table, BP);
+        else if (L.prog.sd == 2) leaf_table<2>(L, pt, scratch, table, BP);
+        else leaf_table<3>(L, pt, scratch, table, BP);
+    }
+    int n[FB_MAX_LEAVES];
+    const double* tab[FB_MAX_LEAVES];
+#pragma unroll
+    for (int l = 0; l < FB_MAX_LEAVES; ++l) {
+        n[l] = l < Q.nleaf ? Q.leaf[l].prog.nrows : 1;
+        tab[l] = smem + (size_t)(l < Q.nleaf ? Q.leaf[l].table_off : 0) * BP + tid;
+    }
+    for (int al = 0; al < Q.nalpha; ++al) {
+        const int* aidx = Q.alpha_leaf + al * FB_MAX_LEAVES;
+        const double* t0 = tab[0] + (size_t)__ldg(aidx + 0) * n[0] * BP;
+        const double* t1 = tab[1] + (size_t)(Q.nleaf > 1 ? __ldg(aidx + 1) : 0) * n[1] * BP;
+        const double* t2 = tab[2] + (size_t)(Q.nleaf > 2 ? __ldg(aidx + 2) : 0) * n[2] * BP;
+        const double* t3 = tab[3] + (size_t)(Q.nleaf > 3 ? __ldg(aidx + 3) : 0) * n[3] * BP;
+        double* o = out + (size_t)al * Q.nrows * ostride + p;
+        for (int i0 = 0; i0 < n[0]; ++i0) {
+            const double f0 = t0[(size_t)i0 * BP];
+            for (int i1 = 0; i1 < n[1]; ++i1) {
+                const double f1 = Q.nleaf > 1 ? f0 * t1[(size_t)i1 * BP] : f0;
+                for (int i2 = 0; i2 < n[2]; ++i2) {
+                    const double f2 = Q.nleaf > 2 ? f1 * t2[(size_t)i2 * BP] : f1;
+                    if (Q.nleaf > 3) {
+                        for (int i3 = 0; i3 < n[3]; ++i3) {
+                            *o = f2 * t3[(size_t)i3 * BP];
+                            o += ostride;
+                        }
+                    } else {
+                        *o = f2;
+                        o += ostride;
+                    }
+                }
+            }
+        }
+    }
+}

@@ -1,0 +1,477 @@
+"""Compile an element description into the point-independent tables the CUDA kernels consume.
+
+Everything that does not depend on the evaluation point is worked out here, once per element:
+
+* the *recurrence program* of the Dubiner / integrated-Jacobi expansion
+  (`FIAT/expansions.py:202-249`): one record per three-term step with the Jacobi coefficients
+  (`jrc` / `integrated_jrc`, `:24-40`) and the point-independent parts of the recurrence-factor
+  derivatives (`jacobi_factors`, `:54-63,205`), grouped into chains that can run concurrently;
+* the per-pass normalisation (`:251-266`), accumulated per member and folded into the columns of
+  the coefficient matrix together with the C0 entity reordering (`:297-322`), so that the device
+  recurrence runs un-normalised and `PolynomialSet.tabulate`'s contraction
+  (`FIAT/polynomial_set.py:71`) absorbs both for free;
+* the C0 fix-ups (`:281-295`) as (target, source, weight) triples;
+* per-subcell coefficient matrices `coeffs[:, cell_node_map[c]]` (`:477-490`);
+* the 8x4 block-sparse packing of the coefficient matrix in `mma.m8n8k4.f64` fragment order;
+* 1-D tables: Legendre/Jacobi recurrence constants and running derivative scales
+  (`:659-678`, `FIAT/jacobi.py:47-74`), Lagrange nodes/weights/dmat
+  (`FIAT/barycentric_interpolation.py:22-59`);
+* for tensor-product elements the flattened list of leaf factors (`FIAT/tensor_product.py:231-292`).
+"""
+import math
+from dataclasses import dataclass, field
+
+import numpy
+
+__all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf"]
+
+EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
+STEP_DOUBLES = 16      # a, b, c, dF[3], g1[3], ddG[6], pad
+GEOM_DOUBLES = 16      # A[9], b[3], start value, pad
+
+
+def multi_indices(m, n):
+    """m-tuples summing to n, first entry descending (the order of FIAT's `mis`)."""
+    if m == 1:
+        return [(n,)]
+    out = []
+    for first in range(n, -1, -1):
+        out.extend((first,) + rest for rest in multi_indices(m - 1, n - first))
+    return out
+
+
+def alpha_list(sd, order):
+    """Dict-key order of a tabulation: mis(sd,0), mis(sd,1), ..., mis(sd,order)."""
+    out = []
+    for k in range(order + 1):
+        out.extend(multi_indices(sd, k))
+    return out
+
+
+def _morton(index, sd):
+    index = tuple(index) + (0,) * (sd - len(index))
+    if sd == 1:
+        return index[0]
+    if sd == 2:
+        p, q = index
+        return (p + q) * (p + q + 1) // 2 + q
+    p, q, r = index
+    s = p + q + r
+    return s * (s + 1) * (s + 2) // 6 + (q + r) * (q + r + 1) // 2 + r
+
+
+def _sub_indices(n, length):
+    """Index tuples of the given length with non-negative entries and sum < n."""
+    if length == 0:
+        return [()]
+    out = []
+    for last in range(n):
+        out.extend(head + (last,) for head in _sub_indices(n - last, length - 1))
+    return out
+
+
+def _jacobi_abc(a, b, i):
+    den = 2 * (i + 1) * (i + 1 + a + b)
+    an = (2 * i + 1 + a + b) * (2 * i + 2 + a + b) / den
+    bn = (a + b) * (a - b) * (2 * i + 1 + a + b) / (den * (2 * i + a + b))
+    cn = (i + a) * (i + b) * (2 * i + 2 + a + b) / ((i + 1) * (i + 1 + a + b) * (2 * i + a + b))
+    return an, bn, cn
+
+
+def _chain_coefficients(variant, sub, length):
+    """(a, b, c) for the `length` steps of the chain that extends sub-index `sub`."""
+    ssum = sum(sub)
+    beta = 1 if variant == "dual" else 0
+    if variant == "bubble":
+        alpha = 2 * ssum
+        first = (-0.5, -0.5, 0.0)
+    else:
+        alpha = 2 * ssum + len(sub)
+        if variant == "dual":
+            alpha += 1 + len(sub)
+        first = (0.5 * (alpha + beta) + 1.0, 0.5 * (alpha - beta), 0.0)
+    out = [first]
+    for i in range(1, length):
+        if variant == "bubble":
+            if i == 1:
+                out.append(((alpha + beta + 2) / 2, (alpha - 3 * beta - 2) / 2, 0.0))
+            else:
+                out.append(_jacobi_abc(alpha - 1, beta + 1, i - 1))
+        else:
+            out.append(_jacobi_abc(alpha, beta, i))
+    return out
+
+
+def _normalisation(sd, n, variant):
+    """Accumulated normalisation factor of every Morton-numbered member.
+
+    Pass d rescales every member whose index has length d (trailing zeros implied); members
+    created later by a chain inherit what their chain start had accumulated by then, because the
+    recurrence is linear in its start value.
+    """
+    total = numpy.ones(math.comb(n + sd, sd))
+    shift = 1 if variant == "dual" else 0
+    for d in range(1, sd + 1):
+        before = total.copy()
+        for index in _sub_indices(n + 1, d):
+            if variant == "none":
+                norm2 = (2 * sum(index) + d) / d
+            else:
+                p = index[-1] + shift
+                al = 2 * (sum(index[:-1]) + d * shift) - 1
+                norm2 = (0.5 + d) / d
+                if p > 0 and p + al > 0:
+                    norm2 *= (p + al) * (2 * p + al) / p
+            start = _morton(index[:-1], sd)
+            total[_morton(index, sd)] = before[start] * math.sqrt(norm2)
+    return total
+
+
+def _c0_layout(sd, n):
+    """(entity_order, fixups): gather list Morton -> entity order, and the in-place corrections
+    [(target, source)] applied to the normalised hierarchical functions."""
+    ix = lambda *idx: _morton(idx, sd)  # noqa: E731
+    rng = range(2, n + 1)
+    order = list(range(sd + 1))
+    fix = []
+    if sd == 1:
+        order += list(rng)
+    elif sd == 2:
+        order += [ix(1, i - 1) for i in rng] + [ix(0, i) for i in rng] + [ix(i, 0) for i in rng]
+        order += [ix(i, j) for j in range(1, n + 1) for i in range(2, n - j + 1)]
+        fix += [(ix(0, i), ix(1, i - 1)) for i in rng]
+    else:
+        order += [ix(0, 1, i - 1) for i in rng] + [ix(1, 0, i - 1) for i in rng]
+        order += [ix(1, i - 1, 0) for i in rng] + [ix(0, 0, i) for i in rng]
+        order += [ix(0, i, 0) for i in rng] + [ix(i, 0, 0) for i in rng]
+        inner = [(i, j) for j in range(1, n + 1) for i in range(2, n - j + 1)]
+        order += [ix(1, i - 1, j) for i, j in inner] + [ix(0, i, j) for i, j in inner]
+        order += [ix(i, 0, j) for i, j in inner] + [ix(i, j, 0) for i, j in inner]
+        order += [ix(i, j, k) for k in range(1, n + 1) for j in range(1, n - k + 1)
+                  for i in range(2, n - j - k + 1)]
+        for i in rng:
+            fix += [(ix(0, i, j), ix(1, i - 1, j)) for j in range(0, n + 1 - i)]
+            fix += [(ix(0, 0, i), ix(0, 1, i - 1)), (ix(0, 0, i), ix(1, 0, i - 1))]
+    return order, fix
+
+
+def leibniz_tables(sd, order):
+    """Index tables for D^alpha(F G) with F at most quadratic (`_product_derivative`, :66-137).
+
+    low1[j, d]  = index of alpha_j - e_d (or -1), mul1[j, d] = alpha_d
+    low2[j, k]  = index of alpha_j - e_d1 - e_d2 for the k-th pair d1<=d2 (or -1), mul2[j, k]
+    """
+    alphas = alpha_list(sd, order)
+    pos = {a: j for j, a in enumerate(alphas)}
+    pairs = [(d1, d2) for d1 in range(sd) for d2 in range(d1, sd)]
+    low1 = -numpy.ones((len(alphas), 3), dtype=numpy.int32)
+    mul1 = numpy.zeros((len(alphas), 3))
+    low2 = -numpy.ones((len(alphas), 6), dtype=numpy.int32)
+    mul2 = numpy.zeros((len(alphas), 6))
+    for j, al in enumerate(alphas):
+        for d in range(sd):
+            if al[d] >= 1:
+                lo = al[:d] + (al[d] - 1,) + al[d + 1:]
+                low1[j, d], mul1[j, d] = pos[lo], al[d]
+        for k, (d1, d2) in enumerate(pairs):
+            need = 2 if d1 == d2 else 1
+            if al[d1] >= need and al[d2] >= need:
+                lo = list(al)
+                lo[d1] -= 1
+                lo[d2] -= 1
+                low2[j, k] = pos[tuple(lo)]
+                mul2[j, k] = al[d1] * (al[d1] - 1) // 2 if d1 == d2 else al[d1] * al[d2]
+    return low1, mul1, low2, mul2
+
+
+@dataclass
+class SimplexProgram:
+    """Host-side tables for one Ciarlet element and one derivative order."""
+    sd: int
+    degree: int
+    order: int
+    na: int
+    expansion: int
+    ncells: int
+    nslots: int                 # expansion members per (sub)cell
+    nrows: int                  # ndofs * prod(value_shape)
+    ndofs: int
+    value_shape: tuple
+    unique: int                 # first-match binning (continuity is not None and order == 0)
+    geom: numpy.ndarray         # (ncells, GEOM_DOUBLES)
+    bary: numpy.ndarray         # (ncells + 1, 4, 4): rows of A_hat | b_hat
+    step_idx: numpy.ndarray     # (nsteps, 4) int32: next, cur, prev(-1 = first of chain), codim
+    step_dat: numpy.ndarray     # (ncells, nsteps, STEP_DOUBLES)
+    chain_ptr: numpy.ndarray    # (sd + 1,) int32 offsets into chains per codim pass
+    chains: numpy.ndarray       # (nchains, 2) int32: first step, number of steps
+    fix_idx: numpy.ndarray      # (nfix, 2) int32 target, source slots
+    fix_w: numpy.ndarray        # (nfix,)
+    ccell: numpy.ndarray        # (ncells, nrows, nslots) folded coefficients
+    low1: numpy.ndarray
+    mul1: numpy.ndarray
+    low2: numpy.ndarray
+    mul2: numpy.ndarray
+    line_tab: numpy.ndarray     # expansion-specific 1-D tables (see _line_tables)
+    line_n: int = 0
+    # block-sparse packing of ccell[0] (single-cell elements only)
+    blk_ptr: numpy.ndarray = field(default_factory=lambda: numpy.zeros(1, numpy.int32))
+    blk_kb: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))
+    blk_frag: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0))
+    rb_order: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))
+    kpad: int = 0
+
+
+def _dubiner_tables(desc, order):
+    sd, n, variant = int(desc["sd"]), int(desc["degree"]), desc["variant"]
+    ncells = int(desc["ncells"])
+    c0 = bool(desc["c0"])
+    nmem = math.comb(n + sd, sd)
+    if c0:
+        entity_order, fix_pairs = _c0_layout(sd, n)
+    else:
+        entity_order, fix_pairs = list(range(nmem)), []
+    slot_of = numpy.empty(nmem, dtype=numpy.int64)       # Morton member -> slot (output position)
+    slot_of[entity_order] = numpy.arange(nmem)
+
+    # chains and steps, pass by pass
+    step_idx, step_abc, chains, chain_ptr = [], [], [], [0]
+    if n > 0:
+        for codim in range(sd):
+            for sub in _sub_indices(n, codim):
+                length = n - sum(sub)
+                abc = _chain_coefficients(variant, sub, length)
+                first = len(step_idx)
+                for i in range(length):
+                    cur = slot_of[_morton(sub + (i,), sd)]
+                    nxt = slot_of[_morton(sub + (i + 1,), sd)]
+                    prv = slot_of[_morton(sub + (i - 1,), sd)] if i > 0 else -1
+                    step_idx.append((nxt, cur, prv, codim))
+                    step_abc.append(abc[i])
+                chains.append((first, length))
+            chain_ptr.append(len(chains))
+    else:
+        chain_ptr += [0] * sd
+    step_idx = numpy.array(step_idx, dtype=numpy.int32).reshape(-1, 4)
+    nsteps = len(step_idx)
+
+    # per-cell step data: point-independent pieces of F, dF, G, dG, ddG
+    step_dat = numpy.zeros((ncells, nsteps, STEP_DOUBLES))
+    geom = numpy.zeros((ncells, GEOM_DOUBLES))
+    for c in range(ncells):
+        A = numpy.asarray(desc["cell_A"][c], dtype=float)
+        geom[c, :sd * sd] = A.reshape(-1)
+        geom[c, 9:9 + sd] = desc["cell_b"][c]
+        scale = float(desc["cell_scale"][c])
+        geom[c, 12] = -scale if variant == "bubble" else scale
+        dX = [A[i] for i in range(sd)] + [numpy.zeros(sd), numpy.zeros(sd)]
+        for s in range(nsteps):
+            codim = step_idx[s, 3]
+            a, b, cc = step_abc[s]
+            dfb = 0.5 * (dX[codim + 1] + dX[codim + 2])
+            dfa = dX[codim] + dfb
+            rec = step_dat[c, s]
+            rec[0:3] = (a, b, cc)
+            rec[3:3 + sd] = a * dfa - b * dfb
+            rec[6:6 + sd] = -cc * (2 * dfb)
+            k = 0
+            for d1 in range(sd):
+                for d2 in range(d1, sd):
+                    rec[9 + k] = -cc * (2 * dfb[d1] * dfb[d2])
+                    k += 1
+
+    # fold normalisation / sign / reordering into the coefficient columns
+    norm = _normalisation(sd, n, variant) if n > 0 else numpy.ones(nmem)
+    fold = norm.copy()
+    fix_idx, fix_w = [], []
+    if c0:
+        fold[0] = -norm[0]
+        for m in range(1, sd + 1):
+            fix_idx.append((slot_of[0], slot_of[m]))
+            fix_w.append(-norm[m] / norm[0])
+        for t, s in fix_pairs:
+            fix_idx.append((slot_of[t], slot_of[s]))
+            fix_w.append(norm[s] / norm[t])
+    fold_by_slot = numpy.empty(nmem)
+    fold_by_slot[slot_of] = fold
+    return dict(nslots=nmem, step_idx=step_idx, step_dat=step_dat, geom=geom,
+                chains=numpy.array(chains, dtype=numpy.int32).reshape(-1, 2),
+                chain_ptr=numpy.array(chain_ptr, dtype=numpy.int32),
+                fix_idx=numpy.array(fix_idx, dtype=numpy.int32).reshape(-1, 2),
+                fix_w=numpy.array(fix_w, dtype=float), fold_by_slot=fold_by_slot)
+
+
+def _line_tables(desc, order):
+    """1-D sets that do not use the simplex recurrence."""
+    n = int(desc["degree"])
+    ncells = int(desc["ncells"])
+    geom = numpy.zeros((ncells, GEOM_DOUBLES))
+    if desc["expansion"] == "legendre_line":
+        # per order k: Jacobi(k,k) recurrence constants; per cell running scales (expansions.py:669-676)
+        rec = numpy.zeros((order + 1, n + 1, 4))
+        for k in range(order + 1):
+            a = b = float(k)
+            apb = a + b
+            rec[k, 1, 0] = 0.5 * (a - b)
+            rec[k, 1, 1] = 0.5 * (a + b + 2.0)
+            for j in range(2, n + 1):
+                a1 = 2.0 * j * (j + apb) * (2.0 * j + apb - 2.0)
+                a2 = (2.0 * j + apb - 1.0) * (a * a - b * b)
+                a3 = (2.0 * j + apb - 2.0) * (2.0 * j + apb - 1.0) * (2.0 * j + apb)
+                a4 = 2.0 * (j + a - 1.0) * (j + b - 1.0) * (2.0 * j + apb)
+                rec[k, j, :3] = (a2 / a1, a3 / a1, a4 / a1)
+        scales = numpy.zeros((ncells, order + 1, n + 1))
+        for c in range(ncells):
+            A = numpy.asarray(desc["cell_A"][c], dtype=float)
+            geom[c, 0] = A[0, 0]
+            geom[c, 9] = desc["cell_b"][c][0]
+            run = float(desc["cell_scale"][c]) * numpy.sqrt(2 * numpy.arange(n + 1) + 1)
+            for k in range(order + 1):
+                scales[c, k] = run
+                run = run * (0.5 * (numpy.arange(n + 1) + k + 1) * A[0, 0])
+        tab = numpy.concatenate([rec.reshape(-1), scales.reshape(-1)])
+        return dict(nslots=n + 1, geom=geom, line_tab=tab, line_n=n)
+    nodes, wts, dmat = desc["ll_nodes"], desc["ll_wts"], desc["ll_dmat"]
+    nn = nodes.shape[1]
+    tab = numpy.concatenate([numpy.concatenate([nodes[c], wts[c], dmat[c].reshape(-1)]) for c in range(ncells)])
+    return dict(nslots=nn, geom=geom, line_tab=tab, line_n=nn)
+
+
+def pack_blocks(C, drop_tol=0.0):
+    """8x4 block-sparse packing of a (nrows, K) matrix in mma.m8n8k4 A-fragment order.
+
+    Lane l of a warp holds C[8*rb + l//4, 4*kb + l%4].  Returns (blk_ptr, blk_kb, frags, rb_order, Kpad);
+    rb_order lists row blocks by decreasing number of stored blocks (longest first scheduling).
+    """
+    nrows, K = C.shape
+    nrb, nkb = -(-nrows // 8), -(-K // 4)
+    Cp = numpy.zeros((nrb * 8, nkb * 4))
+    Cp[:nrows, :K] = C
+    tiles = Cp.reshape(nrb, 8, nkb, 4).transpose(0, 2, 1, 3)        # (rb, kb, 8, 4)
+    keep = numpy.abs(tiles).max(axis=(2, 3)) > drop_tol
+    blk_ptr = numpy.zeros(nrb + 1, dtype=numpy.int32)
+    blk_kb, frags = [], []
+    for rb in range(nrb):
+        kbs = numpy.nonzero(keep[rb])[0]
+        blk_kb.extend(kbs.tolist())
+        frags.extend(tiles[rb, kb].reshape(32) for kb in kbs)
+        blk_ptr[rb + 1] = len(blk_kb)
+    counts = numpy.diff(blk_ptr)
+    rb_order = numpy.argsort(-counts, kind="stable").astype(numpy.int32)
+    frags = numpy.array(frags, dtype=float).reshape(-1) if frags else numpy.zeros(0)
+    return blk_ptr, numpy.array(blk_kb, dtype=numpy.int32), frags, rb_order, nkb * 4
+
+
+def compile_simplex(desc, order):
+    """Build the SimplexProgram of a `kind == "simplex"` description for one derivative order."""
+    sd, n = int(desc["sd"]), int(desc["degree"])
+    ncells = int(desc["ncells"])
+    coeffs = numpy.asarray(desc["coeffs"], dtype=float)
+    ndofs, ncomp, nexp_total = coeffs.shape
+    nrows = ndofs * ncomp
+    C = coeffs.reshape(nrows, nexp_total)
+    cnm = numpy.asarray(desc["cell_node_map"], dtype=numpy.int64)
+    na = len(alpha_list(sd, order))
+    low1, mul1, low2, mul2 = leibniz_tables(sd, order)
+
+    if desc["expansion"] == "dubiner":
+        t = _dubiner_tables(desc, order)
+        fold = t["fold_by_slot"]
+        line_tab, line_n = numpy.zeros(0), 0
+    else:
+        t = _line_tables(desc, order)
+        fold = numpy.ones(t["nslots"])
+        line_tab, line_n = t["line_tab"], t["line_n"]
+        t.update(step_idx=numpy.zeros((0, 4), numpy.int32), step_dat=numpy.zeros((ncells, 0, STEP_DOUBLES)),
+                 chains=numpy.zeros((0, 2), numpy.int32), chain_ptr=numpy.zeros(sd + 1, numpy.int32),
+                 fix_idx=numpy.zeros((0, 2), numpy.int32), fix_w=numpy.zeros(0))
+    nslots = t["nslots"]
+    if cnm.shape[1] != nslots:
+        raise ValueError("cell -> member map does not match the expansion set")
+    ccell = numpy.empty((ncells, nrows, nslots))
+    for c in range(ncells):
+        ccell[c] = C[:, cnm[c]] * fold[None, :]
+
+    bary = numpy.zeros((ncells + 1, 4, 4))
+    if ncells > 1:
+        bary[:, :sd + 1, :sd] = desc["bary_A"]
+        bary[:, :sd + 1, 3] = desc["bary_b"]
+
+    prog = SimplexProgram(
+        sd=sd, degree=n, order=order, na=na, expansion=EXPANSION_CODES[desc["expansion"]],
+        ncells=ncells, nslots=nslots, nrows=nrows, ndofs=ndofs,
+        value_shape=tuple(int(s) for s in desc["value_shape"]),
+        unique=int(bool(desc["c0"]) and order == 0),
+        geom=t["geom"], bary=bary, step_idx=t["step_idx"], step_dat=t["step_dat"],
+        chain_ptr=t["chain_ptr"], chains=t["chains"], fix_idx=t["fix_idx"], fix_w=t["fix_w"],
+        ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
+    if ncells == 1:
+        scale = numpy.abs(ccell[0]).max() if ccell.size else 0.0
+        (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = pack_blocks(ccell[0], 1e-14 * scale)
+    return prog
+
+
+@dataclass
+class TensorLeaf:
+    desc: dict                  # simplex description of the factor
+    entity: tuple               # (dim, id) on the factor's own cell
+    point_offset: int           # first coordinate of the product point that belongs to this factor
+    point_dim: int              # number of coordinates consumed (dimension of the entity)
+    sd: int                     # spatial dimension of the factor cell (length of its alpha slice)
+
+
+def _cell_dim(desc):
+    if desc["kind"] == "simplex":
+        return int(desc["sd"])
+    if desc["kind"] == "flattened":
+        return _cell_dim(desc["element"])
+    return _cell_dim(desc["A"]) + _cell_dim(desc["B"])
+
+
+def _flat(key):
+    return sum(key) if isinstance(key, (list, tuple)) else int(key)
+
+
+def _count(top, key):
+    key = list(key) if isinstance(key, (list, tuple)) else int(key)
+    for k, cnt in top:
+        if k == key:
+            return cnt
+    raise KeyError(f"no entities of dimension {key}")
+
+
+def flatten_tensor(desc, entity=None, point_offset=0):
+    """Resolve a tensor-product / flattened element tree into its leaf factors for one entity.
+
+    Mirrors the entity factorisation of TensorProductElement.tabulate (tensor_product.py:238-250)
+    and FlattenedDimensions.tabulate (:399-407).  Leaves come out in dof-major order: the global
+    dof index is ((i0 * n1) + i1) * n2 + ..., and the alpha of the product is the concatenation of
+    the leaves' alphas.
+    """
+    kind = desc["kind"]
+    if kind == "simplex":
+        sd = int(desc["sd"])
+        if entity is None:
+            entity = (sd, 0)
+        return [TensorLeaf(desc, (int(entity[0]), int(entity[1])), point_offset, int(entity[0]), sd)]
+    if kind == "flattened":
+        if entity is None:
+            entity = (_cell_dim(desc), 0)
+        for fdim, fent, pdim, pent in desc["unflatten"]:
+            if fdim == entity[0] and fent == entity[1]:
+                pdim = tuple(pdim) if isinstance(pdim, list) else pdim
+                return flatten_tensor(desc["element"], (pdim, pent), point_offset)
+        raise KeyError(f"no entity {entity} on the flattened cell")
+    if kind != "tensor":
+        raise ValueError(kind)
+    if entity is None:
+        entity = ((_cell_dim(desc["A"]), _cell_dim(desc["B"])), 0)
+    (dA, dB), eid = entity
+    shape = (_count(desc["topA"], dA), _count(desc["topB"], dB))
+    if not 0 <= eid < shape[0] * shape[1]:
+        raise KeyError(f"no entity {entity} on the product cell")
+    idA, idB = divmod(int(eid), shape[1])
+    dA = tuple(dA) if isinstance(dA, (list, tuple)) else dA
+    dB = tuple(dB) if isinstance(dB, (list, tuple)) else dB
+    left = flatten_tensor(desc["A"], (dA, idA), point_offset)
+    right = flatten_tensor(desc["B"], (dB, idB), point_offset + _flat(dA))
+    return left + right

@@ -1,0 +1,141 @@
+/* fiat_b200 -- C ABI of the B200-native basis-tabulation path.
+ *
+ * This is the drop-in boundary for the reference's `FiniteElement.tabulate(order, points, entity)`
+ * (FIAT/finite_element.py:98-109,181-197).  The reference has no FFI of its own (it is pure
+ * Python + numpy); a maintainer binds these entry points with ctypes, as INTEGRATION.md shows and
+ * as fiat_b200/_lib.py does.  Plain pointers and sizes only; every function returns 0 on success
+ * and a non-zero code otherwise (fiatb200_last_error() gives the text); nothing throws across the
+ * boundary.  All device pointers refer to the CUDA device that was current when the plan was
+ * created; `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ * asynchronous with respect to the host unless stated otherwise.
+ *
+ * Output layout (all kernels): out[(alpha_index * nrows + row) * out_row_stride + point], float64,
+ * alpha_index running over mis(sd,0), mis(sd,1), ..., mis(sd,order) (FIAT/polynomial_set.py:23-32,
+ * FIAT/expansions.py:427-432) and row = dof * prod(value_shape) + component, i.e. exactly the
+ * C-ordered `(ndofs, *value_shape, npoints)` arrays of the reference's result dict, one after the
+ * other, when out_row_stride == npoints.
+ */
+#ifndef FIAT_B200_H
+#define FIAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIATB200_OK 0
+#define FIATB200_ERR_CUDA 1
+#define FIATB200_ERR_ARG 2
+#define FIATB200_ERR_UNSUPPORTED 3
+
+typedef struct fiatb200_plan fiatb200_plan;
+
+/* Point-independent tables of one Ciarlet element on a (possibly split) simplex and one derivative
+ * order; built on the host by fiat_b200/plan.py from the reference-constructed element.  Replaces the
+ * per-call Python set-up of ExpansionSet._tabulate_on_cell / dubiner_recurrence
+ * (FIAT/expansions.py:140-267,411-447), C0_basis (:270-322), the macro scatter (:449-490) and the
+ * coefficient tensor of PolynomialSet.tabulate (FIAT/polynomial_set.py:68-72).  All pointers are HOST
+ * pointers; the tables are copied to the device by fiatb200_simplex_plan_create. */
+typedef struct {
+    int32_t sd;            /* spatial dimension 1..3 */
+    int32_t degree;        /* embedded degree n */
+    int32_t order;         /* maximum derivative order */
+    int32_t na;            /* number of derivative multi-indices C(sd+order, order) */
+    int32_t expansion;     /* 0 Dubiner recurrence, 1 Legendre line (jacobi.py:47-74), 2 Lagrange line
+                              (barycentric_interpolation.py:22-47) */
+    int32_t ncells;        /* subcells of the split complex (1 = plain simplex), <= 32 */
+    int32_t nslots;        /* expansion members per subcell */
+    int32_t nrows;         /* ndofs * prod(value_shape) */
+    int32_t unique;        /* 1: first matching subcell wins (expansions.py:452,805-807) */
+    int32_t nsteps, nchains, nfix, line_n;
+    int32_t chain_ptr[4];  /* chains of recurrence pass d are chains[chain_ptr[d] .. chain_ptr[d+1]) */
+    const int32_t* step_idx;   /* nsteps x 4: next, cur, prev (-1 first of chain), codim */
+    const double* step_dat;    /* ncells x nsteps x 16: a,b,c | dF[3] | -2c*dfb[3] | -2c*dfb(x)dfb[6] */
+    const int32_t* chains;     /* nchains x 2: first step, number of steps */
+    const int32_t* fix_idx;    /* nfix x 2: target, source slot (C0_basis fix-ups) */
+    const double* fix_w;       /* nfix */
+    const double* geom;        /* ncells x 16: A[9] (row-major sd x sd), b[3] at 9, start value at 12 */
+    const double* bary;        /* (ncells+1) x 4 x 4: rescaled barycentric rows A_hat | b_hat, parent last
+                                  (reference_element.py:616-644) */
+    const double* ccell;       /* ncells x nrows x nslots folded coefficients coeffs[:, cell_node_map[c]] */
+    const int32_t* low1;       /* na x 3, Leibniz index tables (expansions.py:66-137) */
+    const double* mul1;        /* na x 3 */
+    const int32_t* low2;       /* na x 6 */
+    const double* mul2;        /* na x 6 */
+    const double* line_tab;    /* expansion 1/2 tables */
+    int64_t line_tab_len;
+    /* 8x4 block-sparse packing of ccell[0] in mma.m8n8k4 fragment order (ncells == 1 only) */
+    int32_t nrb, kpad, nblk;
+    const int32_t* blk_ptr;    /* nrb + 1 */
+    const int32_t* blk_kb;     /* nblk */
+    const double* blk_frag;    /* nblk x 32 */
+    const int32_t* rb_order;   /* nrb, longest row block first */
+} fiatb200_simplex_program;
+
+/* Entity transform x_cell = x_entity * C + offset (FIAT/reference_element.py:570-609);
+ * identity != 0 skips it (default cell entity, :585-587). */
+typedef struct {
+    int32_t dim;           /* number of coordinates per input point */
+    int32_t identity;
+    double C[9];           /* dim x sd, row-major */
+    double offset[3];
+} fiatb200_entity_map;
+
+/* One leaf factor of a (flattened) tensor-product element: a simplex plan evaluated on a slice of the
+ * product point (FIAT/tensor_product.py:238-258). */
+typedef struct {
+    const fiatb200_plan* plan;     /* simplex plan of the factor, same order as the product */
+    fiatb200_entity_map entity;    /* factor entity transform */
+    int32_t point_offset;          /* first coordinate of the product point used by this factor */
+} fiatb200_tensor_leaf;
+
+int fiatb200_version(void);
+const char* fiatb200_last_error(void);
+
+/* Upload the tables to the current device.  Replaces nothing in the reference (it re-derives them on
+ * every call); corresponds to the per-element caches of FIAT/expansions.py:377-378. */
+int fiatb200_simplex_plan_create(const fiatb200_simplex_program* prog, fiatb200_plan** plan);
+
+/* Scalar x scalar tensor-product plan over nleaf <= 4 factor plans
+ * (TensorProductElement.tabulate / FlattenedDimensions.tabulate, FIAT/tensor_product.py:231-292,396-407).
+ * The factor plans must outlive the tensor plan. */
+int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nleaf, int32_t order,
+                                fiatb200_plan** plan);
+
+int fiatb200_plan_destroy(fiatb200_plan* plan);
+
+/* Number of result rows per derivative multi-index, and number of multi-indices. */
+int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalpha);
+
+/* Tabulate at npts device-resident points (row-major, leading dimension pts_ld doubles).
+ * = CiarletElement.tabulate (FIAT/finite_element.py:181-197) / TensorProductElement.tabulate.
+ * `entity` may be NULL for tensor plans (their leaves carry the factor entities).
+ * flags: bit 0 forces the thread-per-point kernel, bit 1 forces the block-sparse DMMA kernel
+ *        (testing / profiling); 0 lets the library choose. */
+int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* entity,
+                      const double* pts_dev, int64_t npts, int64_t pts_ld,
+                      double* out_dev, int64_t out_row_stride, uint32_t flags, void* stream);
+
+/* Split-cell point location only: bitmask of the subcells each point is binned to
+ * (= compute_cell_point_map, FIAT/expansions.py:771-811).  The object the parity tests compare
+ * bit-for-bit with the reference. */
+int fiatb200_locate_subcells(const fiatb200_plan* plan, const fiatb200_entity_map* entity,
+                             const double* pts_dev, int64_t npts, int64_t pts_ld, int32_t unique,
+                             uint32_t* mask_out_dev, void* stream);
+
+/* End-to-end call with HOST buffers (what a numpy caller of the reference holds): points are staged
+ * to the device, tabulated in chunks of at most chunk_pts points and copied back, with copies and
+ * kernels overlapped on two internal streams.  out_host has the layout above with
+ * out_row_stride == npts.  Synchronous. */
+int fiatb200_tabulate_host(const fiatb200_plan* plan, const fiatb200_entity_map* entity,
+                           const double* pts_host, int64_t npts, int64_t pts_ld,
+                           double* out_host, int64_t chunk_pts, uint32_t flags);
+
+/* Number of kernel launches issued by this library in the calling process so far. */
+int64_t fiatb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIAT_B200_H */

@@ -1,0 +1,78 @@
+"""Test helper: interpret a compiled SimplexProgram with numpy, step by step, the way the CUDA
+kernel does (un-normalised recurrence, fix-ups, folded per-cell coefficient matrices).  It lets the
+CPU test-suite check the host-side plan compiler without a GPU.  Not a product path."""
+import numpy
+
+from fiat_b200.plan import alpha_list
+
+
+def _jets(prog, cell, x):
+    """Run the Dubiner program of one cell at default-simplex coordinates x (sd, npts)."""
+    sd, na = prog.sd, prog.na
+    npts = x.shape[1]
+    T = numpy.zeros((prog.nslots, na, npts))
+    T[0, 0] = prog.geom[cell, 12]
+    X = [x[i] for i in range(sd)] + [-numpy.ones(npts), -numpy.ones(npts)]
+    pairs = [(d1, d2) for d1 in range(sd) for d2 in range(d1, sd)]
+    for s, (nxt, cur, prv, codim) in enumerate(prog.step_idx):
+        rec = prog.step_dat[cell, s]
+        a, b, c = rec[0:3]
+        fb = 0.5 * (X[codim + 1] + X[codim + 2])
+        fa = X[codim] + (fb + 1.0)
+        F = a * fa - b * fb
+        dF = rec[3:3 + sd]
+        G = -c * (fb * fb)
+        dG = [fb * rec[6 + d] for d in range(sd)]
+        ddG = rec[9:9 + len(pairs)]
+        for j in range(na):
+            v = F * T[cur, j]
+            for d in range(sd):
+                if prog.low1[j, d] >= 0:
+                    v = v + prog.mul1[j, d] * dF[d] * T[cur, prog.low1[j, d]]
+            if prv >= 0:
+                v = v + G * T[prv, j]
+                for d in range(sd):
+                    if prog.low1[j, d] >= 0:
+                        v = v + prog.mul1[j, d] * dG[d] * T[prv, prog.low1[j, d]]
+                for k in range(len(pairs)):
+                    if prog.low2[j, k] >= 0:
+                        v = v + prog.mul2[j, k] * ddG[k] * T[prv, prog.low2[j, k]]
+            T[nxt, j] = v
+    for (t, s), w in zip(prog.fix_idx, prog.fix_w):
+        T[t] -= w * T[s]
+    return T
+
+
+def run_simplex(prog, pts, near):
+    """out[alpha_index, row, point] for already-transformed points and a membership matrix."""
+    assert prog.expansion == 0
+    sd = prog.sd
+    npts = len(pts)
+    out = numpy.zeros((prog.na, prog.nrows, npts))
+    mult = near.sum(axis=0)
+    for c in range(prog.ncells):
+        ip = numpy.where(near[c])[0]
+        if len(ip) == 0:
+            continue
+        A = prog.geom[c, :sd * sd].reshape(sd, sd)
+        b = prog.geom[c, 9:9 + sd]
+        x = (pts[ip] @ A.T + b).T
+        T = _jets(prog, c, x)
+        vals = numpy.einsum("rk,kap->arp", prog.ccell[c], T)
+        out[:, :, ip] += vals / (1.0 if prog.unique else mult[None, None, ip])
+    return out
+
+
+def blocks_to_dense(prog):
+    """Rebuild the dense folded coefficient matrix from the 8x4 block packing."""
+    nrb = len(prog.blk_ptr) - 1
+    C = numpy.zeros((nrb * 8, prog.kpad))
+    for rb in range(nrb):
+        for q in range(prog.blk_ptr[rb], prog.blk_ptr[rb + 1]):
+            kb = prog.blk_kb[q]
+            C[rb * 8:rb * 8 + 8, kb * 4:kb * 4 + 4] = prog.blk_frag[q * 32:(q + 1) * 32].reshape(8, 4)
+    return C[:prog.nrows, :prog.nslots]
+
+
+def keys(prog):
+    return alpha_list(prog.sd, prog.order)

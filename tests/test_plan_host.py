@@ -1,0 +1,63 @@
+"""Host-side plan compiler checked on CPU: the compiled recurrence program, fix-ups, folded
+coefficients and block packing reproduce the reference outputs stored in the golden fixtures."""
+import numpy
+import pytest
+
+from conftest import golden_case_names, load_case, tolerance
+from fiat_b200 import plan as planmod
+from oracle import fiat_oracle
+import program_emulator as emu
+
+
+def _simplex_dubiner_cases():
+    out = []
+    for name in golden_case_names():
+        case = load_case(name)
+        d = case["desc"]
+        if d["kind"] == "simplex" and d["expansion"] == "dubiner":
+            out.append(name)
+    return out
+
+
+@pytest.mark.parametrize("name", _simplex_dubiner_cases())
+def test_program_reproduces_reference(name):
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    prog = planmod.compile_simplex(desc, order)
+    pts = numpy.asarray(case["points"], dtype=float)
+    tr = fiat_oracle.resolve_entity(desc, case["entity"])
+    if tr is not None:
+        pts = pts.reshape(len(pts), tr[0].shape[0]) @ tr[0] + tr[1]
+    near = fiat_oracle.locate_cells(desc, pts, unique=bool(prog.unique))
+    out = emu.run_simplex(prog, pts, near)
+    for j, alpha in enumerate(emu.keys(prog)):
+        ref = case["ref"][alpha].reshape(prog.nrows, -1)
+        scale = max(abs(ref).max(), 1e-300)
+        assert abs(out[j] - ref).max() <= tolerance(desc, alpha) * scale, alpha
+
+
+def test_mis_order_matches_reference_keys():
+    for name in golden_case_names():
+        case = load_case(name)
+        if case["desc"]["kind"] != "simplex":
+            continue
+        sd = int(case["desc"]["sd"])
+        assert [tuple(k) for k in case["keys"]] == planmod.alpha_list(sd, case["order"])
+
+
+@pytest.mark.parametrize("name", ["p8_tet_o2", "n2curl4_tet_o1", "p3_tri_o1"])
+def test_block_packing_roundtrip(name):
+    case = load_case(name)
+    prog = planmod.compile_simplex(case["desc"], case["order"])
+    dense = emu.blocks_to_dense(prog)
+    full = prog.ccell[0]
+    # dropped blocks hold nothing but Vandermonde round-off
+    assert abs(dense - full).max() <= 1e-14 * abs(full).max()
+    assert prog.kpad % 4 == 0 and len(prog.rb_order) == len(prog.blk_ptr) - 1
+
+
+def test_tensor_flattening_hex():
+    from conftest import load_desc
+    leaves = planmod.flatten_tensor(load_desc("gll_q10_hex"))
+    assert [(lf.point_offset, lf.point_dim, lf.sd) for lf in leaves] == [(0, 1, 1), (1, 1, 1), (2, 1, 1)]
+    assert all(lf.entity == (1, 0) for lf in leaves)
