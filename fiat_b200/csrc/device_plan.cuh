@@ -3,20 +3,36 @@
 #include <stdint.h>
 #include "../../include/fiat_b200.h"
 
-#define FB_STEP_DOUBLES 16
-#define FB_GEOM_DOUBLES 16
+#define FB_GEOM_DOUBLES 32
 #define FB_NA_MAX 35          // C(3+4, 4): derivative order <= 4 in 3-D on the generic path
 #define FB_MAX_LEAVES 4
 
+// Recurrence program of one expansion set, small enough to travel as a kernel parameter
+// (constant bank): the tile kernel dedicates all of shared memory and therefore all of L1 to the
+// expansion table, so per-step tables read from global memory would pay an L2 round trip each.
+#define FB_MAX_STEPS 455      // C(12+3,3) - 1: degree 12 on a tetrahedron
+#define FB_MAX_LEVELS 30
+#define FB_MAX_FIX 128
+
+struct StepRec {
+    short nxt, cur, prv, codim;     // member slots; prv < 0: first step of a chain
+    double a, b, c;                 // Jacobi recurrence coefficients
+};
+
+struct RecTab {
+    int nsteps, nlevels, nfix, nfixgrp;
+    short level_ptr[FB_MAX_LEVELS + 2];
+    short fix_tgt[FB_MAX_FIX], fix_first[FB_MAX_FIX], fix_cnt[FB_MAX_FIX];   // per distinct target
+    short fix_src[FB_MAX_FIX];
+    double fix_w[FB_MAX_FIX];
+    double geom0[FB_GEOM_DOUBLES];  // geometry of cell 0 (single-cell elements)
+    StepRec steps[FB_MAX_STEPS];    // sorted by total degree of the member produced
+};
+
 struct DevSimplex {
     int sd, degree, order, na, expansion, ncells, nslots, nrows, unique;
-    int nsteps, nchains, nfix, line_n;
-    int chain_ptr[4];
-    const int4* step_idx;
-    const double* step_dat;
-    const int2* chains;
-    const int2* fix_idx;
-    const double* fix_w;
+    int line_n;
+    const RecTab* tab;          // device copy of the recurrence program (tensor-product leaves)
     const double* geom;
     const double* bary;
     const double* ccell;

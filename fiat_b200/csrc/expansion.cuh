@@ -25,10 +25,15 @@ __device__ __forceinline__ void apply_entity(const DevEntity& E, const double* _
         for (int j = 0; j < SD; ++j) x[j] = pt[j];
         return;
     }
+    double e[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        if (d < E.dim) e[d] = pt[d];
 #pragma unroll
     for (int j = 0; j < SD; ++j) {
         double s = 0.0;
-        for (int d = 0; d < E.dim; ++d) s = fma(pt[d], E.C[d * SD + j], s);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) s = fma(e[d], E.C[d * SD + j], s);   // C rows beyond E.dim are zero
         x[j] = s + E.off[j];
     }
 }
@@ -198,73 +203,72 @@ __device__ __forceinline__ double pick3(const double (&v)[3], int i) {
     return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]);
 }
 
-// Run one chain of the recurrence program for one point.  T addresses member slot s, jet
-// component a at T[s * slot_stride + a * comp_stride]; the chain start is read from T.
+// One recurrence step for one point.  T addresses member slot s, jet component a at
+// T[s * slot_stride + a * comp_stride]; `geom` is the cell's geometry record.
 template <int SD, int ORDER>
-__device__ __forceinline__ void run_chain(const DevSimplex& P, const double* __restrict__ step_dat_cell,
-                                          int step0, int nst, const double (&fa)[3], const double (&fb)[3],
-                                          double* __restrict__ T, int slot_stride, int comp_stride, int na) {
+__device__ __forceinline__ void run_step(const DevSimplex& P, const StepRec& r, const double* __restrict__ geom,
+                                         const double (&fa)[3], const double (&fb)[3], double* __restrict__ T,
+                                         int slot_stride, int comp_stride, int na) {
     typedef Jet<SD, ORDER> J;
     double cur[J::CAP], prv[J::CAP], nxt[J::CAP];
-    const int4 s0 = __ldg(P.step_idx + step0);
-    const int codim = s0.w;
+    const int codim = r.codim;
     const double fav = pick3(fa, codim), fbv = pick3(fb, codim);
-    const double fcv = fbv * fbv;
-    {
-        const double* src = T + (size_t)s0.y * slot_stride;
+    const double* src = T + (size_t)r.cur * slot_stride;
 #pragma unroll
-        for (int a = 0; a < (J::NA > 0 ? J::NA : FB_NA_MAX); ++a)
-            if (J::NA > 0 || a < na) cur[a] = src[a * comp_stride];
+    for (int a = 0; a < J::CAP; ++a)
+        if (J::NA > 0 || a < na) cur[a] = src[a * comp_stride];
+    const double F = r.a * fav - r.b * fbv;
+    double dfb[3], dF[3];
+#pragma unroll
+    for (int d = 0; d < SD; ++d) {
+        dfb[d] = geom[23 + 3 * codim + d];
+        dF[d] = r.a * geom[14 + 3 * codim + d] - r.b * dfb[d];
     }
-    for (int s = 0; s < nst; ++s) {
-        const int4 idx = __ldg(P.step_idx + step0 + s);
-        const double* rec = step_dat_cell + (size_t)(step0 + s) * FB_STEP_DOUBLES;
-        const double a = __ldg(rec + 0), b = __ldg(rec + 1), c = __ldg(rec + 2);
-        const double F = a * fav - b * fbv;
-        double dF[3], dG[3], ddG[6];
+    if (r.prv < 0) {
+        J::first(P, na, nxt, cur, F, dF);
+    } else {
+        const double* srp = T + (size_t)r.prv * slot_stride;
 #pragma unroll
-        for (int d = 0; d < SD; ++d) dF[d] = __ldg(rec + 3 + d);
-        if (s == 0) {
-            J::first(P, na, nxt, cur, F, dF);
-        } else {
-            const double G = -c * fcv;
+        for (int a2 = 0; a2 < J::CAP; ++a2)
+            if (J::NA > 0 || a2 < na) prv[a2] = srp[a2 * comp_stride];
+        const double G = -r.c * (fbv * fbv);
+        double g1[3], dG[3], ddG[6];
 #pragma unroll
-            for (int d = 0; d < SD; ++d) dG[d] = fbv * __ldg(rec + 6 + d);
-#pragma unroll
-            for (int k = 0; k < SD * (SD + 1) / 2; ++k) ddG[k] = __ldg(rec + 9 + k);
-            J::three(P, na, nxt, cur, prv, F, dF, G, dG, ddG);
+        for (int d = 0; d < SD; ++d) {
+            g1[d] = -2.0 * r.c * dfb[d];
+            dG[d] = fbv * g1[d];
         }
-        double* dst = T + (size_t)idx.x * slot_stride;
+        int k = 0;
 #pragma unroll
-        for (int a2 = 0; a2 < (J::NA > 0 ? J::NA : FB_NA_MAX); ++a2) {
-            if (J::NA > 0 || a2 < na) {
-                dst[a2 * comp_stride] = nxt[a2];
-                prv[a2] = cur[a2];
-                cur[a2] = nxt[a2];
-            }
-        }
+        for (int d1 = 0; d1 < SD; ++d1)
+#pragma unroll
+            for (int d2 = d1; d2 < SD; ++d2) ddG[k++] = g1[d1] * dfb[d2];
+        J::three(P, na, nxt, cur, prv, F, dF, G, dG, ddG);
     }
+    double* dst = T + (size_t)r.nxt * slot_stride;
+#pragma unroll
+    for (int a3 = 0; a3 < J::CAP; ++a3)
+        if (J::NA > 0 || a3 < na) dst[a3 * comp_stride] = nxt[a3];
 }
 
 // Whole Dubiner expansion of one cell at one point, thread-private column of T.
 template <int SD, int ORDER>
-__device__ __forceinline__ void dubiner_point(const DevSimplex& P, int cell, double start, const double (&xref)[3],
-                                              double* __restrict__ T, int slot_stride, int comp_stride, int na) {
+__device__ __forceinline__ void dubiner_point(const DevSimplex& P, const RecTab& tab, const double* __restrict__ geom,
+                                              double start, const double (&xref)[3], double* __restrict__ T,
+                                              int slot_stride, int comp_stride, int na) {
     double fa[3], fb[3];
     recurrence_factors<SD>(xref, fa, fb);
     T[0] = start;
     for (int a = 1; a < na; ++a) T[a * comp_stride] = 0.0;
-    const double* sd_cell = P.step_dat + (size_t)cell * P.nsteps * FB_STEP_DOUBLES;
-    for (int ch = 0; ch < P.nchains; ++ch) {
-        const int2 c = __ldg(P.chains + ch);
-        run_chain<SD, ORDER>(P, sd_cell, c.x, c.y, fa, fb, T, slot_stride, comp_stride, na);
-    }
-    for (int f = 0; f < P.nfix; ++f) {
-        const int2 ts = __ldg(P.fix_idx + f);
-        const double w = __ldg(P.fix_w + f);
-        double* t = T + (size_t)ts.x * slot_stride;
-        const double* s = T + (size_t)ts.y * slot_stride;
-        for (int a = 0; a < na; ++a) t[a * comp_stride] = fma(-w, s[a * comp_stride], t[a * comp_stride]);
+    for (int s = 0; s < tab.nsteps; ++s)
+        run_step<SD, ORDER>(P, tab.steps[s], geom, fa, fb, T, slot_stride, comp_stride, na);
+    for (int gi = 0; gi < tab.nfixgrp; ++gi) {
+        double* t = T + (size_t)tab.fix_tgt[gi] * slot_stride;
+        for (int f = tab.fix_first[gi]; f < tab.fix_first[gi] + tab.fix_cnt[gi]; ++f) {
+            const double w = tab.fix_w[f];
+            const double* s = T + (size_t)tab.fix_src[f] * slot_stride;
+            for (int a = 0; a < na; ++a) t[a * comp_stride] = fma(-w, s[a * comp_stride], t[a * comp_stride]);
+        }
     }
 }
 
@@ -333,8 +337,9 @@ __device__ __forceinline__ void lagrange_line_point(const DevSimplex& P, int cel
 
 // Expansion table of one (sub)cell at one point into the thread's column of T.
 template <int SD, int ORDER>
-__device__ __forceinline__ void expansion_point(const DevSimplex& P, int cell, double inv_mult, const double (&x)[3],
-                                                double* __restrict__ T, int slot_stride, int comp_stride, int na) {
+__device__ __forceinline__ void expansion_point(const DevSimplex& P, const RecTab& tab, int cell, double inv_mult,
+                                                const double (&x)[3], double* __restrict__ T, int slot_stride,
+                                                int comp_stride, int na) {
     if (P.expansion == 0) {
         const double* geom = P.geom + cell * FB_GEOM_DOUBLES;
         double xr[3] = {0.0, 0.0, 0.0};
@@ -342,10 +347,10 @@ __device__ __forceinline__ void expansion_point(const DevSimplex& P, int cell, d
         for (int i = 0; i < SD; ++i) {
             double s = 0.0;
 #pragma unroll
-            for (int d = 0; d < SD; ++d) s = fma(x[d], __ldg(geom + i * SD + d), s);
-            xr[i] = s + __ldg(geom + 9 + i);
+            for (int d = 0; d < SD; ++d) s = fma(x[d], geom[i * SD + d], s);
+            xr[i] = s + geom[9 + i];
         }
-        dubiner_point<SD, ORDER>(P, cell, __ldg(geom + 12) * inv_mult, xr, T, slot_stride, comp_stride, na);
+        dubiner_point<SD, ORDER>(P, tab, geom, geom[12] * inv_mult, xr, T, slot_stride, comp_stride, na);
     } else if (SD == 1) {
         if (P.expansion == 1) legendre_line_point(P, cell, inv_mult, x[0], T, slot_stride, comp_stride);
         else lagrange_line_point(P, cell, inv_mult, x[0], T, slot_stride, comp_stride);

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <atomic>
@@ -37,6 +38,7 @@ struct fiatb200_plan {
     int device;
     void* blob;             // one device allocation holding every table
     DevSimplex simplex;
+    RecTab tab;             // host copy, passed to kernels by value
     DevTensor tensor;
     int max_smem_optin;
     int num_sms;
@@ -98,7 +100,7 @@ int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double*
     int rc = set_smem(k_cellwise<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, E, pts, npts, ldp, out, ostride);
+    k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, plan->tab, E, pts, npts, ldp, out, ostride);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -119,10 +121,12 @@ int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const doubl
 bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     const DevSimplex& P = plan->simplex;
     if (P.ncells != 1 || P.expansion != 0 || P.order > 2 || P.nblk == 0) return false;
-    const size_t budget2 = 100 * 1024;                       // two CTAs per SM
+    const size_t budget2 = 113 * 1024;                       // two CTAs per SM (228 KiB, 1 KiB reserved each)
     const size_t budget1 = (size_t)plan->max_smem_optin - 1024;
+    int pt_max = 128;
+    if (const char* env = getenv("FIATB200_MMA_PT")) pt_max = std::max(8, atoi(env)) & ~7;   // tuning override
     for (int pass = 0; pass < 2; ++pass) {
-        for (int pt = 128; pt >= 8; pt >>= 1) {
+        for (int pt = pt_max; pt >= 8; pt >>= 1) {
             int ld = P.na * pt;
             while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
             const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double);
@@ -147,7 +151,7 @@ int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, 
     int rc = set_smem(k_mma<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
-    k_mma<SD, ORDER><<<grid, FB_MMA_THREADS, smem, st>>>(plan->simplex, E, G, pts, npts, ldp, out, ostride);
+    k_mma<SD, ORDER><<<grid, FB_MMA_THREADS, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -235,12 +239,28 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     int rc = device_limits(plan);
     if (rc) { delete plan; return rc; }
 
+    if (h->nsteps > FB_MAX_STEPS || h->nlevels > FB_MAX_LEVELS || h->nfix > FB_MAX_FIX || h->nfixgrp > FB_MAX_FIX) {
+        delete plan;
+        return fail(FIATB200_ERR_UNSUPPORTED, "expansion degree too high for the device recurrence tables");
+    }
+    RecTab& R = plan->tab;
+    R.nsteps = h->nsteps; R.nlevels = h->nlevels; R.nfix = h->nfix; R.nfixgrp = h->nfixgrp;
+    for (int i = 0; i <= h->nlevels; ++i) R.level_ptr[i] = (short)h->level_ptr[i];
+    for (int i = 0; i < h->nsteps; ++i) {
+        StepRec& r = R.steps[i];
+        r.nxt = (short)h->step_idx[4 * i + 0]; r.cur = (short)h->step_idx[4 * i + 1];
+        r.prv = (short)h->step_idx[4 * i + 2]; r.codim = (short)h->step_idx[4 * i + 3];
+        r.a = h->step_abc[3 * i + 0]; r.b = h->step_abc[3 * i + 1]; r.c = h->step_abc[3 * i + 2];
+    }
+    for (int i = 0; i < h->nfix; ++i) { R.fix_src[i] = (short)h->fix_idx[2 * i + 1]; R.fix_w[i] = h->fix_w[i]; }
+    for (int g = 0; g < h->nfixgrp; ++g) {
+        R.fix_first[g] = (short)h->fix_grp[2 * g]; R.fix_cnt[g] = (short)h->fix_grp[2 * g + 1];
+        R.fix_tgt[g] = (short)h->fix_idx[2 * h->fix_grp[2 * g]];
+    }
+    for (int i = 0; i < FB_GEOM_DOUBLES; ++i) R.geom0[i] = h->geom[i];
+
     Arena A;
-    const size_t o_step_idx = A.add(h->step_idx, sizeof(int32_t) * 4 * h->nsteps);
-    const size_t o_step_dat = A.add(h->step_dat, sizeof(double) * FB_STEP_DOUBLES * h->nsteps * h->ncells);
-    const size_t o_chains = A.add(h->chains, sizeof(int32_t) * 2 * h->nchains);
-    const size_t o_fix_idx = A.add(h->fix_idx, sizeof(int32_t) * 2 * h->nfix);
-    const size_t o_fix_w = A.add(h->fix_w, sizeof(double) * h->nfix);
+    const size_t o_tab = A.add(&R, sizeof(RecTab));
     const size_t o_geom = A.add(h->geom, sizeof(double) * FB_GEOM_DOUBLES * h->ncells);
     const size_t o_bary = A.add(h->bary, sizeof(double) * 16 * (h->ncells + 1));
     const size_t o_ccell = A.add(h->ccell, sizeof(double) * (size_t)h->ncells * h->nrows * h->nslots);
@@ -264,14 +284,9 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     DevSimplex& P = plan->simplex;
     P.sd = h->sd; P.degree = h->degree; P.order = h->order; P.na = h->na; P.expansion = h->expansion;
     P.ncells = h->ncells; P.nslots = h->nslots; P.nrows = h->nrows; P.unique = h->unique;
-    P.nsteps = h->nsteps; P.nchains = h->nchains; P.nfix = h->nfix; P.line_n = h->line_n;
-    for (int i = 0; i < 4; ++i) P.chain_ptr[i] = h->chain_ptr[i];
+    P.line_n = h->line_n;
     void* b = plan->blob;
-    P.step_idx = at<int4>(b, o_step_idx);
-    P.step_dat = at<double>(b, o_step_dat);
-    P.chains = at<int2>(b, o_chains);
-    P.fix_idx = at<int2>(b, o_fix_idx);
-    P.fix_w = at<double>(b, o_fix_w);
+    P.tab = at<RecTab>(b, o_tab);
     P.geom = at<double>(b, o_geom);
     P.bary = at<double>(b, o_bary);
     P.ccell = at<double>(b, o_ccell);

@@ -21,8 +21,8 @@
 // ---------------------------------------------------------------------------------------------
 template <int SD, int ORDER>
 __global__ void __launch_bounds__(128)
-k_cellwise(const DevSimplex P, const DevEntity E, const double* __restrict__ pts, long long npts, long long ldp,
-           double* __restrict__ out, long long ostride) {
+k_cellwise(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const double* __restrict__ pts,
+           long long npts, long long ldp, double* __restrict__ out, long long ostride) {
     extern __shared__ double smem[];
     const int BP = blockDim.x;
     const int tid = threadIdx.x;
@@ -40,7 +40,7 @@ k_cellwise(const DevSimplex P, const DevEntity E, const double* __restrict__ pts
     while (mask) {
         const int cell = __ffs(mask) - 1;
         mask &= mask - 1;
-        expansion_point<SD, ORDER>(P, cell, inv_mult, x, T, slot_stride, comp_stride, na);
+        expansion_point<SD, ORDER>(P, tab, cell, inv_mult, x, T, slot_stride, comp_stride, na);
         const double* C = P.ccell + (size_t)cell * P.nrows * P.nslots;
         for (int r = 0; r < P.nrows; ++r) {
             const double* Cr = C + (size_t)r * P.nslots;
@@ -100,13 +100,13 @@ struct MmaGeom {
     int S;         // column blocks (8 columns) per work item, <= FB_MMA_SMAX
     int ngroups;   // work items per row block
 };
-#define FB_MMA_SMAX 8
+#define FB_MMA_SMAX 10
 #define FB_MMA_THREADS 256
 
 template <int SD, int ORDER>
 __global__ void __launch_bounds__(FB_MMA_THREADS)
-k_mma(const DevSimplex P, const DevEntity E, const MmaGeom G, const double* __restrict__ pts, long long npts,
-      long long ldp, double* __restrict__ out, long long ostride) {
+k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const MmaGeom G,
+      const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride) {
     constexpr int NA = Jet<SD, ORDER>::NA;
     extern __shared__ double smem[];
     double* T = smem;                                   // kpad x ldT
@@ -128,8 +128,8 @@ k_mma(const DevSimplex P, const DevEntity E, const MmaGeom G, const double* __re
         for (int i = 0; i < SD; ++i) {
             double s = 0.0;
 #pragma unroll
-            for (int d = 0; d < SD; ++d) s = fma(x[d], __ldg(P.geom + i * SD + d), s);
-            xr[i] = s + __ldg(P.geom + 9 + i);
+            for (int d = 0; d < SD; ++d) s = fma(x[d], tab.geom0[i * SD + d], s);
+            xr[i] = s + tab.geom0[9 + i];
         }
         double fa[3], fb[3];
         recurrence_factors<SD>(xr, fa, fb);
@@ -138,53 +138,50 @@ k_mma(const DevSimplex P, const DevEntity E, const MmaGeom G, const double* __re
             s_fa[c * PT + tid] = fa[c];
             s_fb[c * PT + tid] = fb[c];
         }
-        const double start = __ldg(P.geom + 12);
+        const double start = tab.geom0[12];
 #pragma unroll
         for (int a = 0; a < NA; ++a) T[a * PT + tid] = (a == 0) ? start : 0.0;
     }
     for (int i = tid; i < (P.kpad - P.nslots) * G.ldT; i += FB_MMA_THREADS) T[(size_t)P.nslots * G.ldT + i] = 0.0;
     __syncthreads();
 
-    // phase 1: recurrence, one (chain, point) pair per thread and pass
-    for (int pass = 0; pass < SD; ++pass) {
-        const int c0 = P.chain_ptr[pass];
-        const int items = (P.chain_ptr[pass + 1] - c0) * PT;
+    // phase 1: recurrence in wavefront order -- every member of total degree d is an independent
+    // (step, point) work item once degrees d-1 and d-2 are in T
+    for (int lev = 0; lev < tab.nlevels; ++lev) {
+        const int l0 = tab.level_ptr[lev];
+        const int items = (tab.level_ptr[lev + 1] - l0) * PT;
         for (int it = tid; it < items; it += FB_MMA_THREADS) {
-            const int ch = c0 + it / PT, pl = it % PT;
-            const int2 c = __ldg(P.chains + ch);
+            const int sid = l0 + it / PT, pl = it % PT;
             const double fa[3] = {s_fa[pl], s_fa[PT + pl], s_fa[2 * PT + pl]};
             const double fb[3] = {s_fb[pl], s_fb[PT + pl], s_fb[2 * PT + pl]};
-            run_chain<SD, ORDER>(P, P.step_dat, c.x, c.y, fa, fb, T + pl, G.ldT, PT, NA);
+            run_step<SD, ORDER>(P, tab.steps[sid], tab.geom0, fa, fb, T + pl, G.ldT, PT, NA);
         }
         __syncthreads();
     }
-    // C0 fix-ups: target -= w * source (targets are never sources)
-    if (P.nfix) {
-        const int items = P.nfix * NA * PT;
+    // C0 fix-ups: target -= sum_k w_k * source_k, one work item per (target, column); targets are never sources
+    if (tab.nfixgrp) {
+        const int ncol = NA * PT;
+        const int items = tab.nfixgrp * ncol;
         for (int it = tid; it < items; it += FB_MMA_THREADS) {
-            const int f = it / (NA * PT), col = it % (NA * PT);
-            const int2 ts = __ldg(P.fix_idx + f);
-            const double w = __ldg(P.fix_w + f);
-            // several fix-ups may share a target: serialise them per column
-            if (f > 0 && __ldg(P.fix_idx + f - 1).x == ts.x) continue;
-            double v = T[(size_t)ts.x * G.ldT + col];
-            for (int g = f; g < P.nfix; ++g) {
-                const int2 t2 = __ldg(P.fix_idx + g);
-                if (t2.x != ts.x) break;
-                v = fma(-__ldg(P.fix_w + g), T[(size_t)t2.y * G.ldT + col], v);
-            }
-            (void)w;
-            T[(size_t)ts.x * G.ldT + col] = v;
+            const int grp = it / ncol, col = it % ncol;
+            const int f0 = tab.fix_first[grp], f1 = f0 + tab.fix_cnt[grp];
+            double* tp = T + (size_t)tab.fix_tgt[grp] * G.ldT + col;
+            double v = *tp;
+            for (int f = f0; f < f1; ++f) v = fma(-tab.fix_w[f], T[(size_t)tab.fix_src[f] * G.ldT + col], v);
+            *tp = v;
         }
         __syncthreads();
     }
 
-    // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe
+    // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe.
+    // Work item = (row block, group of S column blocks); coefficient fragments are fetched CH blocks
+    // ahead so that their L2 latency hides behind the DMMAs of the current chunk.
+    constexpr int CH = 8;
     const int lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int ncb = NA * PT / 8;                         // column blocks of the tile
     const int nitems = P.nrb * G.ngroups;
-    const bool vec_ok = ((ostride & 1) == 0) && ((base & 1) == 0) && ((((size_t)out) & 15) == 0);
+    const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0);
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&s_next, 1);
@@ -192,33 +189,47 @@ k_mma(const DevSimplex P, const DevEntity E, const MmaGeom G, const double* __re
         if (item >= nitems) break;
         const int rb = __ldg(P.rb_order + item / G.ngroups);
         const int cb0 = (item % G.ngroups) * G.S;
+        const int ns = min(G.S, ncb - cb0);
         double acc[FB_MMA_SMAX][2];
 #pragma unroll
         for (int s = 0; s < FB_MMA_SMAX; ++s) acc[s][0] = acc[s][1] = 0.0;
         const int q0 = __ldg(P.blk_ptr + rb), q1 = __ldg(P.blk_ptr + rb + 1);
-        double a_next = (q0 < q1) ? __ldg(P.blk_frag + (size_t)q0 * 32 + lane) : 0.0;
-        int kb_next = (q0 < q1) ? __ldg(P.blk_kb + q0) : 0;
-        for (int q = q0; q < q1; ++q) {
-            const double a = a_next;
-            const int kb = kb_next;
-            if (q + 1 < q1) {
-                a_next = __ldg(P.blk_frag + (size_t)(q + 1) * 32 + lane);
-                kb_next = __ldg(P.blk_kb + q + 1);
-            }
-            const double* Tb = T + (size_t)(4 * kb + t) * G.ldT + 8 * cb0 + g;
+        double a_cur[CH], a_nxt[CH];
+        int kb_cur = 0, kb_nxt = 0;
 #pragma unroll
-            for (int s = 0; s < FB_MMA_SMAX; ++s) {
-                if (s < G.S && cb0 + s < ncb) {
-                    const double b = Tb[8 * s];
-                    dmma_8x8x4(acc[s][0], acc[s][1], a, b);
+        for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
+        if (lane < CH && q0 + lane < q1) kb_cur = __ldg(P.blk_kb + q0 + lane);
+        const double* Tcol = T + 8 * cb0 + g + (size_t)t * G.ldT;
+        for (int q = q0; q < q1; q += CH) {
+            if (q + CH < q1) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    a_nxt[j] = (q + CH + j < q1) ? __ldg(P.blk_frag + (size_t)(q + CH + j) * 32 + lane) : 0.0;
+                kb_nxt = (lane < CH && q + CH + lane < q1) ? __ldg(P.blk_kb + q + CH + lane) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                if (q + j < q1) {
+                    const int kb = __shfl_sync(0xffffffffu, kb_cur, j);
+                    const double* Tb = Tcol + (size_t)(4 * kb) * G.ldT;
+#pragma unroll
+                    for (int s = 0; s < FB_MMA_SMAX; ++s) {
+                        if (s < ns) {
+                            const double b = Tb[8 * s];
+                            dmma_8x8x4(acc[s][0], acc[s][1], a_cur[j], b);
+                        }
+                    }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) a_cur[j] = a_nxt[j];
+            kb_cur = kb_nxt;
         }
         const int row = rb * 8 + g;
         if (row < P.nrows) {
 #pragma unroll
             for (int s = 0; s < FB_MMA_SMAX; ++s) {
-                if (s < G.S && cb0 + s < ncb) {
+                if (s < ns) {
                     const int col = 8 * (cb0 + s);
                     const int a = col / PT, pl = col % PT + 2 * t;
                     const long long p = base + pl;
@@ -251,7 +262,7 @@ __device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double*
     while (mask) {
         const int cell = __ffs(mask) - 1;
         mask &= mask - 1;
-        expansion_point<SD, -1>(P, cell, inv_mult, x, scratch, na * BP, BP, na);
+        expansion_point<SD, -1>(P, *P.tab, cell, inv_mult, x, scratch, na * BP, BP, na);
         const double* C = P.ccell + (size_t)cell * P.nrows * P.nslots;
         for (int r = 0; r < P.nrows; ++r) {
             for (int a = 0; a < na; ++a) {

@@ -5,7 +5,8 @@ Everything that does not depend on the evaluation point is worked out here, once
 * the *recurrence program* of the Dubiner / integrated-Jacobi expansion
   (`FIAT/expansions.py:202-249`): one record per three-term step with the Jacobi coefficients
   (`jrc` / `integrated_jrc`, `:24-40`) and the point-independent parts of the recurrence-factor
-  derivatives (`jacobi_factors`, `:54-63,205`), grouped into chains that can run concurrently;
+  derivatives (`jacobi_factors`, `:54-63,205`), ordered by the total degree of the member they
+  produce so that all steps of one degree can run concurrently;
 * the per-pass normalisation (`:251-266`), accumulated per member and folded into the columns of
   the coefficient matrix together with the C0 entity reordering (`:297-322`), so that the device
   recurrence runs un-normalised and `PolynomialSet.tabulate`'s contraction
@@ -26,8 +27,7 @@ import numpy
 __all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf"]
 
 EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
-STEP_DOUBLES = 16      # a, b, c, dF[3], g1[3], ddG[6], pad
-GEOM_DOUBLES = 16      # A[9], b[3], start value, pad
+GEOM_DOUBLES = 32      # A[9], b[3] @9, start value @12, dfa[codim][d] @14, dfb[codim][d] @23
 
 
 def multi_indices(m, n):
@@ -200,12 +200,12 @@ class SimplexProgram:
     unique: int                 # first-match binning (continuity is not None and order == 0)
     geom: numpy.ndarray         # (ncells, GEOM_DOUBLES)
     bary: numpy.ndarray         # (ncells + 1, 4, 4): rows of A_hat | b_hat
-    step_idx: numpy.ndarray     # (nsteps, 4) int32: next, cur, prev(-1 = first of chain), codim
-    step_dat: numpy.ndarray     # (ncells, nsteps, STEP_DOUBLES)
-    chain_ptr: numpy.ndarray    # (sd + 1,) int32 offsets into chains per codim pass
-    chains: numpy.ndarray       # (nchains, 2) int32: first step, number of steps
+    step_idx: numpy.ndarray     # (nsteps, 4) int32: next, cur, prev(-1 = first of chain), codim; level order
+    step_abc: numpy.ndarray     # (nsteps, 3) Jacobi recurrence coefficients a, b, c
+    level_ptr: numpy.ndarray    # (degree + 1,) int32: steps producing degree d+1 are [level_ptr[d], level_ptr[d+1])
     fix_idx: numpy.ndarray      # (nfix, 2) int32 target, source slots
     fix_w: numpy.ndarray        # (nfix,)
+    fix_grp: numpy.ndarray      # (ngroups, 2) int32: first fix-up and count per distinct target
     ccell: numpy.ndarray        # (ncells, nrows, nslots) folded coefficients
     low1: numpy.ndarray
     mul1: numpy.ndarray
@@ -233,29 +233,30 @@ def _dubiner_tables(desc, order):
     slot_of = numpy.empty(nmem, dtype=numpy.int64)       # Morton member -> slot (output position)
     slot_of[entity_order] = numpy.arange(nmem)
 
-    # chains and steps, pass by pass
-    step_idx, step_abc, chains, chain_ptr = [], [], [], [0]
+    # steps, pass by pass (expansions.py:202-249)
+    step_idx, step_abc, step_level = [], [], []
     if n > 0:
         for codim in range(sd):
             for sub in _sub_indices(n, codim):
                 length = n - sum(sub)
                 abc = _chain_coefficients(variant, sub, length)
-                first = len(step_idx)
                 for i in range(length):
                     cur = slot_of[_morton(sub + (i,), sd)]
                     nxt = slot_of[_morton(sub + (i + 1,), sd)]
                     prv = slot_of[_morton(sub + (i - 1,), sd)] if i > 0 else -1
                     step_idx.append((nxt, cur, prv, codim))
                     step_abc.append(abc[i])
-                chains.append((first, length))
-            chain_ptr.append(len(chains))
-    else:
-        chain_ptr += [0] * sd
+                    step_level.append(sum(sub) + i + 1)      # total degree of the member produced
     step_idx = numpy.array(step_idx, dtype=numpy.int32).reshape(-1, 4)
-    nsteps = len(step_idx)
+    step_abc = numpy.array(step_abc, dtype=float).reshape(-1, 3)
+    # wavefront order: a member of total degree d only needs members of degree d-1 and d-2
+    step_level = numpy.array(step_level, dtype=numpy.int64)
+    by_level = numpy.argsort(step_level, kind="stable")
+    step_idx, step_abc = step_idx[by_level], step_abc[by_level]
+    level_ptr = numpy.searchsorted(step_level[by_level], numpy.arange(1, n + 2)).astype(numpy.int32)
 
-    # per-cell step data: point-independent pieces of F, dF, G, dG, ddG
-    step_dat = numpy.zeros((ncells, nsteps, STEP_DOUBLES))
+    # per-cell geometry: affine map to the default simplex and the constant gradients of the
+    # recurrence factors fa, fb of every collapsing pass (jacobi_factors, expansions.py:54-63)
     geom = numpy.zeros((ncells, GEOM_DOUBLES))
     for c in range(ncells):
         A = numpy.asarray(desc["cell_A"][c], dtype=float)
@@ -264,20 +265,11 @@ def _dubiner_tables(desc, order):
         scale = float(desc["cell_scale"][c])
         geom[c, 12] = -scale if variant == "bubble" else scale
         dX = [A[i] for i in range(sd)] + [numpy.zeros(sd), numpy.zeros(sd)]
-        for s in range(nsteps):
-            codim = step_idx[s, 3]
-            a, b, cc = step_abc[s]
+        for codim in range(sd):
             dfb = 0.5 * (dX[codim + 1] + dX[codim + 2])
             dfa = dX[codim] + dfb
-            rec = step_dat[c, s]
-            rec[0:3] = (a, b, cc)
-            rec[3:3 + sd] = a * dfa - b * dfb
-            rec[6:6 + sd] = -cc * (2 * dfb)
-            k = 0
-            for d1 in range(sd):
-                for d2 in range(d1, sd):
-                    rec[9 + k] = -cc * (2 * dfb[d1] * dfb[d2])
-                    k += 1
+            geom[c, 14 + 3 * codim:14 + 3 * codim + sd] = dfa
+            geom[c, 23 + 3 * codim:23 + 3 * codim + sd] = dfb
 
     # fold normalisation / sign / reordering into the coefficient columns
     norm = _normalisation(sd, n, variant) if n > 0 else numpy.ones(nmem)
@@ -293,9 +285,7 @@ def _dubiner_tables(desc, order):
             fix_w.append(norm[s] / norm[t])
     fold_by_slot = numpy.empty(nmem)
     fold_by_slot[slot_of] = fold
-    return dict(nslots=nmem, step_idx=step_idx, step_dat=step_dat, geom=geom,
-                chains=numpy.array(chains, dtype=numpy.int32).reshape(-1, 2),
-                chain_ptr=numpy.array(chain_ptr, dtype=numpy.int32),
+    return dict(nslots=nmem, step_idx=step_idx, step_abc=step_abc, geom=geom, level_ptr=level_ptr,
                 fix_idx=numpy.array(fix_idx, dtype=numpy.int32).reshape(-1, 2),
                 fix_w=numpy.array(fix_w, dtype=float), fold_by_slot=fold_by_slot)
 
@@ -381,8 +371,8 @@ def compile_simplex(desc, order):
         t = _line_tables(desc, order)
         fold = numpy.ones(t["nslots"])
         line_tab, line_n = t["line_tab"], t["line_n"]
-        t.update(step_idx=numpy.zeros((0, 4), numpy.int32), step_dat=numpy.zeros((ncells, 0, STEP_DOUBLES)),
-                 chains=numpy.zeros((0, 2), numpy.int32), chain_ptr=numpy.zeros(sd + 1, numpy.int32),
+        t.update(step_idx=numpy.zeros((0, 4), numpy.int32), step_abc=numpy.zeros((0, 3)),
+                 level_ptr=numpy.zeros(1, numpy.int32),
                  fix_idx=numpy.zeros((0, 2), numpy.int32), fix_w=numpy.zeros(0))
     nslots = t["nslots"]
     if cnm.shape[1] != nslots:
@@ -390,6 +380,13 @@ def compile_simplex(desc, order):
     ccell = numpy.empty((ncells, nrows, nslots))
     for c in range(ncells):
         ccell[c] = C[:, cnm[c]] * fold[None, :]
+
+    # fix-ups sorted by target, with one (first, count) record per distinct target
+    fix_idx, fix_w = t["fix_idx"], t["fix_w"]
+    perm = numpy.argsort(fix_idx[:, 0], kind="stable") if len(fix_idx) else numpy.zeros(0, dtype=int)
+    t["fix_idx"], t["fix_w"] = fix_idx[perm], fix_w[perm]
+    targets, first, count = numpy.unique(t["fix_idx"][:, 0], return_index=True, return_counts=True)
+    fix_grp = numpy.stack([first, count], axis=1).astype(numpy.int32).reshape(-1, 2)
 
     bary = numpy.zeros((ncells + 1, 4, 4))
     if ncells > 1:
@@ -401,9 +398,9 @@ def compile_simplex(desc, order):
         ncells=ncells, nslots=nslots, nrows=nrows, ndofs=ndofs,
         value_shape=tuple(int(s) for s in desc["value_shape"]),
         unique=int(bool(desc["c0"]) and order == 0),
-        geom=t["geom"], bary=bary, step_idx=t["step_idx"], step_dat=t["step_dat"],
-        chain_ptr=t["chain_ptr"], chains=t["chains"], fix_idx=t["fix_idx"], fix_w=t["fix_w"],
-        ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
+        geom=t["geom"], bary=bary, step_idx=t["step_idx"], step_abc=t["step_abc"], level_ptr=t["level_ptr"],
+        fix_idx=t["fix_idx"], fix_w=t["fix_w"],
+        fix_grp=fix_grp, ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
     if ncells == 1:
         scale = numpy.abs(ccell[0]).max() if ccell.size else 0.0
         (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = pack_blocks(ccell[0], 1e-14 * scale)

@@ -48,14 +48,16 @@ typedef struct {
     int32_t nslots;        /* expansion members per subcell */
     int32_t nrows;         /* ndofs * prod(value_shape) */
     int32_t unique;        /* 1: first matching subcell wins (expansions.py:452,805-807) */
-    int32_t nsteps, nchains, nfix, line_n;
-    int32_t chain_ptr[4];  /* chains of recurrence pass d are chains[chain_ptr[d] .. chain_ptr[d+1]) */
-    const int32_t* step_idx;   /* nsteps x 4: next, cur, prev (-1 first of chain), codim */
-    const double* step_dat;    /* ncells x nsteps x 16: a,b,c | dF[3] | -2c*dfb[3] | -2c*dfb(x)dfb[6] */
-    const int32_t* chains;     /* nchains x 2: first step, number of steps */
+    int32_t nsteps, nlevels, nfix, nfixgrp, line_n;
+    const int32_t* step_idx;   /* nsteps x 4: next, cur, prev (-1 first of chain), codim; sorted by the total
+                                  degree of the member produced (wavefront order) */
+    const double* step_abc;    /* nsteps x 3 Jacobi recurrence coefficients (expansions.py:24-40) */
+    const int32_t* level_ptr;  /* nlevels + 1: steps producing degree d+1 are [level_ptr[d], level_ptr[d+1]) */
     const int32_t* fix_idx;    /* nfix x 2: target, source slot (C0_basis fix-ups) */
     const double* fix_w;       /* nfix */
-    const double* geom;        /* ncells x 16: A[9] (row-major sd x sd), b[3] at 9, start value at 12 */
+    const int32_t* fix_grp;    /* nfixgrp x 2: fix-ups sorted by target; first entry and count per target */
+    const double* geom;        /* ncells x 32: A[9] (row-major sd x sd), b[3] at 9, start value at 12,
+                                  grad fa per pass at 14 (3x3), grad fb per pass at 23 (3x3) */
     const double* bary;        /* (ncells+1) x 4 x 4: rescaled barycentric rows A_hat | b_hat, parent last
                                   (reference_element.py:616-644) */
     const double* ccell;       /* ncells x nrows x nslots folded coefficients coeffs[:, cell_node_map[c]] */

@@ -14,16 +14,17 @@ def _jets(prog, cell, x):
     T[0, 0] = prog.geom[cell, 12]
     X = [x[i] for i in range(sd)] + [-numpy.ones(npts), -numpy.ones(npts)]
     pairs = [(d1, d2) for d1 in range(sd) for d2 in range(d1, sd)]
+    g = prog.geom[cell]
     for s, (nxt, cur, prv, codim) in enumerate(prog.step_idx):
-        rec = prog.step_dat[cell, s]
-        a, b, c = rec[0:3]
+        a, b, c = prog.step_abc[s]
+        dfa, dfb = g[14 + 3 * codim:14 + 3 * codim + sd], g[23 + 3 * codim:23 + 3 * codim + sd]
         fb = 0.5 * (X[codim + 1] + X[codim + 2])
         fa = X[codim] + (fb + 1.0)
         F = a * fa - b * fb
-        dF = rec[3:3 + sd]
+        dF = a * dfa - b * dfb
         G = -c * (fb * fb)
-        dG = [fb * rec[6 + d] for d in range(sd)]
-        ddG = rec[9:9 + len(pairs)]
+        dG = [fb * (-2 * c * dfb[d]) for d in range(sd)]
+        ddG = [(-2 * c * dfb[d1]) * dfb[d2] for (d1, d2) in pairs]
         for j in range(na):
             v = F * T[cur, j]
             for d in range(sd):
