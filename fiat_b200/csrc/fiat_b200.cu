@@ -121,25 +121,19 @@ int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const doubl
 bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     const DevSimplex& P = plan->simplex;
     if (P.ncells != 1 || P.expansion != 0 || P.order > 2 || P.nblk == 0) return false;
-    const size_t budget2 = 113 * 1024;                       // two CTAs per SM (228 KiB, 1 KiB reserved each)
-    const size_t budget1 = (size_t)plan->max_smem_optin - 1024;
+    // one CTA per SM: the widest tile whose expansion table fits in shared memory
+    const size_t budget = (size_t)plan->max_smem_optin - 1024;
     int pt_max = 128;
     if (const char* env = getenv("FIATB200_MMA_PT")) pt_max = std::max(8, atoi(env)) & ~7;   // tuning override
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int pt = pt_max; pt >= 8; pt >>= 1) {
-            int ld = P.na * pt;
-            while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
-            const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double);
-            if (bytes <= (pass == 0 ? budget2 : budget1)) {
-                const int ncb = P.na * pt / 8;
-                int ngroups = (ncb + FB_MMA_SMAX - 1) / FB_MMA_SMAX;
-                G->PT = pt;
-                G->ldT = ld;
-                G->ngroups = ngroups;
-                G->S = (ncb + ngroups - 1) / ngroups;
-                *smem_out = bytes;
-                return true;
-            }
+    for (int pt = pt_max; pt >= 8; pt >>= 1) {
+        int ld = P.na * pt;
+        while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
+        const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double);
+        if (bytes <= budget) {
+            G->PT = pt;
+            G->ldT = ld;
+            *smem_out = bytes;
+            return true;
         }
     }
     return false;

@@ -4,7 +4,7 @@
 //                -> contraction with the per-subcell coefficient matrix.  Handles every simplex plan
 //                (split cells, 1-D sets, any order); the only path for split cells.
 //   k_mma        single-cell Dubiner elements: a CTA owns a tile of PT points, runs the recurrence
-//                chain-parallel into a shared expansion table T[member][alpha][point] and contracts
+//                level-parallel into a shared expansion table T[member][octet][alpha][8] and contracts
 //                it with the 8x4 block-sparse coefficient matrix on the FP64 tensor pipe
 //                (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), skipping all-zero blocks.
 //   k_tensor     scalar tensor-product elements: factor tables per point in shared memory, then the
@@ -97,14 +97,17 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 struct MmaGeom {
     int PT;        // points per tile (multiple of 8)
     int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)
-    int S;         // column blocks (8 columns) per work item, <= FB_MMA_SMAX
-    int ngroups;   // work items per row block
 };
-#define FB_MMA_SMAX 10
-#define FB_MMA_THREADS 256
+#define FB_MMA_THREADS 512
 
+// One CTA per SM, two phases that never overlap: FP64 vector work (recurrence) and FP64 tensor work
+// (contraction) share one pipe on B200, and a DFMA issued between DMMAs waits for the 16-cycle
+// DMMA in front of it, so interleaving the two phases of different CTAs costs more than it hides.
+//
+// T layout: T[slot][octet][alpha][8 points]; one work item of the contraction is (row block, octet),
+// whose NA column blocks are contiguous.
 template <int SD, int ORDER>
-__global__ void __launch_bounds__(FB_MMA_THREADS)
+__global__ void __launch_bounds__(FB_MMA_THREADS, 1)
 k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const MmaGeom G,
       const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride) {
     constexpr int NA = Jet<SD, ORDER>::NA;
@@ -139,8 +142,9 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             s_fb[c * PT + tid] = fb[c];
         }
         const double start = tab.geom0[12];
+        double* t0 = T + (tid >> 3) * (8 * NA) + (tid & 7);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) T[a * PT + tid] = (a == 0) ? start : 0.0;
+        for (int a = 0; a < NA; ++a) t0[a * 8] = (a == 0) ? start : 0.0;
     }
     for (int i = tid; i < (P.kpad - P.nslots) * G.ldT; i += FB_MMA_THREADS) T[(size_t)P.nslots * G.ldT + i] = 0.0;
     __syncthreads();
@@ -154,52 +158,39 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             const int sid = l0 + it / PT, pl = it % PT;
             const double fa[3] = {s_fa[pl], s_fa[PT + pl], s_fa[2 * PT + pl]};
             const double fb[3] = {s_fb[pl], s_fb[PT + pl], s_fb[2 * PT + pl]};
-            run_step<SD, ORDER>(P, tab.steps[sid], tab.geom0, fa, fb, T + pl, G.ldT, PT, NA);
-        }
-        __syncthreads();
-    }
-    // C0 fix-ups: target -= sum_k w_k * source_k, one work item per (target, column); targets are never sources
-    if (tab.nfixgrp) {
-        const int ncol = NA * PT;
-        const int items = tab.nfixgrp * ncol;
-        for (int it = tid; it < items; it += FB_MMA_THREADS) {
-            const int grp = it / ncol, col = it % ncol;
-            const int f0 = tab.fix_first[grp], f1 = f0 + tab.fix_cnt[grp];
-            double* tp = T + (size_t)tab.fix_tgt[grp] * G.ldT + col;
-            double v = *tp;
-            for (int f = f0; f < f1; ++f) v = fma(-tab.fix_w[f], T[(size_t)tab.fix_src[f] * G.ldT + col], v);
-            *tp = v;
+            run_step<SD, ORDER>(P, tab.steps[sid], tab.geom0, fa, fb, T + (pl >> 3) * (8 * NA) + (pl & 7), G.ldT, 8, NA);
         }
         __syncthreads();
     }
 
-    // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe.
-    // Work item = (row block, group of S column blocks); coefficient fragments are fetched CH blocks
-    // ahead so that their L2 latency hides behind the DMMAs of the current chunk.
+    // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe (the C0 fix-ups
+    // are folded into C).  Coefficient fragments are fetched CH blocks ahead so that their L2
+    // latency hides behind the DMMAs of the current chunk.
     constexpr int CH = 8;
     const int lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int ncb = NA * PT / 8;                         // column blocks of the tile
-    const int nitems = P.nrb * G.ngroups;
+    const int noct = PT >> 3;
+    const int nitems = P.nrb * noct;
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0);
+    const double* Tlane = T + (size_t)t * G.ldT + g;
+    const size_t kb_stride = (size_t)4 * G.ldT;
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&s_next, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nitems) break;
-        const int rb = __ldg(P.rb_order + item / G.ngroups);
-        const int cb0 = (item % G.ngroups) * G.S;
-        const int ns = min(G.S, ncb - cb0);
-        double acc[FB_MMA_SMAX][2];
+        const int rb = __ldg(P.rb_order + item / noct);
+        const int oct = item % noct;
+        double acc[NA][2];
 #pragma unroll
-        for (int s = 0; s < FB_MMA_SMAX; ++s) acc[s][0] = acc[s][1] = 0.0;
+        for (int s = 0; s < NA; ++s) acc[s][0] = acc[s][1] = 0.0;
         const int q0 = __ldg(P.blk_ptr + rb), q1 = __ldg(P.blk_ptr + rb + 1);
         double a_cur[CH], a_nxt[CH];
         int kb_cur = 0, kb_nxt = 0;
 #pragma unroll
         for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
         if (lane < CH && q0 + lane < q1) kb_cur = __ldg(P.blk_kb + q0 + lane);
-        const double* Tcol = T + 8 * cb0 + g + (size_t)t * G.ldT;
+        const double* Titem = Tlane + oct * (8 * NA);
         for (int q = q0; q < q1; q += CH) {
             if (q + CH < q1) {
 #pragma unroll
@@ -207,18 +198,17 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                     a_nxt[j] = (q + CH + j < q1) ? __ldg(P.blk_frag + (size_t)(q + CH + j) * 32 + lane) : 0.0;
                 kb_nxt = (lane < CH && q + CH + lane < q1) ? __ldg(P.blk_kb + q + CH + lane) : 0;
             }
+            const int nj = min(CH, q1 - q);
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
-                if (q + j < q1) {
+                if (j < nj) {
                     const int kb = __shfl_sync(0xffffffffu, kb_cur, j);
-                    const double* Tb = Tcol + (size_t)(4 * kb) * G.ldT;
+                    const double* Tb = Titem + kb * kb_stride;
+                    double bfrag[NA];
 #pragma unroll
-                    for (int s = 0; s < FB_MMA_SMAX; ++s) {
-                        if (s < ns) {
-                            const double b = Tb[8 * s];
-                            dmma_8x8x4(acc[s][0], acc[s][1], a_cur[j], b);
-                        }
-                    }
+                    for (int s = 0; s < NA; ++s) bfrag[s] = Tb[8 * s];
+#pragma unroll
+                    for (int s = 0; s < NA; ++s) dmma_8x8x4(acc[s][0], acc[s][1], a_cur[j], bfrag[s]);
                 }
             }
 #pragma unroll
@@ -227,19 +217,15 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         }
         const int row = rb * 8 + g;
         if (row < P.nrows) {
+            const long long p = base + oct * 8 + 2 * t;
 #pragma unroll
-            for (int s = 0; s < FB_MMA_SMAX; ++s) {
-                if (s < ns) {
-                    const int col = 8 * (cb0 + s);
-                    const int a = col / PT, pl = col % PT + 2 * t;
-                    const long long p = base + pl;
-                    double* o = out + ((size_t)a * P.nrows + row) * ostride + p;
-                    if (vec_ok && p + 1 < npts) {
-                        *reinterpret_cast<double2*>(o) = make_double2(acc[s][0], acc[s][1]);
-                    } else {
-                        if (p < npts) o[0] = acc[s][0];
-                        if (p + 1 < npts) o[1] = acc[s][1];
-                    }
+            for (int s = 0; s < NA; ++s) {
+                double* o = out + ((size_t)s * P.nrows + row) * ostride + p;
+                if (vec_ok && p + 1 < npts) {
+                    *reinterpret_cast<double2*>(o) = make_double2(acc[s][0], acc[s][1]);
+                } else {
+                    if (p < npts) o[0] = acc[s][0];
+                    if (p + 1 < npts) o[1] = acc[s][1];
                 }
             }
         }

@@ -402,8 +402,12 @@ def compile_simplex(desc, order):
         fix_idx=t["fix_idx"], fix_w=t["fix_w"],
         fix_grp=fix_grp, ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
     if ncells == 1:
-        scale = numpy.abs(ccell[0]).max() if ccell.size else 0.0
-        (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = pack_blocks(ccell[0], 1e-14 * scale)
+        # the tile kernel has no fix-up phase: T' = X T  =>  C T' = (C X) T
+        folded = ccell[0].copy()
+        for (tgt, src), w in zip(prog.fix_idx, prog.fix_w):
+            folded[:, src] -= w * ccell[0][:, tgt]
+        scale = numpy.abs(folded).max() if folded.size else 0.0
+        (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = pack_blocks(folded, 1e-14 * scale)
     return prog
 
 
