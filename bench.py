@@ -284,7 +284,8 @@ def main():
             "config": {"workload": label, "points_per_gpu_per_step": batch, "values_per_point": vpp,
                        "total_points": world * args.steps * batch,
                        "l2": "output buffer per step is %.1f GB >> L2; rewritten every step" % (8 * vpp * batch / 1e9),
-                       "sharding": "contiguous point shards, one rank per GPU, no collective"},
+                       "sharding": "contiguous point shards, one rank per GPU, no collective",
+                       "kernel": tab.kernel_path(order, args.flags)},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "values/s", "h2d_bytes_per_step": int(ne * sd * 8),
                     "d2h_bytes_per_step": int(ne * vpp * 8), "points_per_step": ne},

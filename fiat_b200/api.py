@@ -29,6 +29,7 @@ __all__ = ["tabulate", "tabulate_into", "tabulate_host", "locate_subcells", "Tab
 
 FORCE_THREAD_PER_POINT = 1
 FORCE_DMMA = 2
+FORCE_GENERAL = 4          # do not use the product-form (lattice) kernel
 
 
 def _resolve_simplex_entity(desc, entity):
@@ -104,6 +105,54 @@ class Tabulator:
                 self._plans[key] = (_Plan(handle, keep), prog)
             return self._plans[key]
 
+    def _lattice_plan(self, desc, order):
+        """Product-form plan for equispaced Lagrange elements, or None.  Selected only after it has
+        reproduced the general kernel on the device."""
+        key = ("lattice", id(desc), order)
+        with self._lock:
+            if key in self._plans:
+                return self._plans[key]
+        plan = None
+        rowmap = planmod.lattice_rowmap(desc) if order <= 2 else None
+        if rowmap is not None:
+            keep = [numpy.ascontiguousarray(rowmap, dtype=numpy.int32)]
+            handle = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fiatb200_lattice_plan_create(
+                    int(desc["sd"]), int(desc["degree"]), order, keep[0].ctypes.data_as(_lib.p_i32), len(rowmap),
+                    ctypes.byref(handle)))
+            cand = _Plan(handle, keep)
+            if self._lattice_agrees(desc, order, cand):
+                plan = cand
+        with self._lock:
+            self._plans[key] = plan
+        return plan
+
+    def _lattice_agrees(self, desc, order, cand):
+        sd = int(desc["sd"])
+        general, prog = self._simplex_plan(desc, order)
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(20261018)
+        u, _ = torch.sort(torch.rand((96, sd), generator=gen, dtype=torch.float64), dim=1)
+        pts = torch.diff(torch.cat([torch.zeros((96, 1), dtype=torch.float64), u], dim=1), dim=1)
+        pts = pts.to(self.device).contiguous()
+        ent = _lib.entity_struct(sd, None)
+        a = torch.empty((prog.na, prog.nrows, 96), dtype=torch.float64, device=self.device)
+        b = torch.empty_like(a)
+        self._launch(general, ent, pts, a, 96, FORCE_GENERAL)
+        self._launch(cand, ent, pts, b, 96, 0)
+        scale = a.abs().amax(dim=(1, 2)).clamp_min(1e-300)
+        err = (a - b).abs().amax(dim=(1, 2)) / scale
+        return bool((err <= 1e-13).all().item())
+
+    def kernel_path(self, order, flags=0):
+        """Which device path `tabulate(order, ...)` takes: 'lattice', 'simplex' or 'tensor'."""
+        if self.kind != "simplex":
+            return "tensor"
+        if flags & (FORCE_GENERAL | FORCE_THREAD_PER_POINT | FORCE_DMMA):
+            return "simplex"
+        return "lattice" if self._lattice_plan(self.desc, order) is not None else "simplex"
+
     def _tensor_plan(self, order, entity):
         ekey = None if entity is None else (tuple(entity[0]) if isinstance(entity[0], (list, tuple)) else entity[0], entity[1])
         key = ("tensor", order, ekey)
@@ -137,12 +186,15 @@ class Tabulator:
             self._plans[key] = out
         return out
 
-    def _resolve(self, order, entity):
+    def _resolve(self, order, entity, flags=0):
         """(plan handle, entity struct or None, nrows, point dimension, result shape prefix)."""
         if order < 0:
             raise ValueError("order must be non-negative")
         if self.kind == "simplex":
             p, prog = self._simplex_plan(self.desc, order)
+            if not (flags & (FORCE_GENERAL | FORCE_THREAD_PER_POINT | FORCE_DMMA)):
+                fast = self._lattice_plan(self.desc, order)
+                p = fast if fast is not None else p
             dim, tr = _resolve_simplex_entity(self.desc, entity)
             ent = _lib.entity_struct(prog.sd, tr)
             return p, ent, prog.nrows, dim, (prog.ndofs,) + prog.value_shape
@@ -162,7 +214,7 @@ class Tabulator:
         return pts.contiguous()
 
     def tabulate(self, order, points, entity=None, flags=0):
-        p, ent, nrows, pdim, prefix = self._resolve(order, entity)
+        p, ent, nrows, pdim, prefix = self._resolve(order, entity, flags)
         pts = self._points(points, pdim)
         npts = pts.shape[0]
         alphas = self.alphas(order)
@@ -173,7 +225,7 @@ class Tabulator:
     def tabulate_into(self, out, order, points, entity=None, flags=0):
         """Streaming form: write into a caller-owned (nalpha, nrows, >=npts) float64 cuda tensor
         (row stride = out.stride(1)); returns the number of points written."""
-        p, ent, nrows, pdim, _ = self._resolve(order, entity)
+        p, ent, nrows, pdim, _ = self._resolve(order, entity, flags)
         pts = self._points(points, pdim)
         npts = pts.shape[0]
         na = len(self.alphas(order))
@@ -196,7 +248,7 @@ class Tabulator:
 
     def tabulate_host(self, order, points, entity=None, chunk_pts=1 << 16, flags=0, out=None):
         """End-to-end with host (numpy) buffers: returns a dict of numpy arrays, like the reference."""
-        p, ent, nrows, pdim, prefix = self._resolve(order, entity)
+        p, ent, nrows, pdim, prefix = self._resolve(order, entity, flags)
         pts = numpy.ascontiguousarray(numpy.asarray(points, dtype=numpy.float64)).reshape(-1, pdim)
         npts = pts.shape[0]
         alphas = self.alphas(order)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "lattice.cuh"
 
 namespace {
 
@@ -29,7 +30,7 @@ int fail(int code, const std::string& msg) {
             return fail(FIATB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-enum PlanKind { PLAN_SIMPLEX = 1, PLAN_TENSOR = 2 };
+enum PlanKind { PLAN_SIMPLEX = 1, PLAN_TENSOR = 2, PLAN_LATTICE = 3 };
 
 }  // namespace
 
@@ -40,6 +41,7 @@ struct fiatb200_plan {
     DevSimplex simplex;
     RecTab tab;             // host copy, passed to kernels by value
     DevTensor tensor;
+    DevLattice lattice;
     int max_smem_optin;
     int num_sms;
 };
@@ -202,6 +204,43 @@ int tabulate_tensor(const fiatb200_plan* plan, const double* pts, long long npts
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
+}
+
+template <int SD, int ORDER>
+int launch_lattice(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
+                   double* out, long long ostride, cudaStream_t st) {
+    const DevLattice& L = plan->lattice;
+    const size_t per_point = (size_t)(SD + 1) * (L.degree + 1) * (ORDER + 1) * sizeof(double);
+    int bp = 128;
+    while (bp > 32 && per_point * bp > 56 * 1024) bp >>= 1;          // keep >= 4 CTAs per SM resident
+    const size_t smem = per_point * bp;
+    if (smem > (size_t)plan->max_smem_optin)
+        return fail(FIATB200_ERR_UNSUPPORTED, "lattice factor tables do not fit in shared memory");
+    int rc = set_smem(k_lattice<SD, ORDER>, smem);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((npts + bp - 1) / bp);
+    k_lattice<SD, ORDER><<<grid, bp, smem, st>>>(L, E, pts, npts, ldp, out, ostride);
+    g_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
+int tabulate_lattice(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts, long long npts,
+                     long long ldp, double* out, long long ostride, cudaStream_t st) {
+    const DevLattice& L = plan->lattice;
+    const DevEntity E = make_entity(entity, L.sd);
+    if (L.sd == 2) {
+        switch (L.order) {
+            case 0: return launch_lattice<2, 0>(plan, E, pts, npts, ldp, out, ostride, st);
+            case 1: return launch_lattice<2, 1>(plan, E, pts, npts, ldp, out, ostride, st);
+            default: return launch_lattice<2, 2>(plan, E, pts, npts, ldp, out, ostride, st);
+        }
+    }
+    switch (L.order) {
+        case 0: return launch_lattice<3, 0>(plan, E, pts, npts, ldp, out, ostride, st);
+        case 1: return launch_lattice<3, 1>(plan, E, pts, npts, ldp, out, ostride, st);
+        default: return launch_lattice<3, 2>(plan, E, pts, npts, ldp, out, ostride, st);
+    }
 }
 
 int device_limits(fiatb200_plan* plan) {
@@ -384,6 +423,37 @@ int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nlea
     return FIATB200_OK;
 }
 
+int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, const int32_t* rowmap, int32_t ndofs,
+                                 fiatb200_plan** out) {
+    if (!rowmap || !out) return fail(FIATB200_ERR_ARG, "null argument");
+    if ((sd != 2 && sd != 3) || order < 0 || order > 2 || degree < 1)
+        return fail(FIATB200_ERR_UNSUPPORTED, "lattice plans cover sd 2..3, order <= 2, degree >= 1");
+    if (ndofs != fb_binom(degree + sd, sd)) return fail(FIATB200_ERR_ARG, "ndofs does not match the lattice");
+    fiatb200_plan* plan = new fiatb200_plan();
+    memset(static_cast<void*>(plan), 0, sizeof(*plan));
+    plan->kind = PLAN_LATTICE;
+    int rc = device_limits(plan);
+    if (rc) { delete plan; return rc; }
+    std::vector<double> recip(degree);
+    for (int k = 0; k < degree; ++k) recip[k] = 1.0 / (double)(k + 1);
+    Arena A;
+    const size_t o_map = A.add(rowmap, sizeof(int32_t) * ndofs);
+    const size_t o_rec = A.add(recip.data(), sizeof(double) * degree);
+    cudaError_t e = cudaMalloc(&plan->blob, A.host.size() + 256);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->blob, A.host.data(), A.host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (plan->blob) cudaFree(plan->blob);
+        delete plan;
+        return fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+    }
+    DevLattice& L = plan->lattice;
+    L.sd = sd; L.degree = degree; L.order = order; L.na = fb_binom(sd + order, order); L.ndofs = ndofs;
+    L.rowmap = at<int>(plan->blob, o_map);
+    L.recip = at<double>(plan->blob, o_rec);
+    *out = plan;
+    return FIATB200_OK;
+}
+
 int fiatb200_plan_destroy(fiatb200_plan* plan) {
     if (!plan) return FIATB200_OK;
     if (plan->blob) cudaFree(plan->blob);
@@ -396,6 +466,9 @@ int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalp
     if (plan->kind == PLAN_SIMPLEX) {
         if (nrows) *nrows = plan->simplex.nrows;
         if (nalpha) *nalpha = plan->simplex.na;
+    } else if (plan->kind == PLAN_LATTICE) {
+        if (nrows) *nrows = plan->lattice.ndofs;
+        if (nalpha) *nalpha = plan->lattice.na;
     } else {
         if (nrows) *nrows = plan->tensor.nrows;
         if (nalpha) *nalpha = plan->tensor.nalpha;
@@ -413,6 +486,8 @@ int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* enti
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (plan->kind == PLAN_SIMPLEX)
         return tabulate_simplex(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, flags, st);
+    if (plan->kind == PLAN_LATTICE)
+        return tabulate_lattice(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, st);
     return tabulate_tensor(plan, pts_dev, npts, pts_ld, out_dev, out_row_stride, st);
 }
 

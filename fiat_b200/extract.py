@@ -193,7 +193,33 @@ def _describe_ciarlet(element):
 
     keys, Cs, offs = _entity_transforms(element.get_reference_element())
     desc["ent_keys"], desc["ent_C"], desc["ent_off"] = keys, Cs, offs
+
+    # Plain point-evaluation dual sets (Lagrange-type elements): keep the nodes.  The plan compiler
+    # uses them to recognise the nodal basis of the principal lattice, which has a closed product
+    # form (fiat_b200/plan.py: lattice_rowmap).
+    desc["vertices"] = numpy.array(complex_.get_vertices(), dtype=float).reshape(-1, sd)
+    nodes = _point_evaluation_nodes(element, sd)
+    if nodes is not None and value_shape == ():
+        desc["nodes"] = nodes
     return desc
+
+
+def _point_evaluation_nodes(element, sd):
+    """(ndofs, sd) evaluation points if every dof is u -> u(x) (functional.py:156-166), else None."""
+    try:
+        dual_nodes = element.dual_basis()
+    except Exception:
+        return None
+    pts = []
+    for node in dual_nodes:
+        pt_dict = getattr(node, "pt_dict", None)
+        if not pt_dict or getattr(node, "deriv_dict", None) or len(pt_dict) != 1:
+            return None
+        (x, terms), = pt_dict.items()
+        if len(terms) != 1 or tuple(terms[0][1]) != () or float(terms[0][0]) != 1.0 or len(x) != sd:
+            return None
+        pts.append([float(v) for v in x])
+    return numpy.array(pts, dtype=float).reshape(-1, sd)
 
 
 def _topology_counts(cell):

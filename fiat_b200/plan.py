@@ -24,7 +24,7 @@ from dataclasses import dataclass, field
 
 import numpy
 
-__all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf"]
+__all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf", "lattice_rowmap"]
 
 EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
 GEOM_DOUBLES = 32      # A[9], b[3] @9, start value @12, dfa[codim][d] @14, dfb[codim][d] @23
@@ -409,6 +409,50 @@ def compile_simplex(desc, order):
         scale = numpy.abs(folded).max() if folded.size else 0.0
         (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = pack_blocks(folded, 1e-14 * scale)
     return prog
+
+
+def lattice_rowmap(desc):
+    """Recognise the nodal basis of the principal lattice on the UFC simplex.
+
+    If the element is scalar, spans the full P_n (ndofs = C(n+sd, sd) = number of expansion
+    members), and its dofs are point evaluations at exactly the points with barycentric
+    coordinates alpha/n, |alpha| = n, then its basis is the Lagrange basis of that lattice, which
+    has the closed form  phi_alpha(lambda) = prod_i l_{alpha_i}(lambda_i),
+    l_k(t) = prod_{j<k} (n t - j)/(j + 1)  -- mathematically the same functions as
+    coeffs . expansion (FIAT/finite_element.py:132-165 solves for exactly these), at a fraction of
+    the arithmetic.  Returns rowmap[loop index] = dof index for the loop nest
+    a0 = 0..n, a1 = 0..n-a0, (a2 = 0..n-a0-a1 in 3-D), or None if the element does not qualify.
+    The caller still verifies the fast path against the general kernel on the device.
+    """
+    if desc.get("kind") != "simplex" or "nodes" not in desc or int(desc["ncells"]) != 1:
+        return None
+    sd, n = int(desc["sd"]), int(desc["degree"])
+    if sd not in (2, 3) or n < 1 or len(desc["value_shape"]) != 0 or desc["expansion"] != "dubiner":
+        return None
+    nodes = numpy.asarray(desc["nodes"], dtype=float)
+    ndofs = math.comb(n + sd, sd)
+    if nodes.shape != (ndofs, sd) or desc["coeffs"].shape != (ndofs, 1, ndofs):
+        return None
+    verts = numpy.asarray(desc["vertices"], dtype=float)
+    ufc = numpy.concatenate([numpy.zeros((1, sd)), numpy.eye(sd)])
+    if verts.shape != ufc.shape or not numpy.array_equal(verts, ufc):
+        return None
+    lam = numpy.concatenate([1.0 - nodes.sum(axis=1, keepdims=True), nodes], axis=1) * n
+    alpha = numpy.rint(lam).astype(numpy.int64)
+    if numpy.abs(lam - alpha).max() > 1e-9 or (alpha < 0).any() or (alpha.sum(axis=1) != n).any():
+        return None
+    where = {tuple(a): i for i, a in enumerate(alpha)}
+    if len(where) != ndofs:
+        return None
+    rowmap = []
+    for a0 in range(n + 1):
+        for a1 in range(n + 1 - a0):
+            if sd == 2:
+                rowmap.append(where[(a0, a1, n - a0 - a1)])
+            else:
+                for a2 in range(n + 1 - a0 - a1):
+                    rowmap.append(where[(a0, a1, a2, n - a0 - a1 - a2)])
+    return numpy.array(rowmap, dtype=numpy.int32)
 
 
 @dataclass

@@ -105,6 +105,13 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* prog, fiatb200_
 int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nleaf, int32_t order,
                                 fiatb200_plan** plan);
 
+/* Product-form plan for the nodal basis of the principal lattice on the UFC simplex (equispaced
+ * Lagrange elements, FIAT/lagrange.py:75-88): same results as the simplex plan of that element at a
+ * fraction of the arithmetic.  rowmap[loop index of (a0, a1[, a2])] = dof index (fiat_b200/plan.py:
+ * lattice_rowmap).  sd in {2, 3}, order <= 2. */
+int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, const int32_t* rowmap,
+                                 int32_t ndofs, fiatb200_plan** plan);
+
 int fiatb200_plan_destroy(fiatb200_plan* plan);
 
 /* Number of result rows per derivative multi-index, and number of multi-indices. */

@@ -92,3 +92,42 @@ def test_tabulate_into_streaming(cuda_device):
         ref = case["ref"][alpha]
         assert abs(buf[j, :, :200].cpu().numpy() - ref).max() <= 1e-12 * abs(ref).max()
     assert torch.isnan(buf[:, :, 200:]).all()
+
+
+@pytest.mark.parametrize("name,expect", [("p8_tet_o2", "lattice"), ("p3_tri_o1", "lattice"), ("p1_tri_o2", "lattice"),
+                                         ("p4_tet_face2_o2", "lattice"), ("p5_tet_o3", "simplex"),
+                                         ("dg3_tri_o1", "lattice"), ("cr_tri_o1", "simplex"), ("n2curl4_tet_o1", "simplex"),
+                                         ("hct_o2", "simplex"), ("gll_q10_hex_o1", "tensor")])
+def test_kernel_selection_and_parity(name, expect, cuda_device):
+    """Equispaced Lagrange elements take the product-form kernel (after its on-device self-check);
+    everything else the general kernels.  Both must match the reference."""
+    from fiat_b200.api import Tabulator, FORCE_GENERAL
+    case = load_case(name)
+    tab = Tabulator(case["desc"], cuda_device)
+    assert tab.kernel_path(case["order"]) == expect
+    _compare(case["desc"], tab.tabulate(case["order"], case["points"], case["entity"]), case["ref"])
+    if expect == "lattice":
+        _compare(case["desc"], tab.tabulate(case["order"], case["points"], case["entity"], flags=FORCE_GENERAL),
+                 case["ref"])
+
+
+def test_full_size_properties_p8(cuda_device):
+    """Size-independent properties at bench scale: partition of unity (values sum to 1, every
+    derivative of the sum vanishes) for 2^17 points on both kernel paths."""
+    from conftest import load_desc
+    from fiat_b200.api import Tabulator, FORCE_GENERAL
+    desc = load_desc("p8_tet")
+    tab = Tabulator(desc, cuda_device)
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(5)
+    u, _ = torch.sort(torch.rand((1 << 17, 3), generator=g, device=cuda_device, dtype=torch.float64), dim=1)
+    pts = torch.diff(torch.cat([torch.zeros((1 << 17, 1), device=cuda_device, dtype=torch.float64), u], dim=1), dim=1)
+    for flags in (0, FORCE_GENERAL):
+        got = tab.tabulate(2, pts, flags=flags)
+        for alpha, v in got.items():
+            total = v.sum(dim=0)
+            target = 1.0 if sum(alpha) == 0 else 0.0
+            assert (total - target).abs().max().item() <= 1e-9 * max(1.0, v.abs().max().item())
+    a, b = tab.tabulate(2, pts), tab.tabulate(2, pts, flags=FORCE_GENERAL)
+    for alpha in a:
+        assert (a[alpha] - b[alpha]).abs().max().item() <= 1e-12 * b[alpha].abs().max().item()
