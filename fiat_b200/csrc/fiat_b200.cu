@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,13 @@ struct fiatb200_plan {
     DevLattice lattice;
     int max_smem_optin;
     int num_sms;
+    // staging for fiatb200_tabulate_host: two streams with one points/result buffer each, kept
+    // across calls so that the end-to-end path issues no allocation or stream creation per call
+    std::mutex host_mutex;
+    cudaStream_t host_stream[2];
+    double* host_pts[2];
+    double* host_out[2];
+    size_t host_pts_cap, host_out_cap;
 };
 
 namespace {
@@ -243,6 +251,30 @@ int tabulate_lattice(const fiatb200_plan* plan, const fiatb200_entity_map* entit
     }
 }
 
+fiatb200_plan* new_plan() {
+    fiatb200_plan* plan = new fiatb200_plan();
+    plan->kind = 0; plan->device = 0; plan->blob = nullptr;
+    memset(&plan->simplex, 0, sizeof(plan->simplex));
+    memset(&plan->tab, 0, sizeof(plan->tab));
+    memset(&plan->tensor, 0, sizeof(plan->tensor));
+    memset(&plan->lattice, 0, sizeof(plan->lattice));
+    plan->max_smem_optin = plan->num_sms = 0;
+    for (int i = 0; i < 2; ++i) { plan->host_stream[i] = nullptr; plan->host_pts[i] = nullptr; plan->host_out[i] = nullptr; }
+    plan->host_pts_cap = plan->host_out_cap = 0;
+    return plan;
+}
+
+void free_staging(fiatb200_plan* plan) {
+    for (int i = 0; i < 2; ++i) {
+        if (plan->host_pts[i]) cudaFree(plan->host_pts[i]);
+        if (plan->host_out[i]) cudaFree(plan->host_out[i]);
+        if (plan->host_stream[i]) cudaStreamDestroy(plan->host_stream[i]);
+        plan->host_pts[i] = plan->host_out[i] = nullptr;
+        plan->host_stream[i] = nullptr;
+    }
+    plan->host_pts_cap = plan->host_out_cap = 0;
+}
+
 int device_limits(fiatb200_plan* plan) {
     FB_CUDA(cudaGetDevice(&plan->device));
     FB_CUDA(cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device));
@@ -266,8 +298,7 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     if (h->ncells < 1 || h->ncells > 32) return fail(FIATB200_ERR_UNSUPPORTED, "at most 32 subcells are supported");
     if (h->na < 1 || h->na > FB_NA_MAX) return fail(FIATB200_ERR_UNSUPPORTED, "derivative order too high");
     if (h->expansion != 0 && h->sd != 1) return fail(FIATB200_ERR_ARG, "line expansion on a non-line cell");
-    fiatb200_plan* plan = new fiatb200_plan();
-    memset(static_cast<void*>(plan), 0, sizeof(*plan));
+    fiatb200_plan* plan = new_plan();
     plan->kind = PLAN_SIMPLEX;
     int rc = device_limits(plan);
     if (rc) { delete plan; return rc; }
@@ -342,8 +373,7 @@ int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nlea
     if (!leaves || !out) return fail(FIATB200_ERR_ARG, "null argument");
     if (nleaf < 1 || nleaf > FB_MAX_LEAVES)
         return fail(FIATB200_ERR_UNSUPPORTED, "tensor-product elements with 1..4 scalar factors are supported");
-    fiatb200_plan* plan = new fiatb200_plan();
-    memset(static_cast<void*>(plan), 0, sizeof(*plan));
+    fiatb200_plan* plan = new_plan();
     plan->kind = PLAN_TENSOR;
     int rc = device_limits(plan);
     if (rc) { delete plan; return rc; }
@@ -429,8 +459,7 @@ int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, cons
     if ((sd != 2 && sd != 3) || order < 0 || order > 2 || degree < 1)
         return fail(FIATB200_ERR_UNSUPPORTED, "lattice plans cover sd 2..3, order <= 2, degree >= 1");
     if (ndofs != fb_binom(degree + sd, sd)) return fail(FIATB200_ERR_ARG, "ndofs does not match the lattice");
-    fiatb200_plan* plan = new fiatb200_plan();
-    memset(static_cast<void*>(plan), 0, sizeof(*plan));
+    fiatb200_plan* plan = new_plan();
     plan->kind = PLAN_LATTICE;
     int rc = device_limits(plan);
     if (rc) { delete plan; return rc; }
@@ -456,6 +485,7 @@ int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, cons
 
 int fiatb200_plan_destroy(fiatb200_plan* plan) {
     if (!plan) return FIATB200_OK;
+    free_staging(plan);
     if (plan->blob) cudaFree(plan->blob);
     delete plan;
     return FIATB200_OK;
@@ -510,45 +540,49 @@ int fiatb200_locate_subcells(const fiatb200_plan* plan, const fiatb200_entity_ma
     return FIATB200_OK;
 }
 
-int fiatb200_tabulate_host(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_host,
+int fiatb200_tabulate_host(const fiatb200_plan* cplan, const fiatb200_entity_map* entity, const double* pts_host,
                            int64_t npts, int64_t pts_ld, double* out_host, int64_t chunk_pts, uint32_t flags) {
-    if (!plan) return fail(FIATB200_ERR_ARG, "null plan");
+    if (!cplan) return fail(FIATB200_ERR_ARG, "null plan");
     if (npts == 0) return FIATB200_OK;
     if ((!pts_host && pts_ld != 0) || !out_host || chunk_pts <= 0)
         return fail(FIATB200_ERR_ARG, "bad host buffers / chunk size");
+    fiatb200_plan* plan = const_cast<fiatb200_plan*>(cplan);
+    std::lock_guard<std::mutex> guard(plan->host_mutex);
     int64_t nrows = 0, nalpha = 0;
     fiatb200_plan_shape(plan, &nrows, &nalpha);
     const int64_t rows = nrows * nalpha;
     chunk_pts = std::min<int64_t>(chunk_pts, npts);
     chunk_pts = (chunk_pts + 7) & ~int64_t(7);
-    cudaStream_t st[2];
-    double* d_pts[2] = {nullptr, nullptr};
-    double* d_out[2] = {nullptr, nullptr};
-    int rc = FIATB200_OK;
-    for (int i = 0; i < 2; ++i) {
-        FB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-        FB_CUDA(cudaMalloc(&d_pts[i], sizeof(double) * chunk_pts * std::max<int64_t>(pts_ld, 1)));
-        FB_CUDA(cudaMalloc(&d_out[i], sizeof(double) * chunk_pts * rows));
+    const size_t need_pts = sizeof(double) * chunk_pts * std::max<int64_t>(pts_ld, 1);
+    const size_t need_out = sizeof(double) * chunk_pts * rows;
+    if (!plan->host_stream[0] || need_pts > plan->host_pts_cap || need_out > plan->host_out_cap) {
+        free_staging(plan);
+        for (int i = 0; i < 2; ++i) {
+            FB_CUDA(cudaStreamCreateWithFlags(&plan->host_stream[i], cudaStreamNonBlocking));
+            FB_CUDA(cudaMalloc(&plan->host_pts[i], need_pts));
+            FB_CUDA(cudaMalloc(&plan->host_out[i], need_out));
+        }
+        plan->host_pts_cap = need_pts;
+        plan->host_out_cap = need_out;
     }
+    int rc = FIATB200_OK;
     int64_t done = 0;
     for (int it = 0; done < npts && rc == FIATB200_OK; ++it, done += chunk_pts) {
         const int b = it & 1;
+        cudaStream_t st = plan->host_stream[b];
         const int64_t n = std::min<int64_t>(chunk_pts, npts - done);
         if (pts_ld > 0)
-            FB_CUDA(cudaMemcpyAsync(d_pts[b], pts_host + done * pts_ld, sizeof(double) * n * pts_ld,
-                                    cudaMemcpyHostToDevice, st[b]));
-        rc = fiatb200_tabulate(plan, entity, d_pts[b], n, pts_ld, d_out[b], chunk_pts, flags, st[b]);
+            FB_CUDA(cudaMemcpyAsync(plan->host_pts[b], pts_host + done * pts_ld, sizeof(double) * n * pts_ld,
+                                    cudaMemcpyHostToDevice, st));
+        rc = fiatb200_tabulate(plan, entity, plan->host_pts[b], n, pts_ld, plan->host_out[b], chunk_pts, flags, st);
         if (rc) break;
         // rows of the chunk land at column offset `done` of the (rows x npts) host result
-        FB_CUDA(cudaMemcpy2DAsync(out_host + done, sizeof(double) * npts, d_out[b], sizeof(double) * chunk_pts,
-                                  sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st[b]));
+        FB_CUDA(cudaMemcpy2DAsync(out_host + done, sizeof(double) * npts, plan->host_out[b], sizeof(double) * chunk_pts,
+                                  sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < 2; ++i) {
-        cudaError_t e = cudaStreamSynchronize(st[i]);
+        cudaError_t e = cudaStreamSynchronize(plan->host_stream[i]);
         if (e != cudaSuccess && rc == FIATB200_OK) rc = fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
-        cudaFree(d_pts[i]);
-        cudaFree(d_out[i]);
-        cudaStreamDestroy(st[i]);
     }
     return rc;
 }

@@ -450,9 +450,11 @@ def _tabulate_simplex(desc, order, pts, entity):
     base = expansion_tabulate(desc, pts, order)              # (nexp, nalpha, npts)
     coeffs = desc["coeffs"]                                   # (ndofs, ncomp, nexp)
     vs = tuple(int(s) for s in desc["value_shape"])
+    flat = numpy.ascontiguousarray(coeffs.reshape(-1, coeffs.shape[-1]))
     result = {}
     for j, alpha in enumerate(all_alphas(sd, order)):
-        vals = numpy.dot(coeffs, base[:, j, :])               # polynomial_set.py:71
+        # polynomial_set.py:71 -- same contraction, laid out so that numpy hands it to dgemm
+        vals = numpy.dot(flat, numpy.ascontiguousarray(base[:, j, :]))
         result[alpha] = vals.reshape((coeffs.shape[0],) + vs + (pts.shape[0],))
     return result
 
