@@ -263,6 +263,23 @@ __device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double*
     }
 }
 
+// Fused outer product over the leaf tables of one point: value = prod_l tab[l][i_l], global dof
+// index ((i0 * n1 + i1) * n2 + i2) * n3 + i3 (FIAT/tensor_product.py:288-292), rows streamed in order.
+template <int L, int NL>
+__device__ __forceinline__ void emit_products(double f, const double* const (&tab)[FB_MAX_LEAVES],
+                                              const int (&n)[FB_MAX_LEAVES], int BP, double*& o, long long ostride) {
+    const double* t = tab[L];
+    if constexpr (L == NL - 1) {
+#pragma unroll 4
+        for (int i = 0; i < n[L]; ++i) {
+            *o = f * t[(size_t)i * BP];
+            o += ostride;
+        }
+    } else {
+        for (int i = 0; i < n[L]; ++i) emit_products<L + 1, NL>(f * t[(size_t)i * BP], tab, n, BP, o, ostride);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_tensor(const DevTensor Q, const double* __restrict__ pts, long long npts, long long ldp,
          double* __restrict__ out, long long ostride) {
@@ -281,36 +298,22 @@ k_tensor(const DevTensor Q, const double* __restrict__ pts, long long npts, long
         else leaf_table<3>(L, pt, scratch, table, BP);
     }
     int n[FB_MAX_LEAVES];
-    const double* tab[FB_MAX_LEAVES];
 #pragma unroll
-    for (int l = 0; l < FB_MAX_LEAVES; ++l) {
-        n[l] = l < Q.nleaf ? Q.leaf[l].prog.nrows : 1;
-        tab[l] = smem + (size_t)(l < Q.nleaf ? Q.leaf[l].table_off : 0) * BP + tid;
-    }
+    for (int l = 0; l < FB_MAX_LEAVES; ++l) n[l] = l < Q.nleaf ? Q.leaf[l].prog.nrows : 1;
     for (int al = 0; al < Q.nalpha; ++al) {
         const int* aidx = Q.alpha_leaf + al * FB_MAX_LEAVES;
-        const double* t0 = tab[0] + (size_t)__ldg(aidx + 0) * n[0] * BP;
-        const double* t1 = tab[1] + (size_t)(Q.nleaf > 1 ? __ldg(aidx + 1) : 0) * n[1] * BP;
-        const double* t2 = tab[2] + (size_t)(Q.nleaf > 2 ? __ldg(aidx + 2) : 0) * n[2] * BP;
-        const double* t3 = tab[3] + (size_t)(Q.nleaf > 3 ? __ldg(aidx + 3) : 0) * n[3] * BP;
+        const double* tab[FB_MAX_LEAVES];
+#pragma unroll
+        for (int l = 0; l < FB_MAX_LEAVES; ++l) {
+            const int lo = l < Q.nleaf ? l : 0;
+            tab[l] = smem + ((size_t)Q.leaf[lo].table_off + (size_t)__ldg(aidx + lo) * n[lo]) * BP + tid;
+        }
         double* o = out + (size_t)al * Q.nrows * ostride + p;
-        for (int i0 = 0; i0 < n[0]; ++i0) {
-            const double f0 = t0[(size_t)i0 * BP];
-            for (int i1 = 0; i1 < n[1]; ++i1) {
-                const double f1 = Q.nleaf > 1 ? f0 * t1[(size_t)i1 * BP] : f0;
-                for (int i2 = 0; i2 < n[2]; ++i2) {
-                    const double f2 = Q.nleaf > 2 ? f1 * t2[(size_t)i2 * BP] : f1;
-                    if (Q.nleaf > 3) {
-                        for (int i3 = 0; i3 < n[3]; ++i3) {
-                            *o = f2 * t3[(size_t)i3 * BP];
-                            o += ostride;
-                        }
-                    } else {
-                        *o = f2;
-                        o += ostride;
-                    }
-                }
-            }
+        switch (Q.nleaf) {
+            case 1: emit_products<0, 1>(1.0, tab, n, BP, o, ostride); break;
+            case 2: emit_products<0, 2>(1.0, tab, n, BP, o, ostride); break;
+            case 3: emit_products<0, 3>(1.0, tab, n, BP, o, ostride); break;
+            default: emit_products<0, 4>(1.0, tab, n, BP, o, ostride); break;
         }
     }
 }
