@@ -337,11 +337,10 @@ __device__ __forceinline__ void lagrange_line_point(const DevSimplex& P, int cel
 
 // Expansion table of one (sub)cell at one point into the thread's column of T.
 template <int SD, int ORDER>
-__device__ __forceinline__ void expansion_point(const DevSimplex& P, const RecTab& tab, int cell, double inv_mult,
-                                                const double (&x)[3], double* __restrict__ T, int slot_stride,
-                                                int comp_stride, int na) {
+__device__ __forceinline__ void expansion_point(const DevSimplex& P, const RecTab& tab, const double* __restrict__ geom,
+                                                int cell, double inv_mult, const double (&x)[3],
+                                                double* __restrict__ T, int slot_stride, int comp_stride, int na) {
     if (P.expansion == 0) {
-        const double* geom = P.geom + cell * FB_GEOM_DOUBLES;
         double xr[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int i = 0; i < SD; ++i) {

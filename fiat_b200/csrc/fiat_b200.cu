@@ -104,13 +104,17 @@ int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double*
     int bp = 128;
     while (bp > 32 && per_point * bp > 96 * 1024) bp >>= 1;
     while (bp > 8 && per_point * bp > (size_t)plan->max_smem_optin) bp >>= 1;
-    const size_t smem = per_point * bp;
+    size_t smem = per_point * bp;
+    // small coefficient / geometry tables ride along in shared memory
+    const size_t table_bytes = ((size_t)P.ncells * P.nrows * P.nslots + (size_t)P.ncells * FB_GEOM_DOUBLES) * sizeof(double);
+    const int tables_in_smem = (table_bytes <= 32 * 1024 && smem + table_bytes <= (size_t)plan->max_smem_optin) ? 1 : 0;
+    if (tables_in_smem) smem += table_bytes;
     if (smem > (size_t)plan->max_smem_optin)
         return fail(FIATB200_ERR_UNSUPPORTED, "expansion table of one point tile does not fit in shared memory");
     int rc = set_smem(k_cellwise<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, plan->tab, E, pts, npts, ldp, out, ostride);
+    k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, plan->tab, E, pts, npts, ldp, out, ostride, tables_in_smem);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;

@@ -22,15 +22,29 @@
 template <int SD, int ORDER>
 __global__ void __launch_bounds__(128)
 k_cellwise(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const double* __restrict__ pts,
-           long long npts, long long ldp, double* __restrict__ out, long long ostride) {
+           long long npts, long long ldp, double* __restrict__ out, long long ostride, int tables_in_smem) {
     extern __shared__ double smem[];
     const int BP = blockDim.x;
     const int tid = threadIdx.x;
     const long long p = (long long)blockIdx.x * BP + tid;
-    if (p >= npts) return;
     const int na = (ORDER >= 0) ? Jet<SD, ORDER>::CAP : P.na;
     double* T = smem + tid;
     const int comp_stride = BP, slot_stride = na * BP;
+
+    // per-subcell coefficient matrices and geometry: shared memory when they fit (split cells pick
+    // them per thread), global memory otherwise
+    const double* Call = P.ccell;
+    const double* geom_all = P.geom;
+    if (tables_in_smem) {
+        double* s_C = smem + (size_t)P.nslots * na * BP;
+        double* s_g = s_C + (size_t)P.ncells * P.nrows * P.nslots;
+        for (int i = tid; i < P.ncells * P.nrows * P.nslots; i += BP) s_C[i] = __ldg(P.ccell + i);
+        for (int i = tid; i < P.ncells * FB_GEOM_DOUBLES; i += BP) s_g[i] = __ldg(P.geom + i);
+        __syncthreads();
+        Call = s_C;
+        geom_all = s_g;
+    }
+    if (p >= npts) return;
 
     double x[3];
     apply_entity<SD>(E, pts + p * ldp, x);
@@ -40,31 +54,51 @@ k_cellwise(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEnti
     while (mask) {
         const int cell = __ffs(mask) - 1;
         mask &= mask - 1;
-        expansion_point<SD, ORDER>(P, tab, cell, inv_mult, x, T, slot_stride, comp_stride, na);
-        const double* C = P.ccell + (size_t)cell * P.nrows * P.nslots;
-        for (int r = 0; r < P.nrows; ++r) {
-            const double* Cr = C + (size_t)r * P.nslots;
-            if (ORDER >= 0) {
-                double acc[Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP];
+        expansion_point<SD, ORDER>(P, tab, geom_all + cell * FB_GEOM_DOUBLES, cell, inv_mult, x, T, slot_stride,
+                                   comp_stride, na);
+        const double* C = Call + (size_t)cell * P.nrows * P.nslots;
+        if (ORDER >= 0) {
+            // register tile: RB rows x NA derivative components; T is read once per row block
+            constexpr int NA = Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP;
+            constexpr int RB = 4;
+            for (int r0 = 0; r0 < P.nrows; r0 += RB) {
+                double acc[RB][NA];
 #pragma unroll
-                for (int a = 0; a < Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP; ++a) acc[a] = 0.0;
+                for (int j = 0; j < RB; ++j)
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) acc[j][a] = 0.0;
+                const double* Cr[RB];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) Cr[j] = C + (size_t)min(r0 + j, P.nrows - 1) * P.nslots;
                 for (int k = 0; k < P.nslots; ++k) {
-                    const double c = __ldg(Cr + k);
-                    const double* t = T + (size_t)k * slot_stride;
+                    double t[NA];
+                    const double* tk = T + (size_t)k * slot_stride;
 #pragma unroll
-                    for (int a = 0; a < Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP; ++a)
-                        acc[a] = fma(c, t[a * comp_stride], acc[a]);
+                    for (int a = 0; a < NA; ++a) t[a] = tk[a * comp_stride];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const double c = Cr[j][k];
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) acc[j][a] = fma(c, t[a], acc[j][a]);
+                    }
                 }
 #pragma unroll
-                for (int a = 0; a < Jet<SD, (ORDER >= 0 ? ORDER : 0)>::CAP; ++a) {
-                    double* o = out + ((size_t)a * P.nrows + r) * ostride + p;
-                    *o = first ? acc[a] : (*o + acc[a]);
+                for (int j = 0; j < RB; ++j) {
+                    if (r0 + j < P.nrows) {
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) {
+                            double* o = out + ((size_t)a * P.nrows + r0 + j) * ostride + p;
+                            *o = first ? acc[j][a] : (*o + acc[j][a]);
+                        }
+                    }
                 }
-            } else {
+            }
+        } else {
+            for (int r = 0; r < P.nrows; ++r) {
+                const double* Cr = C + (size_t)r * P.nslots;
                 for (int a = 0; a < na; ++a) {
                     double acc = 0.0;
-                    for (int k = 0; k < P.nslots; ++k)
-                        acc = fma(__ldg(Cr + k), T[(size_t)k * slot_stride + a * comp_stride], acc);
+                    for (int k = 0; k < P.nslots; ++k) acc = fma(Cr[k], T[(size_t)k * slot_stride + a * comp_stride], acc);
                     double* o = out + ((size_t)a * P.nrows + r) * ostride + p;
                     *o = first ? acc : (*o + acc);
                 }
@@ -248,7 +282,7 @@ __device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double*
     while (mask) {
         const int cell = __ffs(mask) - 1;
         mask &= mask - 1;
-        expansion_point<SD, -1>(P, *P.tab, cell, inv_mult, x, scratch, na * BP, BP, na);
+        expansion_point<SD, -1>(P, *P.tab, P.geom + cell * FB_GEOM_DOUBLES, cell, inv_mult, x, scratch, na * BP, BP, na);
         const double* C = P.ccell + (size_t)cell * P.nrows * P.nslots;
         for (int r = 0; r < P.nrows; ++r) {
             for (int a = 0; a < na; ++a) {
