@@ -20,9 +20,9 @@ class SimplexProgramStruct(ctypes.Structure):
         ("sd", c_i32), ("degree", c_i32), ("order", c_i32), ("na", c_i32), ("expansion", c_i32),
         ("ncells", c_i32), ("nslots", c_i32), ("nrows", c_i32), ("unique", c_i32),
         ("nsteps", c_i32), ("nlevels", c_i32), ("nfix", c_i32), ("nfixgrp", c_i32), ("line_n", c_i32),
-        ("step_idx", p_i32), ("step_abc", p_dbl), ("level_ptr", p_i32),
+        ("step_idx", p_i32), ("step_abc", p_dbl), ("nat_abc", p_dbl), ("level_ptr", p_i32),
         ("fix_idx", p_i32), ("fix_w", p_dbl), ("fix_grp", p_i32),
-        ("geom", p_dbl), ("bary", p_dbl), ("ccell", p_dbl),
+        ("geom", p_dbl), ("bary", p_dbl), ("ccell", p_dbl), ("ccell_morton", p_dbl),
         ("low1", p_i32), ("mul1", p_dbl), ("low2", p_i32), ("mul2", p_dbl),
         ("line_tab", p_dbl), ("line_tab_len", c_i64),
         ("nrb", c_i32), ("kpad", c_i32), ("nblk", c_i32),
@@ -108,6 +108,7 @@ def simplex_struct(prog):
     s.nsteps, s.nlevels, s.nfix, s.line_n = len(prog.step_idx), len(prog.level_ptr) - 1, len(prog.fix_idx), prog.line_n
     s.nfixgrp = len(prog.fix_grp)
     s.step_idx, s.step_abc, s.level_ptr = i32(prog.step_idx), f64(prog.step_abc), i32(prog.level_ptr)
+    s.nat_abc, s.ccell_morton = f64(prog.nat_abc), f64(prog.ccell_morton)
     s.fix_idx, s.fix_w, s.fix_grp = i32(prog.fix_idx), f64(prog.fix_w), i32(prog.fix_grp)
     s.geom, s.bary, s.ccell = f64(prog.geom), f64(prog.bary), f64(prog.ccell)
     s.low1, s.mul1, s.low2, s.mul2 = i32(prog.low1), f64(prog.mul1), i32(prog.low2), f64(prog.mul2)

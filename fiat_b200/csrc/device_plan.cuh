@@ -36,6 +36,7 @@ struct DevSimplex {
     const double* geom;
     const double* bary;
     const double* ccell;
+    const double* ccell_morton;
     const int* low1;
     const double* mul1;
     const int* low2;

@@ -13,6 +13,7 @@
 
 #include "kernels.cuh"
 #include "lattice.cuh"
+#include "small.cuh"
 
 namespace {
 
@@ -41,6 +42,7 @@ struct fiatb200_plan {
     void* blob;             // one device allocation holding every table
     DevSimplex simplex;
     RecTab tab;             // host copy, passed to kernels by value
+    SmallTab small_tab;     // generation-order coefficients for the register kernel
     DevTensor tensor;
     DevLattice lattice;
     int max_smem_optin;
@@ -131,6 +133,50 @@ int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const doubl
     }
 }
 
+// ---- register kernel for low-degree elements ------------------------------------------------------
+template <int SD, int N, int ORDER>
+int launch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
+                 double* out, long long ostride, cudaStream_t st) {
+    const DevSimplex& P = plan->simplex;
+    const size_t smem = ((size_t)P.ncells * P.nrows * P.nslots + (size_t)P.ncells * FB_GEOM_DOUBLES) * sizeof(double);
+    int rc = set_smem(k_small<SD, N, ORDER>, smem);
+    if (rc) return rc;
+    const int bp = 128;
+    const unsigned grid = (unsigned)((npts + bp - 1) / bp);
+    k_small<SD, N, ORDER><<<grid, bp, smem, st>>>(P, plan->small_tab, E, pts, npts, ldp, out, ostride);
+    g_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
+// (sd, degree, order) combinations whose expansion table fits in registers (members x alphas <= 64)
+bool small_applicable(const fiatb200_plan* plan) {
+    const DevSimplex& P = plan->simplex;
+    if (P.expansion != 0 || P.order > 2 || P.degree < 1 || P.sd < 2) return false;
+    if ((size_t)P.nslots * P.na > 64) return false;
+    if (P.sd == 2 && P.degree > 4) return false;
+    if (P.sd == 3 && P.degree > 3) return false;
+    const size_t smem = ((size_t)P.ncells * P.nrows * P.nslots + (size_t)P.ncells * FB_GEOM_DOUBLES) * sizeof(double);
+    return smem <= 64 * 1024;
+}
+
+#define FB_SMALL_CASE(SD_, N_, O_)                                                        \
+    if (P.sd == SD_ && P.degree == N_ && P.order == O_)                                   \
+        return launch_small<SD_, N_, O_>(plan, E, pts, npts, ldp, out, ostride, st);
+
+int dispatch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
+                   double* out, long long ostride, cudaStream_t st) {
+    const DevSimplex& P = plan->simplex;
+    FB_SMALL_CASE(2, 1, 0) FB_SMALL_CASE(2, 1, 1) FB_SMALL_CASE(2, 1, 2)
+    FB_SMALL_CASE(2, 2, 0) FB_SMALL_CASE(2, 2, 1) FB_SMALL_CASE(2, 2, 2)
+    FB_SMALL_CASE(2, 3, 0) FB_SMALL_CASE(2, 3, 1) FB_SMALL_CASE(2, 3, 2)
+    FB_SMALL_CASE(2, 4, 0) FB_SMALL_CASE(2, 4, 1)
+    FB_SMALL_CASE(3, 1, 0) FB_SMALL_CASE(3, 1, 1) FB_SMALL_CASE(3, 1, 2)
+    FB_SMALL_CASE(3, 2, 0) FB_SMALL_CASE(3, 2, 1)
+    FB_SMALL_CASE(3, 3, 0)
+    return fail(FIATB200_ERR_UNSUPPORTED, "register kernel not instantiated for this element");
+}
+
 // ---- tile / DMMA launch ------------------------------------------------------------------------
 bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     const DevSimplex& P = plan->simplex;
@@ -187,6 +233,8 @@ int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entit
     if (use_mma && !(flags & 2u) && (long long)P.nrows * P.nslots < 256) use_mma = false;
     if (flags & 1u) use_mma = false;
     if ((flags & 2u) && !use_mma) return fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
+    // low-degree elements (and all split-cell ones of low degree): everything in registers
+    if (!(flags & 3u) && small_applicable(plan)) return dispatch_small(plan, E, pts, npts, ldp, out, ostride, st);
     if (use_mma) {
         switch (P.sd) {
             case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
@@ -260,6 +308,7 @@ fiatb200_plan* new_plan() {
     plan->kind = 0; plan->device = 0; plan->blob = nullptr;
     memset(&plan->simplex, 0, sizeof(plan->simplex));
     memset(&plan->tab, 0, sizeof(plan->tab));
+    memset(&plan->small_tab, 0, sizeof(plan->small_tab));
     memset(&plan->tensor, 0, sizeof(plan->tensor));
     memset(&plan->lattice, 0, sizeof(plan->lattice));
     plan->max_smem_optin = plan->num_sms = 0;
@@ -326,12 +375,16 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
         R.fix_tgt[g] = (short)h->fix_idx[2 * h->fix_grp[2 * g]];
     }
     for (int i = 0; i < FB_GEOM_DOUBLES; ++i) R.geom0[i] = h->geom[i];
+    memset(&plan->small_tab, 0, sizeof(plan->small_tab));
+    for (int i = 0; i < h->nsteps && i < FB_SMALL_MAX_STEPS; ++i)
+        for (int j = 0; j < 3; ++j) plan->small_tab.abc[i][j] = h->nat_abc[3 * i + j];
 
     Arena A;
     const size_t o_tab = A.add(&R, sizeof(RecTab));
     const size_t o_geom = A.add(h->geom, sizeof(double) * FB_GEOM_DOUBLES * h->ncells);
     const size_t o_bary = A.add(h->bary, sizeof(double) * 16 * (h->ncells + 1));
     const size_t o_ccell = A.add(h->ccell, sizeof(double) * (size_t)h->ncells * h->nrows * h->nslots);
+    const size_t o_ccellm = A.add(h->ccell_morton, sizeof(double) * (size_t)h->ncells * h->nrows * h->nslots);
     const size_t o_low1 = A.add(h->low1, sizeof(int32_t) * 3 * h->na);
     const size_t o_mul1 = A.add(h->mul1, sizeof(double) * 3 * h->na);
     const size_t o_low2 = A.add(h->low2, sizeof(int32_t) * 6 * h->na);
@@ -358,6 +411,7 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     P.geom = at<double>(b, o_geom);
     P.bary = at<double>(b, o_bary);
     P.ccell = at<double>(b, o_ccell);
+    P.ccell_morton = at<double>(b, o_ccellm);
     P.low1 = at<int>(b, o_low1);
     P.mul1 = at<double>(b, o_mul1);
     P.low2 = at<int>(b, o_low2);

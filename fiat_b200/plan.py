@@ -202,6 +202,8 @@ class SimplexProgram:
     bary: numpy.ndarray         # (ncells + 1, 4, 4): rows of A_hat | b_hat
     step_idx: numpy.ndarray     # (nsteps, 4) int32: next, cur, prev(-1 = first of chain), codim; level order
     step_abc: numpy.ndarray     # (nsteps, 3) Jacobi recurrence coefficients a, b, c
+    nat_abc: numpy.ndarray      # (nsteps, 3) the same coefficients in generation order (pass, sub-index, i)
+    ccell_morton: numpy.ndarray  # (ncells, nrows, nslots) coefficients on Morton-numbered members, fix-ups folded
     level_ptr: numpy.ndarray    # (degree + 1,) int32: steps producing degree d+1 are [level_ptr[d], level_ptr[d+1])
     fix_idx: numpy.ndarray      # (nfix, 2) int32 target, source slots
     fix_w: numpy.ndarray        # (nfix,)
@@ -249,6 +251,7 @@ def _dubiner_tables(desc, order):
                     step_level.append(sum(sub) + i + 1)      # total degree of the member produced
     step_idx = numpy.array(step_idx, dtype=numpy.int32).reshape(-1, 4)
     step_abc = numpy.array(step_abc, dtype=float).reshape(-1, 3)
+    nat_abc = step_abc.copy()
     # wavefront order: a member of total degree d only needs members of degree d-1 and d-2
     step_level = numpy.array(step_level, dtype=numpy.int64)
     by_level = numpy.argsort(step_level, kind="stable")
@@ -285,7 +288,8 @@ def _dubiner_tables(desc, order):
             fix_w.append(norm[s] / norm[t])
     fold_by_slot = numpy.empty(nmem)
     fold_by_slot[slot_of] = fold
-    return dict(nslots=nmem, step_idx=step_idx, step_abc=step_abc, geom=geom, level_ptr=level_ptr,
+    return dict(nslots=nmem, step_idx=step_idx, step_abc=step_abc, nat_abc=nat_abc, slot_of=slot_of,
+                geom=geom, level_ptr=level_ptr,
                 fix_idx=numpy.array(fix_idx, dtype=numpy.int32).reshape(-1, 2),
                 fix_w=numpy.array(fix_w, dtype=float), fold_by_slot=fold_by_slot)
 
@@ -371,7 +375,8 @@ def compile_simplex(desc, order):
         t = _line_tables(desc, order)
         fold = numpy.ones(t["nslots"])
         line_tab, line_n = t["line_tab"], t["line_n"]
-        t.update(step_idx=numpy.zeros((0, 4), numpy.int32), step_abc=numpy.zeros((0, 3)),
+        t.update(step_idx=numpy.zeros((0, 4), numpy.int32), step_abc=numpy.zeros((0, 3)), nat_abc=numpy.zeros((0, 3)),
+                 slot_of=numpy.arange(t["nslots"]),
                  level_ptr=numpy.zeros(1, numpy.int32),
                  fix_idx=numpy.zeros((0, 2), numpy.int32), fix_w=numpy.zeros(0))
     nslots = t["nslots"]
@@ -388,6 +393,14 @@ def compile_simplex(desc, order):
     targets, first, count = numpy.unique(t["fix_idx"][:, 0], return_index=True, return_counts=True)
     fix_grp = numpy.stack([first, count], axis=1).astype(numpy.int32).reshape(-1, 2)
 
+    # register kernel: members stay Morton-numbered and no fix-up pass runs, so fold both into C
+    ccell_morton = numpy.empty_like(ccell)
+    for c in range(ncells):
+        folded = ccell[c].copy()
+        for (tgt, src), w in zip(t["fix_idx"], t["fix_w"]):
+            folded[:, src] -= w * ccell[c][:, tgt]
+        ccell_morton[c] = folded[:, t["slot_of"]]
+
     bary = numpy.zeros((ncells + 1, 4, 4))
     if ncells > 1:
         bary[:, :sd + 1, :sd] = desc["bary_A"]
@@ -399,6 +412,7 @@ def compile_simplex(desc, order):
         value_shape=tuple(int(s) for s in desc["value_shape"]),
         unique=int(bool(desc["c0"]) and order == 0),
         geom=t["geom"], bary=bary, step_idx=t["step_idx"], step_abc=t["step_abc"], level_ptr=t["level_ptr"],
+        nat_abc=t["nat_abc"], ccell_morton=ccell_morton,
         fix_idx=t["fix_idx"], fix_w=t["fix_w"],
         fix_grp=fix_grp, ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
     if ncells == 1:

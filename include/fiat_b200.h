@@ -52,6 +52,7 @@ typedef struct {
     const int32_t* step_idx;   /* nsteps x 4: next, cur, prev (-1 first of chain), codim; sorted by the total
                                   degree of the member produced (wavefront order) */
     const double* step_abc;    /* nsteps x 3 Jacobi recurrence coefficients (expansions.py:24-40) */
+    const double* nat_abc;     /* nsteps x 3, the same in generation order (pass, sub-index, i) */
     const int32_t* level_ptr;  /* nlevels + 1: steps producing degree d+1 are [level_ptr[d], level_ptr[d+1]) */
     const int32_t* fix_idx;    /* nfix x 2: target, source slot (C0_basis fix-ups) */
     const double* fix_w;       /* nfix */
@@ -61,6 +62,7 @@ typedef struct {
     const double* bary;        /* (ncells+1) x 4 x 4: rescaled barycentric rows A_hat | b_hat, parent last
                                   (reference_element.py:616-644) */
     const double* ccell;       /* ncells x nrows x nslots folded coefficients coeffs[:, cell_node_map[c]] */
+    const double* ccell_morton;/* same on Morton-numbered members with the C0 fix-ups folded in */
     const int32_t* low1;       /* na x 3, Leibniz index tables (expansions.py:66-137) */
     const double* mul1;        /* na x 3 */
     const int32_t* low2;       /* na x 6 */
