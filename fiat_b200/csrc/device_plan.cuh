@@ -13,6 +13,7 @@
 #define FB_MAX_STEPS 455      // C(12+3,3) - 1: degree 12 on a tetrahedron
 #define FB_MAX_LEVELS 30
 #define FB_MAX_FIX 128
+#define FB_MAX_RB 160        // row blocks of 8 (ndofs * components <= 1280)
 
 struct StepRec {
     short nxt, cur, prv, codim;     // member slots; prv < 0: first step of a chain
@@ -26,6 +27,9 @@ struct RecTab {
     short fix_src[FB_MAX_FIX];
     double fix_w[FB_MAX_FIX];
     double geom0[FB_GEOM_DOUBLES];  // geometry of cell 0 (single-cell elements)
+    int nrb;                        // block-sparse coefficient matrix: row blocks, longest first
+    short rb_order[FB_MAX_RB];
+    int blk_ptr[FB_MAX_RB + 1];
     StepRec steps[FB_MAX_STEPS];    // sorted by total degree of the member produced
 };
 

@@ -180,12 +180,13 @@ int dispatch_small(const fiatb200_plan* plan, const DevEntity& E, const double* 
 // ---- tile / DMMA launch ------------------------------------------------------------------------
 bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     const DevSimplex& P = plan->simplex;
-    if (P.ncells != 1 || P.expansion != 0 || P.order > 2 || P.nblk == 0) return false;
+    if (P.ncells != 1 || P.expansion != 0 || P.order > 2 || P.nblk == 0 || plan->tab.nrb == 0) return false;
     // one CTA per SM: the widest tile whose expansion table fits in shared memory
     const size_t budget = (size_t)plan->max_smem_optin - 1024;
     int pt_max = 128;
     if (const char* env = getenv("FIATB200_MMA_PT")) pt_max = std::max(8, atoi(env)) & ~7;   // tuning override
-    for (int pt = pt_max; pt >= 8; pt >>= 1) {
+    const int go = P.na >= 8 ? 1 : (P.na >= 5 ? 2 : 4);      // octets per contraction work item (kernels.cuh)
+    for (int pt = pt_max; pt >= 8 * go; pt >>= 1) {
         int ld = P.na * pt;
         while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
         const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double);
@@ -375,6 +376,12 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
         R.fix_tgt[g] = (short)h->fix_idx[2 * h->fix_grp[2 * g]];
     }
     for (int i = 0; i < FB_GEOM_DOUBLES; ++i) R.geom0[i] = h->geom[i];
+    R.nrb = 0;
+    if (h->nrb <= FB_MAX_RB) {
+        R.nrb = h->nrb;
+        for (int i = 0; i < h->nrb; ++i) R.rb_order[i] = (short)h->rb_order[i];
+        for (int i = 0; i <= h->nrb; ++i) R.blk_ptr[i] = h->blk_ptr[i];
+    }
     memset(&plan->small_tab, 0, sizeof(plan->small_tab));
     for (int i = 0; i < h->nsteps && i < FB_SMALL_MAX_STEPS; ++i)
         for (int j = 0; j < 3; ++j) plan->small_tab.abc[i][j] = h->nat_abc[3 * i + j];

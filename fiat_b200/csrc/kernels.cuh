@@ -198,13 +198,15 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     }
 
     // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe (the C0 fix-ups
-    // are folded into C).  Coefficient fragments are fetched CH blocks ahead so that their L2
-    // latency hides behind the DMMAs of the current chunk.
+    // are folded into C).  Work item = (8-row block, GO point octets): one coefficient fragment feeds
+    // GO * NA DMMAs.  Fragments are fetched CH blocks ahead so that their L2 latency hides behind
+    // the DMMAs of the current chunk; row-block tables come from the constant bank.
     constexpr int CH = 8;
+    constexpr int GO = NA >= 8 ? 1 : (NA >= 5 ? 2 : 4);
     const int lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int noct = PT >> 3;
-    const int nitems = P.nrb * noct;
+    const int ngrp = PT / (8 * GO);
+    const int nitems = tab.nrb * ngrp;
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0);
     const double* Tlane = T + (size_t)t * G.ldT + g;
     const size_t kb_stride = (size_t)4 * G.ldT;
@@ -213,18 +215,20 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         if (lane == 0) item = atomicAdd(&s_next, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nitems) break;
-        const int rb = __ldg(P.rb_order + item / noct);
-        const int oct = item % noct;
-        double acc[NA][2];
+        const int rb = tab.rb_order[item / ngrp];
+        const int oct0 = (item % ngrp) * GO;
+        double acc[GO][NA][2];
 #pragma unroll
-        for (int s = 0; s < NA; ++s) acc[s][0] = acc[s][1] = 0.0;
-        const int q0 = __ldg(P.blk_ptr + rb), q1 = __ldg(P.blk_ptr + rb + 1);
+        for (int o = 0; o < GO; ++o)
+#pragma unroll
+            for (int s = 0; s < NA; ++s) acc[o][s][0] = acc[o][s][1] = 0.0;
+        const int q0 = tab.blk_ptr[rb], q1 = tab.blk_ptr[rb + 1];
         double a_cur[CH], a_nxt[CH];
         int kb_cur = 0, kb_nxt = 0;
 #pragma unroll
         for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
         if (lane < CH && q0 + lane < q1) kb_cur = __ldg(P.blk_kb + q0 + lane);
-        const double* Titem = Tlane + oct * (8 * NA);
+        const double* Titem = Tlane + oct0 * (8 * NA);
         for (int q = q0; q < q1; q += CH) {
             if (q + CH < q1) {
 #pragma unroll
@@ -238,11 +242,12 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                 if (j < nj) {
                     const int kb = __shfl_sync(0xffffffffu, kb_cur, j);
                     const double* Tb = Titem + kb * kb_stride;
-                    double bfrag[NA];
+                    double bfrag[GO * NA];
 #pragma unroll
-                    for (int s = 0; s < NA; ++s) bfrag[s] = Tb[8 * s];
+                    for (int s = 0; s < GO * NA; ++s) bfrag[s] = Tb[8 * s];
 #pragma unroll
-                    for (int s = 0; s < NA; ++s) dmma_8x8x4(acc[s][0], acc[s][1], a_cur[j], bfrag[s]);
+                    for (int s = 0; s < GO * NA; ++s)
+                        dmma_8x8x4(acc[s / NA][s % NA][0], acc[s / NA][s % NA][1], a_cur[j], bfrag[s]);
                 }
             }
 #pragma unroll
@@ -251,15 +256,19 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         }
         const int row = rb * 8 + g;
         if (row < P.nrows) {
-            const long long p = base + oct * 8 + 2 * t;
+            // adjacent 64-byte pieces of a row are stored back to back (octet innermost)
 #pragma unroll
             for (int s = 0; s < NA; ++s) {
-                double* o = out + ((size_t)s * P.nrows + row) * ostride + p;
-                if (vec_ok && p + 1 < npts) {
-                    *reinterpret_cast<double2*>(o) = make_double2(acc[s][0], acc[s][1]);
-                } else {
-                    if (p < npts) o[0] = acc[s][0];
-                    if (p + 1 < npts) o[1] = acc[s][1];
+#pragma unroll
+                for (int o = 0; o < GO; ++o) {
+                    const long long p = base + (oct0 + o) * 8 + 2 * t;
+                    double* dst = out + ((size_t)s * P.nrows + row) * ostride + p;
+                    if (vec_ok && p + 1 < npts) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(acc[o][s][0], acc[o][s][1]);
+                    } else {
+                        if (p < npts) dst[0] = acc[o][s][0];
+                        if (p + 1 < npts) dst[1] = acc[o][s][1];
+                    }
                 }
             }
         }
