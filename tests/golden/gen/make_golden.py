@@ -200,6 +200,29 @@ def main():
     dq = FlattenedDimensions(FIAT.TensorProductElement(FIAT.GaussLegendre(T1, 3), FIAT.GaussLegendre(T1, 2)))
     write_case("dq32_quad_o2", dq, 2, rng.random((10, 2)))
 
+    # more element families through the same path (single-cell, split-cell, vector / tensor valued)
+    from FIAT.reference_element import UFCQuadrilateral
+    extra = [
+        ("hermite3_tet_o2", FIAT.CubicHermite(T3), 2, 3), ("bell_tri_o2", FIAT.Bell(T2), 2, 2),
+        ("ned1_3_tet_o1", FIAT.Nedelec(T3, 3), 1, 3), ("regge2_tet_o1", FIAT.Regge(T3, 2), 1, 3),
+        ("aw_tri_o2", FIAT.ArnoldWinther(T2, 3), 2, 2), ("hz3_tri_o1", FIAT.HuZhang(T2, 3), 1, 2),
+        ("jm_tri_o2", FIAT.JohnsonMercier(T2, 1), 2, 2), ("gn_tet_o2", FIAT.GuzmanNeilanFirstKindH1(T3, 1), 2, 3),
+        ("alfeld_sorokina_tri_o2", FIAT.AlfeldSorokina(T2, 2), 2, 2), ("christiansen_hu_tri_o1", FIAT.ChristiansenHu(T2, 1), 1, 2),
+        ("kmv2_tri_o2", FIAT.KongMulderVeldhuizen(T2, 2), 2, 2), ("p4_spectral_tri_o2", FIAT.Lagrange(T2, 4, variant="spectral"), 2, 2),
+        ("hct4_tri_o2", FIAT.HsiehCloughTocher(T2, 4), 2, 2), ("hct_red_tri_o2", FIAT.HsiehCloughTocher(T2, reduced=True), 2, 2),
+        ("walkington_tet_o2", FIAT.Walkington(T3), 2, 3),
+        ("restricted_p3_tri_o1", FIAT.RestrictedElement(FIAT.Lagrange(T2, 3), restriction_domain="facet"), 1, 2),
+        ("nodal_enriched_tri_o2", FIAT.NodalEnrichedElement(FIAT.Lagrange(T2, 2), FIAT.Bubble(T2, 3)), 2, 2),
+        ("gauss_radau3_line_o2", FIAT.GaussRadau(T1, 3), 2, 1), ("fdm3_line_o2", FIAT.FDMLagrange(T1, 3), 2, 1),
+        ("histopolation3_line_o1", FIAT.Histopolation(T1, 3), 1, 1), ("p10_tri_o2", FIAT.Lagrange(T2, 10), 2, 2),
+        ("p6_tet_o1", FIAT.Lagrange(T3, 6, variant="spectral"), 1, 3),
+    ]
+    for nm, el, order, sd in extra:
+        pts = rng.random((14, 1)) if sd == 1 else simplex_points(rng, 14, sd)
+        macro = el.get_nodal_basis().get_expansion_set().ref_el.is_macrocell()
+        write_case(nm, el, order, pts, with_cells=macro)
+    write_case("dpc2_quad_o2", FIAT.DPC(UFCQuadrilateral(), 2), 2, rng.random((14, 2)))
+
     # element descriptions alone, for bench.py and full-size GPU tests
     for nm, el in (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),
                    ("hct", FIAT.HsiehCloughTocher(T2)), ("ps6", FIAT.QuadraticPowellSabin6(T2)),
