@@ -18,7 +18,7 @@ p_i32, p_dbl, p_void = ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), ctypes.c_vo
 class SimplexProgramStruct(ctypes.Structure):
     _fields_ = [
         ("sd", c_i32), ("degree", c_i32), ("order", c_i32), ("na", c_i32), ("expansion", c_i32),
-        ("ncells", c_i32), ("nslots", c_i32), ("nrows", c_i32), ("unique", c_i32),
+        ("ncells", c_i32), ("nslots", c_i32), ("nrows", c_i32), ("ncomp", c_i32), ("unique", c_i32),
         ("nsteps", c_i32), ("nlevels", c_i32), ("nfix", c_i32), ("nfixgrp", c_i32), ("line_n", c_i32),
         ("step_idx", p_i32), ("step_abc", p_dbl), ("nat_abc", p_dbl), ("level_ptr", p_i32),
         ("fix_idx", p_i32), ("fix_w", p_dbl), ("fix_grp", p_i32),
@@ -38,6 +38,21 @@ class TensorLeafStruct(ctypes.Structure):
     _fields_ = [("plan", p_void), ("entity", EntityMapStruct), ("point_offset", c_i32)]
 
 
+class RowMapStruct(ctypes.Structure):
+    _fields_ = [("nc_in", c_i32), ("nc_out", c_i32), ("dof_base", c_i32), ("total_rows", c_i32),
+                ("comp_out", c_i32 * 9), ("sign", c_dbl * 9)]
+
+
+def row_map_struct(nc_in, nc_out, dof_base, total_rows, comp_out, sign):
+    m = RowMapStruct()
+    m.nc_in, m.nc_out, m.dof_base, m.total_rows = nc_in, nc_out, dof_base, total_rows
+    co = list(comp_out) + [0] * (9 - len(comp_out))
+    sg = list(sign) + [1.0] * (9 - len(sign))
+    m.comp_out = (c_i32 * 9)(*[int(v) for v in co])
+    m.sign = (c_dbl * 9)(*[float(v) for v in sg])
+    return m
+
+
 class LibraryError(RuntimeError):
     pass
 
@@ -46,7 +61,7 @@ _lib = None
 
 EXPORTS = [
     "fiatb200_version", "fiatb200_last_error", "fiatb200_simplex_plan_create", "fiatb200_tensor_plan_create",
-    "fiatb200_lattice_plan_create", "fiatb200_plan_destroy", "fiatb200_plan_shape", "fiatb200_tabulate", "fiatb200_locate_subcells",
+    "fiatb200_lattice_plan_create", "fiatb200_plan_destroy", "fiatb200_plan_shape", "fiatb200_tabulate", "fiatb200_tabulate_mapped", "fiatb200_zero_rows", "fiatb200_locate_subcells",
     "fiatb200_tabulate_host", "fiatb200_launch_count",
 ]
 
@@ -70,6 +85,9 @@ def load():
     lib.fiatb200_plan_shape.argtypes = [p_void, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     lib.fiatb200_tabulate.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, p_void, c_i64,
                                       c_u32, p_void]
+    lib.fiatb200_tabulate_mapped.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, p_void, c_i64,
+                                             ctypes.POINTER(RowMapStruct), c_u32, p_void]
+    lib.fiatb200_zero_rows.argtypes = [p_void, c_i64, c_i64, c_i64, c_i32, p_void, c_i32, p_void]
     lib.fiatb200_locate_subcells.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, c_i32,
                                              p_void, p_void]
     lib.fiatb200_tabulate_host.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, p_void,
@@ -105,6 +123,7 @@ def simplex_struct(prog):
     s = SimplexProgramStruct()
     s.sd, s.degree, s.order, s.na, s.expansion = prog.sd, prog.degree, prog.order, prog.na, prog.expansion
     s.ncells, s.nslots, s.nrows, s.unique = prog.ncells, prog.nslots, prog.nrows, prog.unique
+    s.ncomp = prog.nrows // max(prog.ndofs, 1)
     s.nsteps, s.nlevels, s.nfix, s.line_n = len(prog.step_idx), len(prog.level_ptr) - 1, len(prog.fix_idx), prog.line_n
     s.nfixgrp = len(prog.fix_grp)
     s.step_idx, s.step_abc, s.level_ptr = i32(prog.step_idx), f64(prog.step_abc), i32(prog.level_ptr)

@@ -35,7 +35,7 @@ struct RecTab {
 
 struct DevSimplex {
     int sd, degree, order, na, expansion, ncells, nslots, nrows, unique;
-    int line_n;
+    int line_n, ncomp;
     const RecTab* tab;          // device copy of the recurrence program (tensor-product leaves)
     const double* geom;
     const double* bary;
@@ -53,6 +53,30 @@ struct DevSimplex {
     const int* rb_order;
 };
 
+// Placement of a kernel's rows inside a larger table (wrapper elements: enriched, mixed, H(div)/H(curl)
+// on tensor products -- FIAT/enriched.py:88-113, FIAT/mixed.py:61-92, FIAT/hdivcurl.py:43-108,165-254).
+// Kernel row r = dof * nc_in + k  ->  output row (dof_base + dof) * nc_out + comp_out[k], value * sign[k].
+struct DevRowMap {
+    int identity;       // rows are written in place (no wrapper): skips the index arithmetic
+    int nc_in, nc_out, dof_base, total_rows;
+    int comp_out[9];
+    double sign[9];
+};
+
+__device__ __forceinline__ size_t fb_map_row(const DevRowMap& M, int r, double& sgn) {
+    if (M.identity) {
+        sgn = 1.0;
+        return (size_t)r;
+    }
+    int dof = r, k = 0;
+    if (M.nc_in > 1) {
+        dof = r / M.nc_in;
+        k = r - dof * M.nc_in;
+    }
+    sgn = M.sign[k];
+    return (size_t)(M.dof_base + dof) * M.nc_out + M.comp_out[k];
+}
+
 struct DevEntity {
     int dim, identity;
     double C[9];
@@ -64,10 +88,13 @@ struct DevTensorLeaf {
     DevEntity ent;
     int point_offset;
     int table_off;      // offset (in doubles per point) of this leaf's table in shared memory
+    int ndof, ncomp;    // leaf rows = ndof * ncomp
+    int dof_stride;     // stride of this leaf's dof index in the product dof index
 };
 
 struct DevTensor {
     int nleaf, nalpha, nrows, order;
+    int ncomp;                  // components of the product (that of its one vector-valued leaf, else 1)
     int scratch_doubles;        // per point
     int total_doubles;          // per point: scratch + all leaf tables
     DevTensorLeaf leaf[FB_MAX_LEAVES];

@@ -89,6 +89,22 @@ DevEntity make_entity(const fiatb200_entity_map* e, int sd) {
     return d;
 }
 
+DevRowMap make_row_map(const fiatb200_row_map* m, int ncomp, int nrows) {
+    DevRowMap d;
+    memset(&d, 0, sizeof(d));
+    if (!m) {
+        d.identity = 1;
+        d.nc_in = d.nc_out = ncomp;
+        d.dof_base = 0;
+        d.total_rows = nrows;
+        for (int k = 0; k < 9; ++k) { d.comp_out[k] = k; d.sign[k] = 1.0; }
+        return d;
+    }
+    d.nc_in = m->nc_in; d.nc_out = m->nc_out; d.dof_base = m->dof_base; d.total_rows = m->total_rows;
+    for (int k = 0; k < 9; ++k) { d.comp_out[k] = m->comp_out[k]; d.sign[k] = m->sign[k]; }
+    return d;
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024)
@@ -99,7 +115,7 @@ int set_smem(K kernel, size_t bytes) {
 // ---- thread-per-point launch -----------------------------------------------------------------
 template <int SD, int ORDER>
 int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
-                    double* out, long long ostride, cudaStream_t st) {
+                    double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     const DevSimplex& P = plan->simplex;
     const size_t per_point = (size_t)P.nslots * P.na * sizeof(double);
     // widest block whose private expansion columns fit; very large elements end up with narrow blocks
@@ -116,7 +132,7 @@ int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double*
     int rc = set_smem(k_cellwise<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, plan->tab, E, pts, npts, ldp, out, ostride, tables_in_smem);
+    k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, plan->tab, E, pts, npts, ldp, out, ostride, tables_in_smem, M);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -124,26 +140,26 @@ int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double*
 
 template <int SD>
 int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts,
-                      long long ldp, double* out, long long ostride, cudaStream_t st) {
+                      long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     switch (plan->simplex.order) {
-        case 0: return launch_cellwise<SD, 0>(plan, E, pts, npts, ldp, out, ostride, st);
-        case 1: return launch_cellwise<SD, 1>(plan, E, pts, npts, ldp, out, ostride, st);
-        case 2: return launch_cellwise<SD, 2>(plan, E, pts, npts, ldp, out, ostride, st);
-        default: return launch_cellwise<SD, -1>(plan, E, pts, npts, ldp, out, ostride, st);
+        case 0: return launch_cellwise<SD, 0>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case 1: return launch_cellwise<SD, 1>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case 2: return launch_cellwise<SD, 2>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        default: return launch_cellwise<SD, -1>(plan, E, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
 // ---- register kernel for low-degree elements ------------------------------------------------------
 template <int SD, int N, int ORDER>
 int launch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
-                 double* out, long long ostride, cudaStream_t st) {
+                 double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     const DevSimplex& P = plan->simplex;
     const size_t smem = ((size_t)P.ncells * P.nrows * P.nslots + (size_t)P.ncells * FB_GEOM_DOUBLES) * sizeof(double);
     int rc = set_smem(k_small<SD, N, ORDER>, smem);
     if (rc) return rc;
     const int bp = 128;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_small<SD, N, ORDER><<<grid, bp, smem, st>>>(P, plan->small_tab, E, pts, npts, ldp, out, ostride);
+    k_small<SD, N, ORDER><<<grid, bp, smem, st>>>(P, plan->small_tab, E, pts, npts, ldp, out, ostride, M);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -162,10 +178,10 @@ bool small_applicable(const fiatb200_plan* plan) {
 
 #define FB_SMALL_CASE(SD_, N_, O_)                                                        \
     if (P.sd == SD_ && P.degree == N_ && P.order == O_)                                   \
-        return launch_small<SD_, N_, O_>(plan, E, pts, npts, ldp, out, ostride, st);
+        return launch_small<SD_, N_, O_>(plan, E, pts, npts, ldp, out, ostride, M, st);
 
 int dispatch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
-                   double* out, long long ostride, cudaStream_t st) {
+                   double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     const DevSimplex& P = plan->simplex;
     FB_SMALL_CASE(2, 1, 0) FB_SMALL_CASE(2, 1, 1) FB_SMALL_CASE(2, 1, 2)
     FB_SMALL_CASE(2, 2, 0) FB_SMALL_CASE(2, 2, 1) FB_SMALL_CASE(2, 2, 2)
@@ -186,13 +202,19 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     int pt_max = 128;
     if (const char* env = getenv("FIATB200_MMA_PT")) pt_max = std::max(8, atoi(env)) & ~7;   // tuning override
     const int go = P.na >= 8 ? 1 : (P.na >= 5 ? 2 : 4);      // octets per contraction work item (kernels.cuh)
+    int maxlev = 1;
+    for (int l = 0; l < plan->tab.nlevels; ++l)
+        maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
     for (int pt = pt_max; pt >= 8 * go; pt >>= 1) {
         int ld = P.na * pt;
         while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
-        const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double);
+        const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
         if (bytes <= budget) {
             G->PT = pt;
             G->ldT = ld;
+            G->maxlev = maxlev;
+            G->skip = 0;
+            if (const char* env = getenv("FIATB200_MMA_SKIP")) G->skip = atoi(env);   // profiling only
             *smem_out = bytes;
             return true;
         }
@@ -202,11 +224,11 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
 
 template <int SD, int ORDER>
 int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
-               long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
+               long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     int rc = set_smem(k_mma<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
-    k_mma<SD, ORDER><<<grid, FB_MMA_THREADS, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride);
+    k_mma<SD, ORDER><<<grid, FB_MMA_THREADS, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -214,16 +236,16 @@ int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, 
 
 template <int SD>
 int dispatch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
-                 long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
+                 long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     switch (plan->simplex.order) {
-        case 0: return launch_mma<SD, 0>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
-        case 1: return launch_mma<SD, 1>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
-        default: return launch_mma<SD, 2>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+        case 0: return launch_mma<SD, 0>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+        case 1: return launch_mma<SD, 1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+        default: return launch_mma<SD, 2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
 int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts, long long npts,
-                     long long ldp, double* out, long long ostride, uint32_t flags, cudaStream_t st) {
+                     long long ldp, double* out, long long ostride, const DevRowMap& M, uint32_t flags, cudaStream_t st) {
     const DevSimplex& P = plan->simplex;
     const DevEntity E = make_entity(entity, P.sd);
     if (E.dim < 0 || E.dim > 3) return fail(FIATB200_ERR_ARG, "entity dimension out of range");
@@ -235,23 +257,23 @@ int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entit
     if (flags & 1u) use_mma = false;
     if ((flags & 2u) && !use_mma) return fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
     // low-degree elements (and all split-cell ones of low degree): everything in registers
-    if (!(flags & 3u) && small_applicable(plan)) return dispatch_small(plan, E, pts, npts, ldp, out, ostride, st);
+    if (!(flags & 3u) && small_applicable(plan)) return dispatch_small(plan, E, pts, npts, ldp, out, ostride, M, st);
     if (use_mma) {
         switch (P.sd) {
-            case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
-            case 2: return dispatch_mma<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
-            default: return dispatch_mma<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+            case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+            case 2: return dispatch_mma<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+            default: return dispatch_mma<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
         }
     }
     switch (P.sd) {
-        case 1: return dispatch_cellwise<1>(plan, E, pts, npts, ldp, out, ostride, st);
-        case 2: return dispatch_cellwise<2>(plan, E, pts, npts, ldp, out, ostride, st);
-        default: return dispatch_cellwise<3>(plan, E, pts, npts, ldp, out, ostride, st);
+        case 1: return dispatch_cellwise<1>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case 2: return dispatch_cellwise<2>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        default: return dispatch_cellwise<3>(plan, E, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
 int tabulate_tensor(const fiatb200_plan* plan, const double* pts, long long npts, long long ldp, double* out,
-                    long long ostride, cudaStream_t st) {
+                    long long ostride, const DevRowMap& M, cudaStream_t st) {
     const DevTensor& Q = plan->tensor;
     int bp = 128;
     while (bp > 32 && (size_t)Q.total_doubles * bp * sizeof(double) > 96 * 1024) bp >>= 1;
@@ -261,7 +283,7 @@ int tabulate_tensor(const fiatb200_plan* plan, const double* pts, long long npts
     int rc = set_smem(k_tensor, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_tensor<<<grid, bp, smem, st>>>(Q, pts, npts, ldp, out, ostride);
+    k_tensor<<<grid, bp, smem, st>>>(Q, pts, npts, ldp, out, ostride, M);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -269,7 +291,7 @@ int tabulate_tensor(const fiatb200_plan* plan, const double* pts, long long npts
 
 template <int SD, int ORDER>
 int launch_lattice(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
-                   double* out, long long ostride, cudaStream_t st) {
+                   double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     const DevLattice& L = plan->lattice;
     const size_t per_point = (size_t)(SD + 1) * (L.degree + 1) * (ORDER + 1) * sizeof(double);
     int bp = 128;
@@ -280,27 +302,27 @@ int launch_lattice(const fiatb200_plan* plan, const DevEntity& E, const double* 
     int rc = set_smem(k_lattice<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_lattice<SD, ORDER><<<grid, bp, smem, st>>>(L, E, pts, npts, ldp, out, ostride);
+    k_lattice<SD, ORDER><<<grid, bp, smem, st>>>(L, E, pts, npts, ldp, out, ostride, M);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
 
 int tabulate_lattice(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts, long long npts,
-                     long long ldp, double* out, long long ostride, cudaStream_t st) {
+                     long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     const DevLattice& L = plan->lattice;
     const DevEntity E = make_entity(entity, L.sd);
     if (L.sd == 2) {
         switch (L.order) {
-            case 0: return launch_lattice<2, 0>(plan, E, pts, npts, ldp, out, ostride, st);
-            case 1: return launch_lattice<2, 1>(plan, E, pts, npts, ldp, out, ostride, st);
-            default: return launch_lattice<2, 2>(plan, E, pts, npts, ldp, out, ostride, st);
+            case 0: return launch_lattice<2, 0>(plan, E, pts, npts, ldp, out, ostride, M, st);
+            case 1: return launch_lattice<2, 1>(plan, E, pts, npts, ldp, out, ostride, M, st);
+            default: return launch_lattice<2, 2>(plan, E, pts, npts, ldp, out, ostride, M, st);
         }
     }
     switch (L.order) {
-        case 0: return launch_lattice<3, 0>(plan, E, pts, npts, ldp, out, ostride, st);
-        case 1: return launch_lattice<3, 1>(plan, E, pts, npts, ldp, out, ostride, st);
-        default: return launch_lattice<3, 2>(plan, E, pts, npts, ldp, out, ostride, st);
+        case 0: return launch_lattice<3, 0>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case 1: return launch_lattice<3, 1>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        default: return launch_lattice<3, 2>(plan, E, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
@@ -413,6 +435,7 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     P.sd = h->sd; P.degree = h->degree; P.order = h->order; P.na = h->na; P.expansion = h->expansion;
     P.ncells = h->ncells; P.nslots = h->nslots; P.nrows = h->nrows; P.unique = h->unique;
     P.line_n = h->line_n;
+    P.ncomp = h->ncomp > 0 ? h->ncomp : 1;
     void* b = plan->blob;
     P.tab = at<RecTab>(b, o_tab);
     P.geom = at<double>(b, o_geom);
@@ -461,9 +484,22 @@ int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nlea
         sd_total += lp->simplex.sd;
     }
     off = scratch;
+    Q.ncomp = 1;
+    int nvector = 0;
     for (int l = 0; l < nleaf; ++l) {
         Q.leaf[l].table_off = off;
         off += Q.leaf[l].prog.nrows * Q.leaf[l].prog.na;
+        Q.leaf[l].ncomp = Q.leaf[l].prog.ncomp;
+        Q.leaf[l].ndof = Q.leaf[l].prog.nrows / Q.leaf[l].prog.ncomp;
+        if (Q.leaf[l].ncomp > 1) { Q.ncomp = Q.leaf[l].ncomp; ++nvector; }
+    }
+    if (nvector > 1) {
+        delete plan;
+        return fail(FIATB200_ERR_UNSUPPORTED, "at most one vector-valued tensor-product factor (tensor_product.py:271-272)");
+    }
+    for (int l = nleaf - 1, stride = 1; l >= 0; --l) {
+        Q.leaf[l].dof_stride = stride;
+        stride *= Q.leaf[l].ndof;
     }
     Q.scratch_doubles = scratch;
     Q.total_doubles = off;
@@ -571,19 +607,52 @@ int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalp
     return FIATB200_OK;
 }
 
-int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,
-                      int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride, uint32_t flags,
-                      void* stream) {
+int fiatb200_tabulate_mapped(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,
+                             int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride,
+                             const fiatb200_row_map* map, uint32_t flags, void* stream) {
     if (!plan) return fail(FIATB200_ERR_ARG, "null plan");
     if (npts < 0 || out_row_stride < npts) return fail(FIATB200_ERR_ARG, "bad point count / row stride");
     if (npts == 0) return FIATB200_OK;
     if (!out_dev || (!pts_dev && pts_ld != 0)) return fail(FIATB200_ERR_ARG, "null device pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int ncomp = 1;
+    int64_t nrows = 0;
+    if (plan->kind == PLAN_SIMPLEX) { ncomp = plan->simplex.ncomp; nrows = plan->simplex.nrows; }
+    else if (plan->kind == PLAN_LATTICE) { nrows = plan->lattice.ndofs; }
+    else { ncomp = plan->tensor.ncomp; nrows = plan->tensor.nrows; }
+    if (map) {
+        if (map->nc_in != ncomp || map->nc_in < 1 || map->nc_in > 9 || map->nc_out < 1)
+            return fail(FIATB200_ERR_ARG, "row map does not match the plan's components");
+        for (int k = 0; k < map->nc_in; ++k)
+            if (map->comp_out[k] < 0 || map->comp_out[k] >= map->nc_out)
+                return fail(FIATB200_ERR_ARG, "row map component out of range");
+        if ((int64_t)(map->dof_base + nrows / ncomp) * map->nc_out > map->total_rows)
+            return fail(FIATB200_ERR_ARG, "row map exceeds the output table");
+    }
+    const DevRowMap M = make_row_map(map, ncomp, (int)nrows);
     if (plan->kind == PLAN_SIMPLEX)
-        return tabulate_simplex(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, flags, st);
+        return tabulate_simplex(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, flags, st);
     if (plan->kind == PLAN_LATTICE)
-        return tabulate_lattice(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, st);
-    return tabulate_tensor(plan, pts_dev, npts, pts_ld, out_dev, out_row_stride, st);
+        return tabulate_lattice(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, st);
+    return tabulate_tensor(plan, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, st);
+}
+
+int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,
+                      int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride, uint32_t flags,
+                      void* stream) {
+    return fiatb200_tabulate_mapped(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, nullptr, flags, stream);
+}
+
+int fiatb200_zero_rows(double* out_dev, int64_t out_row_stride, int64_t npts, int64_t total_rows, int32_t nalpha,
+                       const int32_t* rows_dev, int32_t nrows, void* stream) {
+    if (npts == 0 || nrows == 0) return FIATB200_OK;
+    if (!out_dev || !rows_dev || out_row_stride < npts) return fail(FIATB200_ERR_ARG, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((npts + 127) / 128);
+    k_zero_rows<<<grid, 128, 0, st>>>(out_dev, out_row_stride, npts, total_rows, nalpha, rows_dev, nrows);
+    g_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
 }
 
 int fiatb200_locate_subcells(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,

@@ -22,7 +22,8 @@
 template <int SD, int ORDER>
 __global__ void __launch_bounds__(128)
 k_cellwise(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const double* __restrict__ pts,
-           long long npts, long long ldp, double* __restrict__ out, long long ostride, int tables_in_smem) {
+           long long npts, long long ldp, double* __restrict__ out, long long ostride, int tables_in_smem,
+           const __grid_constant__ DevRowMap M) {
     extern __shared__ double smem[];
     const int BP = blockDim.x;
     const int tid = threadIdx.x;
@@ -85,10 +86,12 @@ k_cellwise(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEnti
 #pragma unroll
                 for (int j = 0; j < RB; ++j) {
                     if (r0 + j < P.nrows) {
+                        double sgn;
+                        const size_t orow = fb_map_row(M, r0 + j, sgn);
 #pragma unroll
                         for (int a = 0; a < NA; ++a) {
-                            double* o = out + ((size_t)a * P.nrows + r0 + j) * ostride + p;
-                            *o = first ? acc[j][a] : (*o + acc[j][a]);
+                            double* o = out + ((size_t)a * M.total_rows + orow) * ostride + p;
+                            *o = first ? sgn * acc[j][a] : (*o + sgn * acc[j][a]);
                         }
                     }
                 }
@@ -99,8 +102,10 @@ k_cellwise(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEnti
                 for (int a = 0; a < na; ++a) {
                     double acc = 0.0;
                     for (int k = 0; k < P.nslots; ++k) acc = fma(Cr[k], T[(size_t)k * slot_stride + a * comp_stride], acc);
-                    double* o = out + ((size_t)a * P.nrows + r) * ostride + p;
-                    *o = first ? acc : (*o + acc);
+                    double sgn;
+                    const size_t orow = fb_map_row(M, r, sgn);
+                    double* o = out + ((size_t)a * M.total_rows + orow) * ostride + p;
+                    *o = first ? sgn * acc : (*o + sgn * acc);
                 }
             }
         }
@@ -131,6 +136,8 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 struct MmaGeom {
     int PT;        // points per tile (multiple of 8)
     int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)
+    int maxlev;    // most recurrence steps in one wavefront level
+    int skip;      // profiling only: bit 0 skips the recurrence, bit 1 the contraction
 };
 #define FB_MMA_THREADS 512
 
@@ -143,7 +150,8 @@ struct MmaGeom {
 template <int SD, int ORDER>
 __global__ void __launch_bounds__(FB_MMA_THREADS, 1)
 k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const MmaGeom G,
-      const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride) {
+      const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride,
+      const __grid_constant__ DevRowMap M) {
     constexpr int NA = Jet<SD, ORDER>::NA;
     extern __shared__ double smem[];
     double* T = smem;                                   // kpad x ldT
@@ -184,15 +192,33 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     __syncthreads();
 
     // phase 1: recurrence in wavefront order -- every member of total degree d is an independent
-    // (step, point) work item once degrees d-1 and d-2 are in T
-    for (int lev = 0; lev < tab.nlevels; ++lev) {
+    // (step, point) work item once degrees d-1 and d-2 are in T.  The step records of a level are
+    // staged from the constant bank into shared memory one level ahead (lanes of a warp work on
+    // different steps, which the constant cache would serialise).
+    StepRec* s_rec = reinterpret_cast<StepRec*>(s_fb + 3 * PT);          // 2 x G.maxlev records
+    {
+        const int n0 = tab.level_ptr[1] - tab.level_ptr[0];
+        for (int i = tid; i < n0 * 4; i += FB_MMA_THREADS)
+            reinterpret_cast<double*>(s_rec)[i] = reinterpret_cast<const double*>(&tab.steps[tab.level_ptr[0]])[i];
+    }
+    __syncthreads();
+    for (int lev = 0; lev < ((G.skip & 1) ? 0 : tab.nlevels); ++lev) {
         const int l0 = tab.level_ptr[lev];
-        const int items = (tab.level_ptr[lev + 1] - l0) * PT;
+        const int nst = tab.level_ptr[lev + 1] - l0;
+        const StepRec* rec = s_rec + (lev & 1) * G.maxlev;
+        if (lev + 1 < tab.nlevels) {
+            const int l1 = tab.level_ptr[lev + 1];
+            const int n1 = tab.level_ptr[lev + 2] - l1;
+            double* dst = reinterpret_cast<double*>(s_rec + ((lev + 1) & 1) * G.maxlev);
+            for (int i = tid; i < n1 * 4; i += FB_MMA_THREADS) dst[i] = reinterpret_cast<const double*>(&tab.steps[l1])[i];
+        }
+        const int items = nst * PT;
         for (int it = tid; it < items; it += FB_MMA_THREADS) {
-            const int sid = l0 + it / PT, pl = it % PT;
+            const int sl = it / PT, pl = it % PT;
             const double fa[3] = {s_fa[pl], s_fa[PT + pl], s_fa[2 * PT + pl]};
             const double fb[3] = {s_fb[pl], s_fb[PT + pl], s_fb[2 * PT + pl]};
-            run_step<SD, ORDER>(P, tab.steps[sid], tab.geom0, fa, fb, T + (pl >> 3) * (8 * NA) + (pl & 7), G.ldT, 8, NA);
+            const StepRec r = rec[sl];
+            run_step<SD, ORDER>(P, r, tab.geom0, fa, fb, T + (pl >> 3) * (8 * NA) + (pl & 7), G.ldT, 8, NA);
         }
         __syncthreads();
     }
@@ -206,8 +232,9 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     const int lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int ngrp = PT / (8 * GO);
-    const int nitems = tab.nrb * ngrp;
+    const int nitems = (G.skip & 2) ? 0 : tab.nrb * ngrp;
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0);
+    const size_t astride = (size_t)M.total_rows * ostride;      // distance between derivative tables
     const double* Tlane = T + (size_t)t * G.ldT + g;
     const size_t kb_stride = (size_t)4 * G.ldT;
     for (;;) {
@@ -256,13 +283,27 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         }
         const int row = rb * 8 + g;
         if (row < P.nrows) {
+            double sgn;
+            const size_t orow = fb_map_row(M, row, sgn);
+            if (!M.identity) {
+#pragma unroll
+                for (int o = 0; o < GO; ++o)
+#pragma unroll
+                    for (int s = 0; s < NA; ++s) {
+                        acc[o][s][0] *= sgn;
+                        acc[o][s][1] *= sgn;
+                    }
+            }
+            double* rowp = out + orow * ostride + base + oct0 * 8 + 2 * t;
+            const long long p0 = base + oct0 * 8 + 2 * t;
             // adjacent 64-byte pieces of a row are stored back to back (octet innermost)
 #pragma unroll
             for (int s = 0; s < NA; ++s) {
+                double* dsts = rowp + (size_t)s * astride;
 #pragma unroll
                 for (int o = 0; o < GO; ++o) {
-                    const long long p = base + (oct0 + o) * 8 + 2 * t;
-                    double* dst = out + ((size_t)s * P.nrows + row) * ostride + p;
+                    const long long p = p0 + o * 8;
+                    double* dst = dsts + o * 8;
                     if (vec_ok && p + 1 < npts) {
                         *reinterpret_cast<double2*>(dst) = make_double2(acc[o][s][0], acc[o][s][1]);
                     } else {
@@ -306,26 +347,56 @@ __device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double*
     }
 }
 
-// Fused outer product over the leaf tables of one point: value = prod_l tab[l][i_l], global dof
-// index ((i0 * n1 + i1) * n2 + i2) * n3 + i3 (FIAT/tensor_product.py:288-292), rows streamed in order.
+// Fused outer product over the leaf tables of one point: value = prod_l tab[l][i_l]; the product dof
+// is the mixed-radix number of the leaf dofs, ((j0 * n1 + j1) * n2 + j2) * n3 + j3
+// (FIAT/tensor_product.py:288-292); at most one leaf is vector valued and supplies the component
+// (:293-335).
+struct TensorOut {
+    double* base;           // out + alpha * total_rows * ostride + point
+    long long ostride;
+    int nc_out, dof_base;
+};
+
 template <int L, int NL>
-__device__ __forceinline__ void emit_products(double f, const double* const (&tab)[FB_MAX_LEAVES],
-                                              const int (&n)[FB_MAX_LEAVES], int BP, double*& o, long long ostride) {
+__device__ __forceinline__ void emit_products(double f, int dofacc, int comp, const double* const (&tab)[FB_MAX_LEAVES],
+                                              const DevTensor& Q, const DevRowMap& M, int BP, const TensorOut& O) {
     const double* t = tab[L];
+    const DevTensorLeaf& lf = Q.leaf[L];
     if constexpr (L == NL - 1) {
+        if (lf.ncomp == 1) {
+            // scalar innermost leaf: rows advance by nc_out
+            const double sgn = M.sign[comp];
+            double* o = O.base + ((size_t)(M.dof_base + dofacc) * M.nc_out + M.comp_out[comp]) * O.ostride;
+            const long long step = (long long)M.nc_out * O.ostride;
+            const double fs = sgn * f;
 #pragma unroll 4
-        for (int i = 0; i < n[L]; ++i) {
-            *o = f * t[(size_t)i * BP];
-            o += ostride;
+            for (int i = 0; i < lf.ndof; ++i) {
+                *o = fs * t[(size_t)i * BP];
+                o += step;
+            }
+        } else {
+            for (int j = 0; j < lf.ndof; ++j)
+                for (int k = 0; k < lf.ncomp; ++k) {
+                    double* o = O.base + ((size_t)(M.dof_base + dofacc + j) * M.nc_out + M.comp_out[k]) * O.ostride;
+                    *o = M.sign[k] * f * t[(size_t)(j * lf.ncomp + k) * BP];
+                }
         }
     } else {
-        for (int i = 0; i < n[L]; ++i) emit_products<L + 1, NL>(f * t[(size_t)i * BP], tab, n, BP, o, ostride);
+        if (lf.ncomp == 1) {
+            for (int j = 0; j < lf.ndof; ++j)
+                emit_products<L + 1, NL>(f * t[(size_t)j * BP], dofacc + j * lf.dof_stride, comp, tab, Q, M, BP, O);
+        } else {
+            for (int j = 0; j < lf.ndof; ++j)
+                for (int k = 0; k < lf.ncomp; ++k)
+                    emit_products<L + 1, NL>(f * t[(size_t)(j * lf.ncomp + k) * BP], dofacc + j * lf.dof_stride, k, tab, Q, M,
+                                             BP, O);
+        }
     }
 }
 
 __global__ void __launch_bounds__(128)
 k_tensor(const DevTensor Q, const double* __restrict__ pts, long long npts, long long ldp,
-         double* __restrict__ out, long long ostride) {
+         double* __restrict__ out, long long ostride, const __grid_constant__ DevRowMap M) {
     extern __shared__ double smem[];
     const int BP = blockDim.x;
     const int tid = threadIdx.x;
@@ -340,23 +411,31 @@ k_tensor(const DevTensor Q, const double* __restrict__ pts, long long npts, long
         else if (L.prog.sd == 2) leaf_table<2>(L, pt, scratch, table, BP);
         else leaf_table<3>(L, pt, scratch, table, BP);
     }
-    int n[FB_MAX_LEAVES];
-#pragma unroll
-    for (int l = 0; l < FB_MAX_LEAVES; ++l) n[l] = l < Q.nleaf ? Q.leaf[l].prog.nrows : 1;
     for (int al = 0; al < Q.nalpha; ++al) {
         const int* aidx = Q.alpha_leaf + al * FB_MAX_LEAVES;
         const double* tab[FB_MAX_LEAVES];
 #pragma unroll
         for (int l = 0; l < FB_MAX_LEAVES; ++l) {
             const int lo = l < Q.nleaf ? l : 0;
-            tab[l] = smem + ((size_t)Q.leaf[lo].table_off + (size_t)__ldg(aidx + lo) * n[lo]) * BP + tid;
+            tab[l] = smem + ((size_t)Q.leaf[lo].table_off + (size_t)__ldg(aidx + lo) * Q.leaf[lo].prog.nrows) * BP + tid;
         }
-        double* o = out + (size_t)al * Q.nrows * ostride + p;
+        TensorOut O;
+        O.base = out + (size_t)al * M.total_rows * ostride + p;
+        O.ostride = ostride;
         switch (Q.nleaf) {
-            case 1: emit_products<0, 1>(1.0, tab, n, BP, o, ostride); break;
-            case 2: emit_products<0, 2>(1.0, tab, n, BP, o, ostride); break;
-            case 3: emit_products<0, 3>(1.0, tab, n, BP, o, ostride); break;
-            default: emit_products<0, 4>(1.0, tab, n, BP, o, ostride); break;
+            case 1: emit_products<0, 1>(1.0, 0, 0, tab, Q, M, BP, O); break;
+            case 2: emit_products<0, 2>(1.0, 0, 0, tab, Q, M, BP, O); break;
+            case 3: emit_products<0, 3>(1.0, 0, 0, tab, Q, M, BP, O); break;
+            default: emit_products<0, 4>(1.0, 0, 0, tab, Q, M, BP, O); break;
         }
     }
+}
+
+// zero-fill rows that no part of a wrapper element writes (all derivative tables)
+__global__ void k_zero_rows(double* __restrict__ out, long long ostride, long long npts, long long total_rows,
+                            int nalpha, const int* __restrict__ rows, int nrows) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    for (int a = 0; a < nalpha; ++a)
+        for (int i = 0; i < nrows; ++i) out[((size_t)a * total_rows + __ldg(rows + i)) * ostride + p] = 0.0;
 }

@@ -28,7 +28,7 @@ struct DevLattice {
 template <int SD, int ORDER>
 __global__ void __launch_bounds__(128)
 k_lattice(const DevLattice L, const DevEntity E, const double* __restrict__ pts, long long npts, long long ldp,
-          double* __restrict__ out, long long ostride) {
+          double* __restrict__ out, long long ostride, const __grid_constant__ DevRowMap M) {
     constexpr int NR = ORDER + 1;
     extern __shared__ double smem[];
     const int BP = blockDim.x;
@@ -71,7 +71,8 @@ k_lattice(const DevLattice L, const DevEntity E, const double* __restrict__ pts,
     const double* U1 = U + (size_t)1 * n1 * NR * BP;
     const double* U2 = U + (size_t)2 * n1 * NR * BP;
     const double* U3 = U + (size_t)(SD == 3 ? 3 : 2) * n1 * NR * BP;
-    const size_t nd = (size_t)L.ndofs;
+    const size_t nd = (size_t)M.total_rows;
+    const double sg = M.sign[0];
     double* o = out + p;
     int idx = 0;
     for (int a0 = 0; a0 <= n; ++a0) {
@@ -99,20 +100,20 @@ k_lattice(const DevLattice L, const DevEntity E, const double* __restrict__ pts,
                     if (ORDER >= 1) u3d = u3[BP];
                     if (ORDER >= 2) u3dd = u3[2 * BP];
                 }
-                const size_t row = (size_t)__ldg(L.rowmap + idx);
+                const size_t row = (size_t)(M.dof_base + __ldg(L.rowmap + idx)) * M.nc_out + M.comp_out[0];
                 ++idx;
                 double* orow = o + row * ostride;
-                const double Q = u2v * u3v;
+                const double Q = sg * (u2v * u3v);
                 orow[0] = P * Q;
                 if (ORDER >= 1) {
-                    const double Qc = u2d * u3v;            // d2
-                    const double Qd = u2v * u3d;            // d3 (3-D only)
+                    const double Qc = sg * (u2d * u3v);     // d2
+                    const double Qd = sg * (u2v * u3d);     // d3 (3-D only)
                     const double PaQ = Pa * Q;
                     orow[(1 * nd) * ostride] = Pd1 * Q;                                   // d/dx
                     orow[(2 * nd) * ostride] = fma(P, Qc, -PaQ);                          // d/dy
                     if (SD == 3) orow[(3 * nd) * ostride] = fma(P, Qd, -PaQ);             // d/dz
                     if (ORDER >= 2) {
-                        const double Qcc = u2dd * u3v, Qdd = u2v * u3dd, Qcd = u2d * u3d;
+                        const double Qcc = sg * (u2dd * u3v), Qdd = sg * (u2v * u3dd), Qcd = sg * (u2d * u3d);
                         const double PaaQ = Paa * Q;
                         const double Pd2Q = Pd2 * Q;
                         if (SD == 2) {

@@ -67,7 +67,7 @@ __device__ __forceinline__ void small_chain(const DevSimplex& P, const SmallTab&
 template <int SD, int N, int ORDER>
 __global__ void __launch_bounds__(128)
 k_small(const DevSimplex P, const __grid_constant__ SmallTab st, const DevEntity E, const double* __restrict__ pts,
-        long long npts, long long ldp, double* __restrict__ out, long long ostride) {
+        long long npts, long long ldp, double* __restrict__ out, long long ostride, const __grid_constant__ DevRowMap M) {
     constexpr int NMEM = fb_binom(N + SD, SD);
     constexpr int NA = Jet<SD, ORDER>::NA;
     extern __shared__ double smem[];
@@ -152,10 +152,12 @@ k_small(const DevSimplex P, const __grid_constant__ SmallTab st, const DevEntity
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
                 if (r0 + j < P.nrows) {
+                    double sgn;
+                    const size_t orow = fb_map_row(M, r0 + j, sgn);
 #pragma unroll
                     for (int a = 0; a < NA; ++a) {
-                        double* o = out + ((size_t)a * P.nrows + r0 + j) * ostride + p;
-                        *o = first ? acc[j][a] : (*o + acc[j][a]);
+                        double* o = out + ((size_t)a * M.total_rows + orow) * ostride + p;
+                        *o = first ? sgn * acc[j][a] : (*o + sgn * acc[j][a]);
                     }
                 }
             }

@@ -47,6 +47,7 @@ typedef struct {
     int32_t ncells;        /* subcells of the split complex (1 = plain simplex), <= 32 */
     int32_t nslots;        /* expansion members per subcell */
     int32_t nrows;         /* ndofs * prod(value_shape) */
+    int32_t ncomp;         /* prod(value_shape) */
     int32_t unique;        /* 1: first matching subcell wins (expansions.py:452,805-807) */
     int32_t nsteps, nlevels, nfix, nfixgrp, line_n;
     const int32_t* step_idx;   /* nsteps x 4: next, cur, prev (-1 first of chain), codim; sorted by the total
@@ -94,6 +95,18 @@ typedef struct {
     int32_t point_offset;          /* first coordinate of the product point used by this factor */
 } fiatb200_tensor_leaf;
 
+/* Placement of a plan's result rows inside a larger table, for the wrapper elements that zero-pad,
+ * stack, permute or sign-flip child tabulations (EnrichedElement FIAT/enriched.py:88-113, MixedElement
+ * FIAT/mixed.py:61-92, Hdiv/Hcurl on tensor products FIAT/hdivcurl.py:43-108,165-254):
+ * plan row dof * nc_in + k  ->  output row (dof_base + dof) * nc_out + comp_out[k], value * sign[k];
+ * the output table has total_rows rows per derivative multi-index.  nc_in must equal the plan's
+ * number of components. */
+typedef struct {
+    int32_t nc_in, nc_out, dof_base, total_rows;
+    int32_t comp_out[9];
+    double sign[9];
+} fiatb200_row_map;
+
 int fiatb200_version(void);
 const char* fiatb200_last_error(void);
 
@@ -127,6 +140,17 @@ int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalp
 int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* entity,
                       const double* pts_dev, int64_t npts, int64_t pts_ld,
                       double* out_dev, int64_t out_row_stride, uint32_t flags, void* stream);
+
+/* Same as fiatb200_tabulate, writing through a row placement (map == NULL: identity). */
+int fiatb200_tabulate_mapped(const fiatb200_plan* plan, const fiatb200_entity_map* entity,
+                             const double* pts_dev, int64_t npts, int64_t pts_ld,
+                             double* out_dev, int64_t out_row_stride, const fiatb200_row_map* map,
+                             uint32_t flags, void* stream);
+
+/* Zero-fill the listed rows (device array of nrows row numbers) of every derivative table: the
+ * entries of a wrapper element's table that none of its parts writes. */
+int fiatb200_zero_rows(double* out_dev, int64_t out_row_stride, int64_t npts, int64_t total_rows, int32_t nalpha,
+                       const int32_t* rows_dev, int32_t nrows, void* stream);
 
 /* Split-cell point location only: bitmask of the subcells each point is binned to
  * (= compute_cell_point_map, FIAT/expansions.py:771-811).  The object the parity tests compare
