@@ -84,10 +84,7 @@ class Tabulator:
         return planmod._cell_dim(self.desc)
 
     def value_shape(self):
-        d = self.desc
-        while d["kind"] == "flattened":
-            d = d["element"]
-        return tuple(int(s) for s in d["value_shape"]) if d["kind"] == "simplex" else ()
+        return planmod.value_shape_of(self.desc)
 
     def alphas(self, order):
         return planmod.alpha_list(self.cell_dimension(), order)
@@ -147,27 +144,29 @@ class Tabulator:
 
     def kernel_path(self, order, flags=0):
         """Which device path `tabulate(order, ...)` takes: 'lattice', 'simplex' or 'tensor'."""
+        if self.kind == "composite" or (self.kind == "flattened" and self.desc["element"]["kind"] == "composite"):
+            return "composite"
         if self.kind != "simplex":
             return "tensor"
         if flags & (FORCE_GENERAL | FORCE_THREAD_PER_POINT | FORCE_DMMA):
             return "simplex"
         return "lattice" if self._lattice_plan(self.desc, order) is not None else "simplex"
 
-    def _tensor_plan(self, order, entity):
+    def _tensor_plan(self, desc, order, entity):
         ekey = None if entity is None else (tuple(entity[0]) if isinstance(entity[0], (list, tuple)) else entity[0], entity[1])
-        key = ("tensor", order, ekey)
+        key = ("tensor", id(desc), order, ekey)
         with self._lock:
             cached = self._plans.get(key)
         if cached is not None:
             return cached
-        leaves = planmod.flatten_tensor(self.desc, entity)
+        leaves = planmod.flatten_tensor(desc, entity)
         if len(leaves) > 4:
             raise UnsupportedElement("tensor-product elements with more than 4 factors")
+        if sum(1 for lf in leaves if len(lf.desc["value_shape"])) > 1:
+            raise NotImplementedError("tabulate does not support two vector-valued inputs")
         arr = (_lib.TensorLeafStruct * len(leaves))()
         keep, nrows, npdim = [], 1, 0
         for i, lf in enumerate(leaves):
-            if len(lf.desc["value_shape"]):
-                raise UnsupportedElement("vector-valued tensor-product factors")
             p, prog = self._simplex_plan(lf.desc, order)
             dim, tr = _resolve_simplex_entity(lf.desc, lf.entity)
             arr[i].plan = p.handle
@@ -186,20 +185,58 @@ class Tabulator:
             self._plans[key] = out
         return out
 
+    def _zero_rows(self, parts, ndofs, nc_out):
+        """Device list of the table rows that no part writes (they must read as zero)."""
+        covered = numpy.zeros((ndofs, nc_out), dtype=bool)
+        for part in parts:
+            nd = planmod.num_dofs_of(part.desc)
+            covered[part.dof_base:part.dof_base + nd, part.comp_out] = True
+        rows = numpy.flatnonzero(~covered.reshape(-1)).astype(numpy.int32)
+        if len(rows) == 0:
+            return None
+        return torch.as_tensor(rows, device=self.device)
+
     def _resolve(self, order, entity, flags=0):
-        """(plan handle, entity struct or None, nrows, point dimension, result shape prefix)."""
+        """-> (launches, total_rows, point dimension, result shape prefix, rows to zero).
+
+        launches = [(plan, entity struct or None, row map struct or None)]; a plain element has one
+        launch without a row map, wrapper elements one per part."""
         if order < 0:
             raise ValueError("order must be non-negative")
-        if self.kind == "simplex":
-            p, prog = self._simplex_plan(self.desc, order)
-            if not (flags & (FORCE_GENERAL | FORCE_THREAD_PER_POINT | FORCE_DMMA)):
-                fast = self._lattice_plan(self.desc, order)
-                p = fast if fast is not None else p
-            dim, tr = _resolve_simplex_entity(self.desc, entity)
-            ent = _lib.entity_struct(prog.sd, tr)
-            return p, ent, prog.nrows, dim, (prog.ndofs,) + prog.value_shape
-        p, nrows, npdim = self._tensor_plan(order, entity)
-        return p, None, nrows, npdim, (nrows,)
+        parts = planmod.resolve_parts(self.desc, entity)
+        vs = planmod.value_shape_of(self.desc)
+        nc_out = int(numpy.prod(vs)) if vs else 1
+        ndofs = planmod.num_dofs_of(self.desc)
+        total_rows = ndofs * nc_out
+        single = len(parts) == 1 and parts[0].dof_base == 0 and parts[0].comp_out == list(range(nc_out)) \
+            and all(sg == 1.0 for sg in parts[0].sign)
+        launches, pdim = [], None
+        for part in parts:
+            d = part.desc
+            if d["kind"] == "simplex":
+                p, prog = self._simplex_plan(d, order)
+                if not (flags & (FORCE_GENERAL | FORCE_THREAD_PER_POINT | FORCE_DMMA)):
+                    fast = self._lattice_plan(d, order)
+                    p = fast if fast is not None else p
+                dim, tr = _resolve_simplex_entity(d, part.entity)
+                ent = _lib.entity_struct(prog.sd, tr)
+            else:
+                p, _, dim = self._tensor_plan(d, order, part.entity)
+                ent = None
+            if pdim is not None and dim != pdim:
+                raise ValueError("parts of a wrapper element disagree on the point dimension")
+            pdim = dim
+            rmap = None if single else _lib.row_map_struct(len(part.comp_out), nc_out, part.dof_base, total_rows,
+                                                            part.comp_out, part.sign)
+            launches.append((p, ent, rmap))
+        zero = None
+        if not single:
+            key = ("zero", entity if entity is None else str(entity))
+            with self._lock:
+                if key not in self._plans:
+                    self._plans[key] = self._zero_rows(parts, ndofs, nc_out)
+                zero = self._plans[key]
+        return launches, total_rows, pdim, (ndofs,) + vs, zero
 
     # -- calls --------------------------------------------------------------------------------
     def _points(self, points, pdim):
@@ -214,18 +251,18 @@ class Tabulator:
         return pts.contiguous()
 
     def tabulate(self, order, points, entity=None, flags=0):
-        p, ent, nrows, pdim, prefix = self._resolve(order, entity, flags)
+        launches, nrows, pdim, prefix, zero = self._resolve(order, entity, flags)
         pts = self._points(points, pdim)
         npts = pts.shape[0]
         alphas = self.alphas(order)
         out = torch.empty((len(alphas), nrows, npts), dtype=torch.float64, device=self.device)
-        self._launch(p, ent, pts, out, npts, flags)
+        self._run(launches, zero, pts, out, npts, npts, flags)
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
     def tabulate_into(self, out, order, points, entity=None, flags=0):
         """Streaming form: write into a caller-owned (nalpha, nrows, >=npts) float64 cuda tensor
         (row stride = out.stride(1)); returns the number of points written."""
-        p, ent, nrows, pdim, _ = self._resolve(order, entity, flags)
+        launches, nrows, pdim, _, zero = self._resolve(order, entity, flags)
         pts = self._points(points, pdim)
         npts = pts.shape[0]
         na = len(self.alphas(order))
@@ -233,32 +270,49 @@ class Tabulator:
                 or out.shape[1] != nrows or out.shape[2] < npts or out.stride(2) != 1 \
                 or out.stride(0) != nrows * out.stride(1):
             raise ValueError("out must be a float64 cuda tensor (nalpha, nrows, >=npts) with unit point stride")
-        self._launch(p, ent, pts, out, npts, flags, row_stride=out.stride(1))
+        self._run(launches, zero, pts, out, npts, out.stride(1), flags)
         return npts
 
-    def _launch(self, p, ent, pts, out, npts, flags, row_stride=None):
+    def _run(self, launches, zero, pts, out, npts, row_stride, flags):
         if npts == 0:
             return
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ld = pts.stride(0) if pts.shape[1] else 0
+        cflags = flags & 3
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.fiatb200_tabulate(
-                p.handle, ctypes.byref(ent) if ent is not None else None, pts.data_ptr(), npts, ld,
-                out.data_ptr(), npts if row_stride is None else row_stride, flags, stream))
+            if zero is not None:
+                _lib.check(self.lib.fiatb200_zero_rows(out.data_ptr(), row_stride, npts, out.shape[1], out.shape[0],
+                                                        zero.data_ptr(), zero.numel(), stream))
+            for p, ent, rmap in launches:
+                _lib.check(self.lib.fiatb200_tabulate_mapped(
+                    p.handle, ctypes.byref(ent) if ent is not None else None, pts.data_ptr(), npts, ld,
+                    out.data_ptr(), row_stride, ctypes.byref(rmap) if rmap is not None else None, cflags, stream))
+
+    def _launch(self, p, ent, pts, out, npts, flags, row_stride=None):
+        self._run([(p, ent, None)], None, pts, out, npts, npts if row_stride is None else row_stride, flags)
 
     def tabulate_host(self, order, points, entity=None, chunk_pts=1 << 16, flags=0, out=None):
         """End-to-end with host (numpy) buffers: returns a dict of numpy arrays, like the reference."""
-        p, ent, nrows, pdim, prefix = self._resolve(order, entity, flags)
+        launches, nrows, pdim, prefix, zero = self._resolve(order, entity, flags)
         pts = numpy.ascontiguousarray(numpy.asarray(points, dtype=numpy.float64)).reshape(-1, pdim)
         npts = pts.shape[0]
         alphas = self.alphas(order)
         if out is None:
             out = numpy.empty((len(alphas), nrows, npts))
-        if npts:
+        if npts and len(launches) == 1 and launches[0][2] is None:
+            p, ent, _ = launches[0]
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.fiatb200_tabulate_host(
                     p.handle, ctypes.byref(ent) if ent is not None else None, pts.ctypes.data, npts, pdim,
-                    out.ctypes.data, chunk_pts, flags))
+                    out.ctypes.data, chunk_pts, flags & 3))
+        elif npts:
+            # wrapper elements: chunks through the device path, one device buffer
+            for start in range(0, npts, chunk_pts):
+                stop = min(npts, start + chunk_pts)
+                dpts = torch.as_tensor(pts[start:stop], device=self.device)
+                dout = torch.empty((len(alphas), nrows, stop - start), dtype=torch.float64, device=self.device)
+                self._run(launches, zero, dpts, dout, stop - start, stop - start, flags)
+                out[:, :, start:stop] = dout.cpu().numpy()
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
     def locate_subcells(self, points, unique, entity=None):

@@ -237,8 +237,8 @@ def _dim_sum(key):
 
 def _describe_tensor(element):
     A, B = element.A, element.B
-    if len(A.value_shape()) + len(B.value_shape()) > 0:
-        raise UnsupportedElement("vector-valued tensor-product factors are not on the device path yet")
+    if len(A.value_shape()) + len(B.value_shape()) > 1:
+        raise UnsupportedElement("two vector-valued tensor-product factors (tensor_product.py:271-272)")
     cellA, cellB = element.ref_el.cells
     return {
         "kind": "tensor",
@@ -259,15 +259,93 @@ def _describe_flattened(element):
     return {"kind": "flattened", "element": describe_element(inner), "unflatten": table}
 
 
+def _ncomp(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+def _composite(ndofs, value_shape, parts):
+    return {"kind": "composite", "ndofs": int(ndofs), "value_shape": numpy.array(value_shape, dtype=numpy.int64),
+            "parts": parts}
+
+
+def _describe_enriched(element):
+    """EnrichedElement: child tables stacked along the dof axis (FIAT/enriched.py:88-113)."""
+    vs = tuple(int(v) for v in element.value_shape())
+    nc = _ncomp(vs)
+    parts, off = [], 0
+    for sub in element.elements():
+        parts.append({"element": describe_element(sub), "dof_offset": off,
+                      "comp_out": list(range(nc)), "sign": [1.0] * nc})
+        off += int(sub.space_dimension())
+    return _composite(off, vs, parts)
+
+
+def _describe_mixed(element):
+    """MixedElement: block-diagonal stacking in dofs and components (FIAT/mixed.py:61-92)."""
+    parts, doff, coff = [], 0, 0
+    for sub in element.elements():
+        nc = _ncomp(sub.value_shape())
+        parts.append({"element": describe_element(sub), "dof_offset": doff,
+                      "comp_out": list(range(coff, coff + nc)), "sign": [1.0] * nc})
+        doff += int(sub.space_dimension())
+        coff += nc
+    return _composite(doff, (coff,), parts)
+
+
+def _describe_hdivcurl(element):
+    """Hdiv(...) / Hcurl(...) of a tensor-product element (FIAT/hdivcurl.py:43-108,165-254): the plain
+    tensor-product table with its components placed (possibly rotated and sign-flipped) into a
+    vector of the cell's dimension.  The placement is read off by comparing the wrapper's table with
+    the wrapped one at a few points, which covers every branch of the reference without re-deriving
+    its case analysis."""
+    inner = _describe_tensor(element)
+    cell = element.get_reference_element()
+    sd = int(cell.get_spatial_dimension())
+    verts = numpy.array(cell.get_vertices(), dtype=float)
+    rng = numpy.random.default_rng(7)
+    w = rng.random((7, len(verts))) + 0.1
+    pts = (w / w.sum(axis=1, keepdims=True)) @ verts
+    key = (0,) * sd
+    old = numpy.asarray(element.old_tabulate(0, pts)[key], dtype=float)
+    new = numpy.asarray(element.tabulate(0, pts)[key], dtype=float)
+    nd, npts = old.shape[0], old.shape[-1]
+    old = old.reshape(nd, -1, npts)
+    nc_in = old.shape[1]
+    comp_out, sign = [None] * nc_in, [1.0] * nc_in
+    for c in range(sd):
+        target = new[:, c, :]
+        if not numpy.any(target):
+            continue
+        for k in range(nc_in):
+            for sg in (1.0, -1.0):
+                if comp_out[k] is None and numpy.array_equal(target, sg * old[:, k, :]):
+                    comp_out[k], sign[k] = c, sg
+    if any(c is None for c in comp_out):
+        raise UnsupportedElement("could not identify the component placement of an Hdiv/Hcurl wrapper")
+    return _composite(nd, (sd,), [{"element": inner, "dof_offset": 0, "comp_out": comp_out, "sign": sign}])
+
+
 def describe_element(element):
     """Return the plain-data description of a FIAT element (see module docstring)."""
     names = _mro_names(element)
     if "FlattenedDimensions" in names:
         return _describe_flattened(element)
     if "TensorProductElement" in names:
+        if hasattr(element, "old_tabulate"):
+            return _describe_hdivcurl(element)
         return _describe_tensor(element)
+    if "EnrichedElement" in names:
+        return _describe_enriched(element)
+    if "MixedElement" in names:
+        return _describe_mixed(element)
+    if "DiscontinuousElement" in names:            # FIAT/discontinuous.py:56: same tabulation
+        return describe_element(element._element)
     if "CiarletElement" in names:
         return _describe_ciarlet(element)
     raise UnsupportedElement(
-        f"{type(element).__name__}: only CiarletElement, TensorProductElement and "
-        "FlattenedDimensions are tabulated on the device (no CPU fallback)")
+        f"{type(element).__name__}: only CiarletElement, TensorProductElement, FlattenedDimensions, "
+        "EnrichedElement, MixedElement, DiscontinuousElement and Hdiv/Hcurl wrappers are tabulated "
+        "on the device (no CPU fallback)")

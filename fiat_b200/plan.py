@@ -24,7 +24,8 @@ from dataclasses import dataclass, field
 
 import numpy
 
-__all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf", "lattice_rowmap"]
+__all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf", "lattice_rowmap",
+           "resolve_parts", "Part", "value_shape_of", "num_dofs_of"]
 
 EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
 GEOM_DOUBLES = 32      # A[9], b[3] @9, start value @12, dfa[codim][d] @14, dfb[codim][d] @23
@@ -305,8 +306,9 @@ def _line_tables(desc, order):
         for k in range(order + 1):
             a = b = float(k)
             apb = a + b
-            rec[k, 1, 0] = 0.5 * (a - b)
-            rec[k, 1, 1] = 0.5 * (a + b + 2.0)
+            if n >= 1:
+                rec[k, 1, 0] = 0.5 * (a - b)
+                rec[k, 1, 1] = 0.5 * (a + b + 2.0)
             for j in range(2, n + 1):
                 a1 = 2.0 * j * (j + apb) * (2.0 * j + apb - 2.0)
                 a2 = (2.0 * j + apb - 1.0) * (a * a - b * b)
@@ -483,7 +485,80 @@ def _cell_dim(desc):
         return int(desc["sd"])
     if desc["kind"] == "flattened":
         return _cell_dim(desc["element"])
+    if desc["kind"] == "composite":
+        return _cell_dim(desc["parts"][0]["element"])
     return _cell_dim(desc["A"]) + _cell_dim(desc["B"])
+
+
+def value_shape_of(desc):
+    kind = desc["kind"]
+    if kind in ("simplex", "composite"):
+        return tuple(int(v) for v in desc["value_shape"])
+    if kind == "flattened":
+        return value_shape_of(desc["element"])
+    return value_shape_of(desc["A"]) + value_shape_of(desc["B"])       # at most one factor is vector valued
+
+
+def num_dofs_of(desc):
+    kind = desc["kind"]
+    if kind == "simplex":
+        return int(desc["coeffs"].shape[0])
+    if kind == "composite":
+        return int(desc["ndofs"])
+    if kind == "flattened":
+        return num_dofs_of(desc["element"])
+    return num_dofs_of(desc["A"]) * num_dofs_of(desc["B"])
+
+
+@dataclass
+class Part:
+    """One kernel launch of a (possibly wrapped) element: a simplex or tensor-product description
+    evaluated on `entity`, whose rows land in the final table through a placement map
+    (dof = dof_base + own dof, component = comp_out[own component], value * sign)."""
+    desc: dict
+    entity: object
+    dof_base: int
+    comp_out: list
+    sign: list
+
+
+def resolve_parts(desc, entity=None):
+    """Flatten wrapper elements (composite / flattened) into kernel-level parts for one entity.
+
+    Placement maps compose: a part of a part adds dof offsets, chains component maps and multiplies
+    signs (EnrichedElement of Hdiv(TensorProductElement) etc.)."""
+    kind = desc["kind"]
+    if kind == "simplex":
+        nc = max(1, int(numpy.prod(desc["value_shape"])) if len(desc["value_shape"]) else 1)
+        return [Part(desc, entity, 0, list(range(nc)), [1.0] * nc)]
+    if kind == "tensor":
+        vs = value_shape_of(desc)
+        nc = int(numpy.prod(vs)) if vs else 1
+        return [Part(desc, entity, 0, list(range(nc)), [1.0] * nc)]
+    if kind == "flattened":
+        inner = desc["element"]
+        if inner["kind"] == "tensor":
+            vs = value_shape_of(desc)
+            nc = int(numpy.prod(vs)) if vs else 1
+            return [Part(desc, entity, 0, list(range(nc)), [1.0] * nc)]
+        if entity is None:
+            entity = (_cell_dim(desc), 0)
+        for fdim, fent, pdim, pent in desc["unflatten"]:
+            if fdim == entity[0] and fent == entity[1]:
+                pdim = tuple(pdim) if isinstance(pdim, list) else pdim
+                return resolve_parts(inner, (pdim, pent))
+        raise KeyError(f"no entity {entity} on the flattened cell")
+    if kind != "composite":
+        raise ValueError(kind)
+    out = []
+    for part in desc["parts"]:
+        comp_out = [int(c) for c in part["comp_out"]]
+        sign = [float(v) for v in part["sign"]]
+        for sub in resolve_parts(part["element"], entity):
+            out.append(Part(sub.desc, sub.entity, int(part["dof_offset"]) + sub.dof_base,
+                            [comp_out[c] for c in sub.comp_out],
+                            [sign[c] * sg for c, sg in zip(sub.comp_out, sub.sign)]))
+    return out
 
 
 def _flat(key):

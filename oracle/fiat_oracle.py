@@ -475,6 +475,8 @@ def cell_dimension(desc):
         return int(desc["sd"])
     if desc["kind"] == "flattened":
         return cell_dimension(desc["element"])
+    if desc["kind"] == "composite":
+        return cell_dimension(desc["parts"][0]["element"])
     return cell_dimension(desc["A"]) + cell_dimension(desc["B"])
 
 
@@ -497,8 +499,39 @@ def _tabulate_tensor(desc, order, pts, entity):
     for alpha in all_alphas(sdA + sdB, order):
         a = Atab[alpha[:sdA]]
         b = Btab[alpha[sdA:]]
-        result[alpha] = (a[:, None, :] * b[None, :, :]).reshape(a.shape[0] * b.shape[0], -1)
+        if a.ndim == 2 and b.ndim == 2:                       # scalar x scalar -- :277-292
+            result[alpha] = (a[:, None, :] * b[None, :, :]).reshape(a.shape[0] * b.shape[0], -1)
+        elif a.ndim == 3 and b.ndim == 2:                     # vector x scalar -- :293-314
+            prod = a[:, None, :, :] * b[None, :, None, :]     # (iA, iB, comp, pt)
+            result[alpha] = prod.reshape(a.shape[0] * b.shape[0], a.shape[1], -1)
+        elif a.ndim == 2 and b.ndim == 3:                     # scalar x vector -- :315-335
+            prod = a[:, None, None, :] * b[None, :, :, :]
+            result[alpha] = prod.reshape(a.shape[0] * b.shape[0], b.shape[1], -1)
+        else:
+            raise NotImplementedError("tabulate does not support two vector-valued inputs")
     return result
+
+
+def _tabulate_composite(desc, order, pts, entity):
+    """Wrapper elements: child tables placed into a zero-padded table --
+    EnrichedElement FIAT/enriched.py:88-113, MixedElement FIAT/mixed.py:61-92,
+    Hdiv/Hcurl FIAT/hdivcurl.py:43-108,165-254."""
+    ndofs = int(desc["ndofs"])
+    vs = tuple(int(v) for v in desc["value_shape"])
+    nc_out = int(numpy.prod(vs)) if vs else 1
+    result = {}
+    for part in desc["parts"]:
+        tab = tabulate(part["element"], order, pts, entity)
+        off = int(part["dof_offset"])
+        for alpha, arr in tab.items():
+            npts = arr.shape[-1]
+            arr3 = arr.reshape(arr.shape[0], -1, npts)
+            out = result.get(alpha)
+            if out is None:
+                out = result[alpha] = numpy.zeros((ndofs, nc_out, npts))
+            for k in range(arr3.shape[1]):
+                out[off:off + arr3.shape[0], int(part["comp_out"][k]), :] = float(part["sign"][k]) * arr3[:, k, :]
+    return {alpha: out.reshape((ndofs,) + vs + (out.shape[-1],)) for alpha, out in result.items()}
 
 
 def tabulate(desc, order, pts, entity=None):
@@ -515,4 +548,6 @@ def tabulate(desc, order, pts, entity=None):
         raise KeyError(entity)
     if kind == "tensor":
         return _tabulate_tensor(desc, order, pts, entity)
+    if kind == "composite":
+        return _tabulate_composite(desc, order, pts, entity)
     raise ValueError(kind)

@@ -45,6 +45,8 @@ def tolerance(desc, alpha):
             return int(d["degree"])
         if d["kind"] == "flattened":
             return degree(d["element"])
+        if d["kind"] == "composite":
+            return max(degree(p["element"]) for p in d["parts"])
         return max(degree(d["A"]), degree(d["B"]))
     return 1e-10 if (sum(alpha) >= 2 and degree(desc) >= 8) else 1e-12
 

@@ -223,6 +223,43 @@ def main():
         write_case(nm, el, order, pts, with_cells=macro)
     write_case("dpc2_quad_o2", FIAT.DPC(UFCQuadrilateral(), 2), 2, rng.random((14, 2)))
 
+    # wrapper elements: enriched, mixed, discontinuous, Hdiv/Hcurl on tensor products,
+    # vector-valued tensor-product factors
+    from FIAT.hdivcurl import Hdiv, Hcurl
+    P1, P2 = FIAT.Lagrange(T1, 1), FIAT.Lagrange(T1, 2)
+    DP0, DP1 = FIAT.DiscontinuousLagrange(T1, 0), FIAT.DiscontinuousLagrange(T1, 1)
+    TPE = FIAT.TensorProductElement
+
+    def prism_points(n):
+        return numpy.concatenate([simplex_points(rng, n, 2), rng.random((n, 1))], axis=1)
+
+    rtcf1 = FlattenedDimensions(FIAT.EnrichedElement(Hdiv(TPE(P1, DP0)), Hdiv(TPE(DP0, P1))))
+    rtce2 = FlattenedDimensions(FIAT.EnrichedElement(Hcurl(TPE(DP1, P2)), Hcurl(TPE(P2, DP1))))
+    nchex = FlattenedDimensions(FIAT.EnrichedElement(
+        Hcurl(TPE(FlattenedDimensions(TPE(DP0, P1)), P1)), Hcurl(TPE(FlattenedDimensions(TPE(P1, DP0)), P1)),
+        Hcurl(TPE(FlattenedDimensions(TPE(P1, P1)), DP0))))
+    wrappers = [
+        ("rtcf1_quad_o1", rtcf1, 1, rng.random((11, 2)), None),
+        ("rtcf1_quad_edge1_o1", rtcf1, 1, rng.random((5, 1)), (1, 1)),
+        ("rtce2_quad_o2", rtce2, 2, rng.random((11, 2)), None),
+        ("nce1_hex_o1", nchex, 1, rng.random((11, 3)), None),
+        ("mini_tri_o2", FIAT.EnrichedElement(FIAT.Lagrange(T2, 1), FIAT.Bubble(T2, 3)), 2, simplex_points(rng, 11, 2), None),
+        ("taylor_hood_tri_o1", FIAT.MixedElement([FIAT.Lagrange(T2, 2), FIAT.Lagrange(T2, 2), FIAT.Lagrange(T2, 1)]), 1,
+         simplex_points(rng, 11, 2), None),
+        ("rt1_dg0_mixed_tri_o1", FIAT.MixedElement([FIAT.RaviartThomas(T2, 1), FIAT.DiscontinuousLagrange(T2, 0)]), 1,
+         simplex_points(rng, 11, 2), None),
+        ("rt1xdp0_prism_hdiv_o1", Hdiv(TPE(FIAT.RaviartThomas(T2, 1), DP0)), 1, prism_points(11), None),
+        ("ned1xp1_prism_hcurl_o1", Hcurl(TPE(FIAT.Nedelec(T2, 1), P1)), 1, prism_points(11), None),
+        ("rt1xp1_prism_hcurl_rot_o1", Hcurl(TPE(FIAT.RaviartThomas(T2, 1), P1)), 1, prism_points(11), None),
+        ("dp1xp2_prism_hdiv_o2", Hdiv(TPE(FIAT.DiscontinuousLagrange(T2, 1), P2)), 2, prism_points(11), None),
+        ("rt2xp1_prism_vector_o1", TPE(FIAT.RaviartThomas(T2, 2), P1), 1, prism_points(11), None),
+        ("p1xrt1_vector_b_o1", TPE(P1, FIAT.RaviartThomas(T2, 1)), 1,
+         numpy.concatenate([rng.random((11, 1)), simplex_points(rng, 11, 2)], axis=1), None),
+        ("dg_wrapped_p2_tri_o2", FIAT.DiscontinuousElement(FIAT.Lagrange(T2, 2)), 2, simplex_points(rng, 11, 2), None),
+    ]
+    for nm, el, order, pts, ent in wrappers:
+        write_case(nm, el, order, pts, entity=ent)
+
     # element descriptions alone, for bench.py and full-size GPU tests
     for nm, el in (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),
                    ("hct", FIAT.HsiehCloughTocher(T2)), ("ps6", FIAT.QuadraticPowellSabin6(T2)),

@@ -63,3 +63,33 @@ def test_tensor_flattening_hex():
     leaves = planmod.flatten_tensor(load_desc("gll_q10_hex"))
     assert [(lf.point_offset, lf.point_dim, lf.sd) for lf in leaves] == [(0, 1, 1), (1, 1, 1), (2, 1, 1)]
     assert all(lf.entity == (1, 0) for lf in leaves)
+
+
+def _simplex_leaves(desc):
+    kind = desc["kind"]
+    if kind == "simplex":
+        yield desc
+    elif kind == "flattened":
+        yield from _simplex_leaves(desc["element"])
+    elif kind == "tensor":
+        yield from _simplex_leaves(desc["A"])
+        yield from _simplex_leaves(desc["B"])
+    elif kind == "composite":
+        for part in desc["parts"]:
+            yield from _simplex_leaves(part["element"])
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_every_golden_description_compiles(name):
+    """Plan compilation (incl. degenerate degree-0 line sets, wrapper elements) needs no GPU."""
+    case = load_case(name)
+    for leaf in _simplex_leaves(case["desc"]):
+        for order in range(0, case["order"] + 1):
+            prog = planmod.compile_simplex(leaf, order)
+            assert prog.nrows == prog.ndofs * max(1, int(numpy.prod(prog.value_shape)) if prog.value_shape else 1)
+            assert numpy.isfinite(prog.ccell).all() and numpy.isfinite(prog.line_tab).all()
+    parts = planmod.resolve_parts(case["desc"], case["entity"])
+    ndofs = planmod.num_dofs_of(case["desc"])
+    ref0 = next(iter(case["ref"].values()))
+    assert ref0.shape[0] == ndofs and ref0.shape[1:-1] == planmod.value_shape_of(case["desc"])
+    assert all(0 <= p.dof_base < ndofs for p in parts)
