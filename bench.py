@@ -289,6 +289,12 @@ def main():
             hbm_peak, peak_src = FALLBACK_HBM_GBS, "fallback"
         ms_launch = ms / max(launches, 1)
         achieved = bytes_per_point * batch / (ms_launch * 1e-3) / 1e9
+        kernel = tab.kernel_path(order, args.flags)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                f"{args.workload}|{kernel}|{batch}", {}).get("bytes")
+        except Exception:
+            traffic = None
         line = {
             "metric": "tabulated values/s", "value": value, "unit": "values/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -298,13 +304,15 @@ def main():
                        "total_points": world * args.steps * batch,
                        "l2": "output buffer per step is %.1f GB >> L2; rewritten every step" % (8 * vpp * batch / 1e9),
                        "sharding": "contiguous point shards, one rank per GPU, no collective",
-                       "kernel": tab.kernel_path(order, args.flags)},
+                       "kernel": kernel},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "values/s", "h2d_bytes_per_step": int(ne * sd * 8),
                     "d2h_bytes_per_step": int(ne * vpp * 8), "points_per_step": ne},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_point": bytes_per_point, "kernel_ms": ms_launch},
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_point": bytes_per_point, "algorithmic_bytes_per_launch": bytes_per_point * batch,
+                         "kernel_ms": ms_launch, "kernel": kernel,
+                         "fp64_peak_tflops_measured": FP64_PEAK_TFLOPS},
             "clocks": clocks,
         }
         if not args.no_cpu:
