@@ -203,6 +203,16 @@ class Tabulator:
         launch without a row map, wrapper elements one per part."""
         if order < 0:
             raise ValueError("order must be non-negative")
+        ckey = ("resolved", order, None if entity is None else str(entity), flags & 7)
+        hit = self._plans.get(ckey)
+        if hit is not None:
+            return hit
+        resolved = self._resolve_uncached(order, entity, flags)
+        with self._lock:
+            self._plans[ckey] = resolved
+        return resolved
+
+    def _resolve_uncached(self, order, entity, flags):
         parts = planmod.resolve_parts(self.desc, entity)
         vs = planmod.value_shape_of(self.desc)
         nc_out = int(numpy.prod(vs)) if vs else 1

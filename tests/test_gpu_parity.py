@@ -131,3 +131,75 @@ def test_full_size_properties_p8(cuda_device):
     a, b = tab.tabulate(2, pts), tab.tabulate(2, pts, flags=FORCE_GENERAL)
     for alpha in a:
         assert (a[alpha] - b[alpha]).abs().max().item() <= 1e-12 * b[alpha].abs().max().item()
+
+
+def _device_points(kind, n, device, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    sd = int(kind[-1])
+    u = torch.rand((n, sd), generator=g, device=device, dtype=torch.float64)
+    if kind.startswith("cube"):
+        return u
+    u, _ = torch.sort(u, dim=1)
+    return torch.diff(torch.cat([torch.zeros((n, 1), device=device, dtype=torch.float64), u], dim=1), dim=1).contiguous()
+
+
+@pytest.mark.parametrize("name,order,kind,npts", [("gll_q10_hex", 1, "cube3", 1 << 14), ("p3_tri", 1, "simplex2", 1 << 18)])
+def test_full_size_partition_of_unity(name, order, kind, npts, cuda_device):
+    """Nodal Lagrange-type bases sum to one and every derivative of the sum vanishes
+    (size-independent property, checked at bench-like point counts)."""
+    from conftest import load_desc
+    from fiat_b200.api import Tabulator
+    tab = Tabulator(load_desc(name), cuda_device)
+    got = tab.tabulate(order, _device_points(kind, npts, cuda_device, 11))
+    for alpha, v in got.items():
+        total = v.sum(dim=0)
+        target = 1.0 if sum(alpha) == 0 else 0.0
+        assert (total - target).abs().max().item() <= 1e-10 * max(1.0, v.abs().max().item())
+
+
+@pytest.mark.parametrize("name", ["hct", "ps6", "ps12"])
+def test_full_size_macro_vertex_functions_sum_to_one(name, cuda_device):
+    """test_hct.py:33-52 / test_powell_sabin.py:14-32 at 2^18 points: the three vertex-value basis
+    functions sum to 1 with vanishing derivatives; also every point is binned to >= 1 subcell and the
+    same subcell mask comes back from the locate entry point as the tabulation used."""
+    from conftest import load_desc
+    from fiat_b200.api import Tabulator
+    desc = load_desc(name)
+    tab = Tabulator(desc, cuda_device)
+    pts = _device_points("simplex2", 1 << 18, cuda_device, 13)
+    got = tab.tabulate(2, pts)
+    ndofs = next(iter(got.values())).shape[0]
+    # vertex point-evaluation dofs come first for each vertex: (value, d/dx, d/dy) triples
+    stride = ndofs // 3 if name != "ps12" else 3
+    vertex_value_dofs = [0, 3, 6]
+    for alpha, v in got.items():
+        total = v[vertex_value_dofs].sum(dim=0)
+        target = 1.0 if sum(alpha) == 0 else 0.0
+        assert (total - target).abs().max().item() <= 1e-9 * max(1.0, v.abs().max().item()), (alpha, stride)
+    mask = tab.locate_subcells(pts, unique=False)
+    assert int((mask == 0).sum().item()) == 0
+    assert int((mask >= (1 << int(desc["ncells"]))).sum().item()) == 0
+
+
+def test_nodality_of_tensor_product_dof_order(cuda_device):
+    """test_fiat.py:560-581: tabulating a nodal tensor-product element at its own nodes gives the
+    identity -- pins the (iA * nB + iB) dof ordering.  The GLL Q10 hex nodes are the products of the
+    1-D node table stored in the description."""
+    from conftest import load_desc
+    from fiat_b200.api import Tabulator
+    desc = load_desc("gll_q10_hex")
+    leaf = desc["element"]["B"]                       # the innermost 1-D GLL factor
+    x = numpy.sort(numpy.asarray(leaf["ll_nodes"][0]))
+    # 1-D dof order of the factor: ask the factor itself
+    one_d = Tabulator(leaf, cuda_device).tabulate(0, x[:, None])[(0,)].cpu().numpy()
+    order_1d = one_d.argmax(axis=0)                   # dof index that is 1 at node j
+    assert numpy.allclose(one_d[order_1d, numpy.arange(len(x))], 1.0)
+    node_of_dof = numpy.empty(len(x), dtype=int)
+    node_of_dof[order_1d] = numpy.arange(len(x))
+    xs = x[node_of_dof]
+    n = len(xs)
+    pts = numpy.stack(numpy.meshgrid(xs, xs, xs, indexing="ij"), axis=-1).reshape(-1, 3)
+    vals = Tabulator(desc, cuda_device).tabulate(0, pts)[(0, 0, 0)]
+    eye = torch.eye(n ** 3, dtype=torch.float64, device=cuda_device)
+    assert (vals - eye).abs().max().item() <= 1e-12
