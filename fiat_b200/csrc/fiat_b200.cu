@@ -205,18 +205,25 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     int maxlev = 1;
     for (int l = 0; l < plan->tab.nlevels; ++l)
         maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
-    for (int pt = pt_max; pt >= 8 * go; pt >>= 1) {
-        int ld = P.na * pt;
-        while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
-        const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
-        if (bytes <= budget) {
-            G->PT = pt;
-            G->ldT = ld;
-            G->maxlev = maxlev;
-            G->skip = 0;
-            if (const char* env = getenv("FIATB200_MMA_SKIP")) G->skip = atoi(env);   // profiling only
-            *smem_out = bytes;
-            return true;
+    // first choice: a tile of >= 32 points small enough for two resident CTAs (256 threads each, see
+    // launch_mma); otherwise the widest tile that fits one CTA per SM
+    for (int pass = 0; pass < 2; ++pass) {
+        const size_t limit = pass == 0 ? (size_t)110 * 1024 : budget;
+        const int pt_min = pass == 0 ? std::max(32, 8 * go) : 8 * go;
+        if (pass == 0 && getenv("FIATB200_MMA_PT")) continue;
+        for (int pt = pt_max; pt >= pt_min; pt >>= 1) {
+            int ld = P.na * pt;
+            while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
+            const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
+            if (bytes <= limit) {
+                G->PT = pt;
+                G->ldT = ld;
+                G->maxlev = maxlev;
+                G->skip = 0;
+                if (const char* env = getenv("FIATB200_MMA_SKIP")) G->skip = atoi(env);   // profiling only
+                *smem_out = bytes;
+                return true;
+            }
         }
     }
     return false;
@@ -228,7 +235,12 @@ int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, 
     int rc = set_smem(k_mma<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
-    k_mma<SD, ORDER><<<grid, FB_MMA_THREADS, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
+    int threads = FB_MMA_THREADS;
+    // tables small enough for two resident CTAs: run them with 256 threads each so that one CTA's
+    // recurrence / tail overlaps the other's contraction
+    if (smem <= 110 * 1024) threads = 256;
+    if (const char* env = getenv("FIATB200_MMA_THREADS")) threads = atoi(env) >= 512 ? 512 : 256;   // tuning override
+    k_mma<SD, ORDER><<<grid, threads, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;

@@ -159,6 +159,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     double* s_fb = s_fa + 3 * G.PT;                     // 3 x PT
     __shared__ int s_next;
     const int tid = threadIdx.x;
+    const int NT = blockDim.x;                          // 512 (one CTA per SM) or 256 (two)
     const int PT = G.PT;
     const long long base = (long long)blockIdx.x * PT;
 
@@ -188,7 +189,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
 #pragma unroll
         for (int a = 0; a < NA; ++a) t0[a * 8] = (a == 0) ? start : 0.0;
     }
-    for (int i = tid; i < (P.kpad - P.nslots) * G.ldT; i += FB_MMA_THREADS) T[(size_t)P.nslots * G.ldT + i] = 0.0;
+    for (int i = tid; i < (P.kpad - P.nslots) * G.ldT; i += NT) T[(size_t)P.nslots * G.ldT + i] = 0.0;
     __syncthreads();
 
     // phase 1: recurrence in wavefront order -- every member of total degree d is an independent
@@ -198,7 +199,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     StepRec* s_rec = reinterpret_cast<StepRec*>(s_fb + 3 * PT);          // 2 x G.maxlev records
     {
         const int n0 = tab.level_ptr[1] - tab.level_ptr[0];
-        for (int i = tid; i < n0 * 4; i += FB_MMA_THREADS)
+        for (int i = tid; i < n0 * 4; i += NT)
             reinterpret_cast<double*>(s_rec)[i] = reinterpret_cast<const double*>(&tab.steps[tab.level_ptr[0]])[i];
     }
     __syncthreads();
@@ -210,10 +211,10 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             const int l1 = tab.level_ptr[lev + 1];
             const int n1 = tab.level_ptr[lev + 2] - l1;
             double* dst = reinterpret_cast<double*>(s_rec + ((lev + 1) & 1) * G.maxlev);
-            for (int i = tid; i < n1 * 4; i += FB_MMA_THREADS) dst[i] = reinterpret_cast<const double*>(&tab.steps[l1])[i];
+            for (int i = tid; i < n1 * 4; i += NT) dst[i] = reinterpret_cast<const double*>(&tab.steps[l1])[i];
         }
         const int items = nst * PT;
-        for (int it = tid; it < items; it += FB_MMA_THREADS) {
+        for (int it = tid; it < items; it += NT) {
             const int sl = it / PT, pl = it % PT;
             const double fa[3] = {s_fa[pl], s_fa[PT + pl], s_fa[2 * PT + pl]};
             const double fb[3] = {s_fb[pl], s_fb[PT + pl], s_fb[2 * PT + pl]};
@@ -282,7 +283,32 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             kb_cur = kb_nxt;
         }
         const int row = rb * 8 + g;
-        if (row < P.nrows) {
+        const long long p0 = base + oct0 * 8 + 2 * t;
+        // warp-uniform: a full 8-row x GO-octet tile with aligned rows and no placement map
+        const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows;
+        if (full_tile) {
+            // trade fragments between lane groups g and g^4 so that one store instruction covers
+            // 4 rows x 128 contiguous bytes (two octets) instead of 8 rows x 64 bytes
+            const bool lo = g < 4;
+            double* row_lo = out + (size_t)(rb * 8 + (g & 3)) * ostride + base + oct0 * 8 + 2 * t;       // rows 0..3
+            double* row_hi = row_lo + 4 * ostride;                                                       // rows 4..7
+#pragma unroll
+            for (int s = 0; s < NA; ++s) {
+#pragma unroll
+                for (int o = 0; o + 1 < GO; o += 2) {
+                    // lanes g<4 send their octet o+1 piece, lanes g>=4 their octet o piece
+                    const double sx = lo ? acc[o + 1][s][0] : acc[o][s][0];
+                    const double sy = lo ? acc[o + 1][s][1] : acc[o][s][1];
+                    const double rx = __shfl_xor_sync(0xffffffffu, sx, 16);
+                    const double ry = __shfl_xor_sync(0xffffffffu, sy, 16);
+                    const int ocol = (o + (lo ? 0 : 1)) * 8;
+                    const double2 first = lo ? make_double2(acc[o][s][0], acc[o][s][1]) : make_double2(rx, ry);
+                    *reinterpret_cast<double2*>(row_lo + (size_t)s * astride + ocol) = first;
+                    const double2 second = lo ? make_double2(rx, ry) : make_double2(acc[o + 1][s][0], acc[o + 1][s][1]);
+                    *reinterpret_cast<double2*>(row_hi + (size_t)s * astride + ocol) = second;
+                }
+            }
+        } else if (row < P.nrows) {
             double sgn;
             const size_t orow = fb_map_row(M, row, sgn);
             if (!M.identity) {
@@ -294,8 +320,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                         acc[o][s][1] *= sgn;
                     }
             }
-            double* rowp = out + orow * ostride + base + oct0 * 8 + 2 * t;
-            const long long p0 = base + oct0 * 8 + 2 * t;
+            double* rowp = out + orow * ostride + p0;
             // adjacent 64-byte pieces of a row are stored back to back (octet innermost)
 #pragma unroll
             for (int s = 0; s < NA; ++s) {
