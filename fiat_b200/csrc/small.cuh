@@ -65,7 +65,7 @@ __device__ __forceinline__ void small_chain(const DevSimplex& P, const SmallTab&
 }
 
 template <int SD, int N, int ORDER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_small(const DevSimplex P, const __grid_constant__ SmallTab st, const DevEntity E, const double* __restrict__ pts,
         long long npts, long long ldp, double* __restrict__ out, long long ostride, const __grid_constant__ DevRowMap M) {
     constexpr int NMEM = fb_binom(N + SD, SD);
