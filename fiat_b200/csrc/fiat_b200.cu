@@ -420,6 +420,7 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     memset(&plan->small_tab, 0, sizeof(plan->small_tab));
     for (int i = 0; i < h->nsteps && i < FB_SMALL_MAX_STEPS; ++i)
         for (int j = 0; j < 3; ++j) plan->small_tab.abc[i][j] = h->nat_abc[3 * i + j];
+    for (int i = 0; i < 16 * (h->ncells + 1); ++i) plan->small_tab.bary[i] = h->bary[i];
 
     Arena A;
     const size_t o_tab = A.add(&R, sizeof(RecTab));

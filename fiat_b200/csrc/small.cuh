@@ -13,6 +13,7 @@
 
 struct SmallTab {
     double abc[FB_SMALL_MAX_STEPS][3];     // generation order: pass, sub-index (last entry outermost), i
+    double bary[33 * 16];                  // rescaled barycentric rows of <= 32 subcells + parent (constant bank)
 };
 
 __host__ __device__ constexpr int fb_morton2(int p, int q) { return (p + q) * (p + q + 1) / 2 + q; }
@@ -82,7 +83,7 @@ k_small(const DevSimplex P, const __grid_constant__ SmallTab st, const DevEntity
 
     double x[3];
     apply_entity<SD>(E, pts + p * ldp, x);
-    unsigned mask = locate_cells<SD>(P.bary, P.ncells, P.unique, x);
+    unsigned mask = locate_cells<SD>(st.bary, P.ncells, P.unique, x);
     const double inv_mult = 1.0 / (double)__popc(mask);
     bool first = true;
     while (mask) {
