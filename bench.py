@@ -319,7 +319,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": label, "points_per_gpu_per_step": batch, "values_per_point": vpp,
                        "total_points": world * args.steps * batch,
-                       "l2": "output buffer per step is %.1f GB >> L2; rewritten every step" % (8 * vpp * batch / 1e9),
+                       "l2": "every step streams %.1f GB of output through L2 (126 MB), which also evicts the %.0f MB of "
+                             "input points between steps; no separate flush" % (8 * vpp * batch / 1e9, 8 * sd * batch / 1e6),
                        "sharding": "contiguous point shards, one rank per GPU, no collective",
                        "kernel": kernel},
             "gpu_launches": int(launches),

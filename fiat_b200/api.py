@@ -325,6 +325,25 @@ class Tabulator:
                 out[:, :, start:stop] = dout.cpu().numpy()
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
+    def evaluate(self, coefficients, order, points, entity=None):
+        """Fused consumer: derivatives of the finite-element functions u_f = sum_i coefficients[f, i] phi_i
+        at the points, without ever writing the (ndofs, npts) tables (point evaluation /
+        interpolation).  Returns {alpha: tensor (nfunc, *value_shape, npts)}.
+
+        Because tabulation is linear in the coefficient tensor (FIAT/polynomial_set.py:71), this is the
+        tabulation of a derived element whose coefficient tensor is coefficients . coeffs; it runs
+        through the same kernels (general paths; Ciarlet elements only)."""
+        if self.kind != "simplex":
+            raise UnsupportedElement("evaluate() is available for Ciarlet elements on simplices")
+        u = numpy.atleast_2d(numpy.asarray(coefficients, dtype=numpy.float64))
+        coeffs = numpy.asarray(self.desc["coeffs"], dtype=numpy.float64)         # (ndofs, ncomp, nexp)
+        if u.shape[1] != coeffs.shape[0]:
+            raise ValueError(f"expected {coeffs.shape[0]} coefficients per function, got {u.shape[1]}")
+        derived = dict(self.desc)
+        derived["coeffs"] = numpy.einsum("fd,dck->fck", u, coeffs)
+        derived.pop("nodes", None)                                               # no longer a nodal basis
+        return Tabulator(derived, self.device).tabulate(order, points, entity)
+
     def locate_subcells(self, points, unique, entity=None):
         """Bitmask (uint32 as int64 tensor) of the subcells each point is binned to."""
         if self.kind != "simplex":

@@ -203,3 +203,22 @@ def test_nodality_of_tensor_product_dof_order(cuda_device):
     vals = Tabulator(desc, cuda_device).tabulate(0, pts)[(0, 0, 0)]
     eye = torch.eye(n ** 3, dtype=torch.float64, device=cuda_device)
     assert (vals - eye).abs().max().item() <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["p8_tet_o2", "hct_o2", "n2curl4_tet_o1", "p2_tri_facet1_o1"])
+def test_fused_point_evaluation(name, cuda_device):
+    """evaluate(): sum_i c[f, i] D^alpha phi_i without materialising the tables, against
+    coefficients . reference table."""
+    from fiat_b200.api import Tabulator
+    case = load_case(name)
+    desc = case["desc"]
+    rng = numpy.random.default_rng(3)
+    ndofs = desc["coeffs"].shape[0]
+    u = rng.standard_normal((3, ndofs))
+    got = Tabulator(desc, cuda_device).evaluate(u, case["order"], case["points"], case["entity"])
+    for alpha, ref in case["ref"].items():
+        want = numpy.tensordot(u, ref, axes=(1, 0))
+        g = got[alpha].cpu().numpy()
+        assert g.shape == want.shape
+        bound = (abs(u)[:, :, None] * abs(ref.reshape(ndofs, -1))[None]).sum(axis=1).max()
+        assert abs(g - want).max() <= tolerance(desc, alpha) * max(bound, 1e-300)
