@@ -2,17 +2,21 @@
 //
 //   k_cellwise   thread per point: locate subcell(s) -> expansion in a private shared-memory column
 //                -> contraction with the per-subcell coefficient matrix.  Handles every simplex plan
-//                (split cells, 1-D sets, any order); the only path for split cells.
+//                (split cells, 1-D sets, any derivative order).  Low-degree elements take the
+//                register-resident variant k_small (small.cuh), equispaced Lagrange elements the
+//                product-form kernel k_lattice (lattice.cuh).
 //   k_mma        single-cell Dubiner elements: a CTA owns a tile of PT points, runs the recurrence
 //                level-parallel into a shared expansion table T[member][octet][alpha][8] and contracts
 //                it with the 8x4 block-sparse coefficient matrix on the FP64 tensor pipe
 //                (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), skipping all-zero blocks.
-//   k_tensor     scalar tensor-product elements: factor tables per point in shared memory, then the
-//                fused outer product streamed straight to global memory.
+//   k_tensor     tensor-product elements (at most one vector-valued factor): factor tables per point
+//                in shared memory, then the fused outer product streamed straight to global memory.
 //   k_locate     subcell bitmasks only.
+//   k_zero_rows  zero-fill of the table rows no part of a wrapper element writes.
 //
-// Output: out[(alpha * nrows + row) * ostride + point]; consecutive threads own consecutive points,
-// so every warp store covers 256 contiguous bytes of one row.
+// Output: out[(alpha * total_rows + row) * ostride + point], rows placed through a DevRowMap
+// (identity for plain elements); consecutive threads own consecutive points, so every warp store
+// covers 256 contiguous bytes of one row.
 #pragma once
 #include "expansion.cuh"
 
