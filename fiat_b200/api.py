@@ -325,6 +325,26 @@ class Tabulator:
                 out[:, :, start:stop] = dout.cpu().numpy()
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
+    def tabulate_factors(self, order, points, entity=None):
+        """Factored result for tensor-product elements: the per-factor tables instead of their outer
+        product (what FInAT's sum-factorisation consumes, finat/tensor_product.py:98-144), which avoids
+        writing prod(n_l) values per point.  Returns a list with one entry per leaf factor, in dof-major
+        order: (alpha_offset, sd_l, {alpha_l: tensor (n_l, *value_shape_l, npts)}); the full table is
+        out[alpha][(i0 * n1 + i1) * n2 + i2] = prod_l tab_l[alpha[slice_l]][i_l]."""
+        d = self.desc
+        if d["kind"] not in ("tensor", "flattened") or (d["kind"] == "flattened" and d["element"]["kind"] != "tensor"):
+            raise UnsupportedElement("tabulate_factors() is defined for tensor-product elements")
+        leaves = planmod.flatten_tensor(d, entity)
+        pdim = max(lf.point_offset + lf.point_dim for lf in leaves)
+        pts = self._points(points, pdim)
+        out, aoff = [], 0
+        for lf in leaves:
+            sub = get_tabulator(lf.desc, self.device)
+            sl = pts[:, lf.point_offset:lf.point_offset + lf.point_dim]
+            out.append((aoff, lf.sd, sub.tabulate(order, sl, lf.entity)))
+            aoff += lf.sd
+        return out
+
     def evaluate(self, coefficients, order, points, entity=None):
         """Fused consumer: derivatives of the finite-element functions u_f = sum_i coefficients[f, i] phi_i
         at the points, without ever writing the (ndofs, npts) tables (point evaluation /

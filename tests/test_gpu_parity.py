@@ -222,3 +222,18 @@ def test_fused_point_evaluation(name, cuda_device):
         assert g.shape == want.shape
         bound = (abs(u)[:, :, None] * abs(ref.reshape(ndofs, -1))[None]).sum(axis=1).max()
         assert abs(g - want).max() <= tolerance(desc, alpha) * max(bound, 1e-300)
+
+
+@pytest.mark.parametrize("name", ["gll_q10_hex_o1", "q2_quad_edge2_o1", "p2xp1_prism_o1"])
+def test_factored_tensor_tables(name, cuda_device):
+    """tabulate_factors(): the per-factor tables multiply back to the reference's full table."""
+    from fiat_b200.api import Tabulator
+    case = load_case(name)
+    factors = Tabulator(case["desc"], cuda_device).tabulate_factors(case["order"], case["points"], case["entity"])
+    for alpha, ref in case["ref"].items():
+        prod = None
+        for aoff, sd, tab in factors:
+            t = tab[tuple(alpha[aoff:aoff + sd])].cpu().numpy()
+            prod = t if prod is None else (prod[:, None, :] * t[None, :, :]).reshape(-1, t.shape[-1])
+        assert prod.shape == ref.shape
+        assert abs(prod - ref).max() <= 1e-12 * max(abs(ref).max(), 1e-300)
