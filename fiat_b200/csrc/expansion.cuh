@@ -78,69 +78,82 @@ __device__ __forceinline__ unsigned locate_cells(const double* __restrict__ bary
 // derivative jets.  Component order = mis(SD,0), mis(SD,1), mis(SD,2): value, gradient, then the
 // upper triangle of the Hessian row by row.  ORDER = -1 selects the table-driven generic path.
 // ---------------------------------------------------------------------------------------------
+// Position of the multi-index (a0, a1, a2) in mis(SD,0), mis(SD,1), ... (first entry descending).
+template <int SD>
+__host__ __device__ constexpr int fb_alpha_index(int a0, int a1, int a2) {
+    const int k = a0 + a1 + a2;
+    if (SD == 1) return k;
+    if (SD == 2) return k * (k + 1) / 2 + a1;
+    return k * (k + 1) * (k + 2) / 6 + (a1 + a2) * (a1 + a2 + 1) / 2 + a2;
+}
+
+// Leibniz rule D^alpha(F g) for an affine F and D^alpha(G h) for a quadratic G (constant Hessian
+// ddG, upper triangle row by row), for every |alpha| <= ORDER.  All loops unroll at compile time,
+// so the multi-index arithmetic folds to constants and the jets stay in registers.
 template <int SD, int ORDER>
 struct Jet {
     static constexpr int NA = fb_binom(SD + ORDER, ORDER);
     static constexpr int CAP = NA;
 
-    __device__ __forceinline__ static void first(const DevSimplex&, int, double* __restrict__ nx,
-                                                 const double* __restrict__ cu, double F,
-                                                 const double* __restrict__ dF) {
-        nx[0] = F * cu[0];
-        if (ORDER >= 1) {
+    template <bool WITH_PREV>
+    __device__ __forceinline__ static void apply(double* __restrict__ nx, const double* __restrict__ cu,
+                                                 const double* __restrict__ pv, double F,
+                                                 const double* __restrict__ dF, double G,
+                                                 const double* __restrict__ dG, const double* __restrict__ ddG) {
 #pragma unroll
-            for (int d = 0; d < SD; ++d) nx[1 + d] = fma(F, cu[1 + d], dF[d] * cu[0]);
-        }
-        if (ORDER >= 2) {
-            int k = 0;
+        for (int a0 = 0; a0 <= ORDER; ++a0) {
 #pragma unroll
-            for (int d1 = 0; d1 < SD; ++d1) {
+            for (int a1 = 0; a1 <= (SD >= 2 ? ORDER - a0 : 0); ++a1) {
 #pragma unroll
-                for (int d2 = d1; d2 < SD; ++d2) {
-                    const int j = 1 + SD + k;
+                for (int a2 = 0; a2 <= (SD >= 3 ? ORDER - a0 - a1 : 0); ++a2) {
+                    const int al[3] = {a0, a1, a2};
+                    const int j = fb_alpha_index<SD>(a0, a1, a2);
                     double v = F * cu[j];
-                    if (d1 == d2) {
-                        v = fma(2.0 * dF[d1], cu[1 + d1], v);
-                    } else {
-                        v = fma(dF[d1], cu[1 + d2], v);
-                        v = fma(dF[d2], cu[1 + d1], v);
+                    if (WITH_PREV) v = fma(G, pv[j], v);
+#pragma unroll
+                    for (int d = 0; d < SD; ++d) {
+                        if (al[d] >= 1) {
+                            const int lo = fb_alpha_index<SD>(a0 - (d == 0), a1 - (d == 1), a2 - (d == 2));
+                            const double m = (double)al[d];
+                            v = fma(m * dF[d], cu[lo], v);
+                            if (WITH_PREV) v = fma(m * dG[d], pv[lo], v);
+                        }
+                    }
+                    if (WITH_PREV) {
+                        int k = 0;
+#pragma unroll
+                        for (int d1 = 0; d1 < SD; ++d1) {
+#pragma unroll
+                            for (int d2 = d1; d2 < SD; ++d2) {
+                                const int need = (d1 == d2) ? 2 : 1;
+                                if (al[d1] >= need && al[d2] >= need) {
+                                    const int lo = fb_alpha_index<SD>(a0 - (d1 == 0) - (d2 == 0), a1 - (d1 == 1) - (d2 == 1),
+                                                                      a2 - (d1 == 2) - (d2 == 2));
+                                    const double m = (d1 == d2) ? (double)(al[d1] * (al[d1] - 1) / 2)
+                                                                : (double)(al[d1] * al[d2]);
+                                    v = fma(m * ddG[k], pv[lo], v);
+                                }
+                                ++k;
+                            }
+                        }
                     }
                     nx[j] = v;
-                    ++k;
                 }
             }
         }
     }
 
-    __device__ __forceinline__ static void three(const DevSimplex& P, int na, double* __restrict__ nx,
+    __device__ __forceinline__ static void first(const DevSimplex&, int, double* __restrict__ nx,
+                                                 const double* __restrict__ cu, double F,
+                                                 const double* __restrict__ dF) {
+        apply<false>(nx, cu, cu, F, dF, 0.0, dF, dF);
+    }
+
+    __device__ __forceinline__ static void three(const DevSimplex&, int, double* __restrict__ nx,
                                                  const double* __restrict__ cu, const double* __restrict__ pv,
                                                  double F, const double* __restrict__ dF, double G,
                                                  const double* __restrict__ dG, const double* __restrict__ ddG) {
-        first(P, na, nx, cu, F, dF);
-        nx[0] = fma(G, pv[0], nx[0]);
-        if (ORDER >= 1) {
-#pragma unroll
-            for (int d = 0; d < SD; ++d) nx[1 + d] = fma(G, pv[1 + d], fma(dG[d], pv[0], nx[1 + d]));
-        }
-        if (ORDER >= 2) {
-            int k = 0;
-#pragma unroll
-            for (int d1 = 0; d1 < SD; ++d1) {
-#pragma unroll
-                for (int d2 = d1; d2 < SD; ++d2) {
-                    const int j = 1 + SD + k;
-                    double v = fma(G, pv[j], nx[j]);
-                    if (d1 == d2) {
-                        v = fma(2.0 * dG[d1], pv[1 + d1], v);
-                    } else {
-                        v = fma(dG[d1], pv[1 + d2], v);
-                        v = fma(dG[d2], pv[1 + d1], v);
-                    }
-                    nx[j] = fma(ddG[k], pv[0], v);
-                    ++k;
-                }
-            }
-        }
+        apply<true>(nx, cu, pv, F, dF, G, dG, ddG);
     }
 };
 

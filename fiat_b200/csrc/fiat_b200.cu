@@ -145,6 +145,7 @@ int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const doubl
         case 0: return launch_cellwise<SD, 0>(plan, E, pts, npts, ldp, out, ostride, M, st);
         case 1: return launch_cellwise<SD, 1>(plan, E, pts, npts, ldp, out, ostride, M, st);
         case 2: return launch_cellwise<SD, 2>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case 3: return launch_cellwise<SD, 3>(plan, E, pts, npts, ldp, out, ostride, M, st);
         default: return launch_cellwise<SD, -1>(plan, E, pts, npts, ldp, out, ostride, M, st);
     }
 }
@@ -168,7 +169,8 @@ int launch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pt
 // (sd, degree, order) combinations whose expansion table fits in registers (members x alphas <= 64)
 bool small_applicable(const fiatb200_plan* plan) {
     const DevSimplex& P = plan->simplex;
-    if (P.expansion != 0 || P.order > 2 || P.degree < 1 || P.sd < 2) return false;
+    if (P.expansion != 0 || P.order > 3 || P.degree < 1 || P.sd < 2) return false;
+    if (P.order == 3 && !(P.sd == 2 && P.degree <= 2)) return false;
     if ((size_t)P.nslots * P.na > 64) return false;
     if (P.sd == 2 && P.degree > 4) return false;
     if (P.sd == 3 && P.degree > 3) return false;
@@ -187,6 +189,7 @@ int dispatch_small(const fiatb200_plan* plan, const DevEntity& E, const double* 
     FB_SMALL_CASE(2, 2, 0) FB_SMALL_CASE(2, 2, 1) FB_SMALL_CASE(2, 2, 2)
     FB_SMALL_CASE(2, 3, 0) FB_SMALL_CASE(2, 3, 1) FB_SMALL_CASE(2, 3, 2)
     FB_SMALL_CASE(2, 4, 0) FB_SMALL_CASE(2, 4, 1)
+    FB_SMALL_CASE(2, 1, 3) FB_SMALL_CASE(2, 2, 3)
     FB_SMALL_CASE(3, 1, 0) FB_SMALL_CASE(3, 1, 1) FB_SMALL_CASE(3, 1, 2)
     FB_SMALL_CASE(3, 2, 0) FB_SMALL_CASE(3, 2, 1)
     FB_SMALL_CASE(3, 3, 0)
@@ -196,7 +199,7 @@ int dispatch_small(const fiatb200_plan* plan, const DevEntity& E, const double* 
 // ---- tile / DMMA launch ------------------------------------------------------------------------
 bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     const DevSimplex& P = plan->simplex;
-    if (P.ncells != 1 || P.expansion != 0 || P.order > 2 || P.nblk == 0 || plan->tab.nrb == 0) return false;
+    if (P.ncells != 1 || P.expansion != 0 || P.order > 3 || P.nblk == 0 || plan->tab.nrb == 0) return false;
     // one CTA per SM: the widest tile whose expansion table fits in shared memory
     const size_t budget = (size_t)plan->max_smem_optin - 1024;
     int pt_max = 128;
@@ -252,7 +255,8 @@ int dispatch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G
     switch (plan->simplex.order) {
         case 0: return launch_mma<SD, 0>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
         case 1: return launch_mma<SD, 1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-        default: return launch_mma<SD, 2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+        case 2: return launch_mma<SD, 2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+        default: return launch_mma<SD, 3>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
