@@ -13,7 +13,7 @@ cap() {  # name workload kernel-regex skip extra-flags
   $CMD > gpurun_out/plain_$1.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:$3 -s $4 -c 1 -o gpurun_out/r01_prof_$1 $CMD > gpurun_out/ncu_$1.log 2>&1
 }
-cap mma_p8 p8_tet_o2 k_mma 8 "--flags 4"
+cap mma_p8 p8_tet_o2 k_mma 7 "--flags 4"
 cap mma_n2curl n2curl4_tet_o1 k_mma 7 ""
 cap small_hct hct_o2 k_small 7 ""
 cap tensor_hex gll_q10_hex_o1 k_tensor 7 ""
