@@ -232,10 +232,10 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     return false;
 }
 
-template <int SD, int ORDER>
-int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
-               long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    int rc = set_smem(k_mma<SD, ORDER>, smem);
+template <int SD, int ORDER, int PW>
+int launch_mma_pw(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
+                  long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
+    int rc = set_smem(k_mma<SD, ORDER, PW>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
     int threads = FB_MMA_THREADS;
@@ -243,10 +243,17 @@ int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, 
     // recurrence / tail overlaps the other's contraction
     if (smem <= 110 * 1024) threads = 256;
     if (const char* env = getenv("FIATB200_MMA_THREADS")) threads = atoi(env) >= 512 ? 512 : 256;   // tuning override
-    k_mma<SD, ORDER><<<grid, threads, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
+    k_mma<SD, ORDER, PW><<<grid, threads, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
     g_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
+}
+
+template <int SD, int ORDER>
+int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
+               long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
+    if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    return launch_mma_pw<SD, ORDER, 8>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
 }
 
 template <int SD>

@@ -149,9 +149,10 @@ struct MmaGeom {
 // (contraction) share one pipe on B200, and a DFMA issued between DMMAs waits for the 16-cycle
 // DMMA in front of it, so interleaving the two phases of different CTAs costs more than it hides.
 //
-// T layout: T[slot][octet][alpha][8 points]; one work item of the contraction is (row block, octet),
-// whose NA column blocks are contiguous.
-template <int SD, int ORDER>
+// T layout: T[slot][point group][alpha][PW points], PW = 16 (8 for the narrowest tile): 16 consecutive
+// points are contiguous so that the recurrence's per-point accesses of a half warp hit 32 distinct
+// banks, and every octet of a group is still 8 contiguous columns for the DMMA fragments.
+template <int SD, int ORDER, int PW>
 __global__ void __launch_bounds__(FB_MMA_THREADS, 1)
 k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const MmaGeom G,
       const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride,
@@ -189,9 +190,9 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             s_fb[c * PT + tid] = fb[c];
         }
         const double start = tab.geom0[12];
-        double* t0 = T + (tid >> 3) * (8 * NA) + (tid & 7);
+        double* t0 = T + (tid / PW) * (PW * NA) + (tid % PW);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) t0[a * 8] = (a == 0) ? start : 0.0;
+        for (int a = 0; a < NA; ++a) t0[a * PW] = (a == 0) ? start : 0.0;
     }
     for (int i = tid; i < (P.kpad - P.nslots) * G.ldT; i += NT) T[(size_t)P.nslots * G.ldT + i] = 0.0;
     __syncthreads();
@@ -223,7 +224,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             const double fa[3] = {s_fa[pl], s_fa[PT + pl], s_fa[2 * PT + pl]};
             const double fb[3] = {s_fb[pl], s_fb[PT + pl], s_fb[2 * PT + pl]};
             const StepRec r = rec[sl];
-            run_step<SD, ORDER>(P, r, tab.geom0, fa, fb, T + (pl >> 3) * (8 * NA) + (pl & 7), G.ldT, 8, NA);
+            run_step<SD, ORDER>(P, r, tab.geom0, fa, fb, T + (pl / PW) * (PW * NA) + (pl % PW), G.ldT, PW, NA);
         }
         __syncthreads();
     }
@@ -260,7 +261,9 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
 #pragma unroll
         for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
         if (lane < CH && q0 + lane < q1) kb_cur = __ldg(P.blk_kb + q0 + lane);
-        const double* Titem = Tlane + oct0 * (8 * NA);
+        // octet o of the tile lives in point group o / (PW/8), at column offset (o % (PW/8)) * 8
+        constexpr int OPG = PW / 8;                         // octets per point group
+        const double* Titem = Tlane + (oct0 / OPG) * (PW * NA) + (oct0 % OPG) * 8;
         for (int q = q0; q < q1; q += CH) {
             if (q + CH < q1) {
 #pragma unroll
@@ -276,7 +279,11 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                     const double* Tb = Titem + kb * kb_stride;
                     double bfrag[GO * NA];
 #pragma unroll
-                    for (int s = 0; s < GO * NA; ++s) bfrag[s] = Tb[8 * s];
+                    for (int s = 0; s < GO * NA; ++s) {
+                        // column block of (octet s / NA past oct0, alpha s % NA); GO is a multiple of OPG or 1
+                        const int o = s / NA, a = s % NA;
+                        bfrag[s] = Tb[(o / OPG) * (PW * NA) + (o % OPG) * 8 + a * PW];
+                    }
 #pragma unroll
                     for (int s = 0; s < GO * NA; ++s)
                         dmma_8x8x4(acc[s / NA][s % NA][0], acc[s / NA][s % NA][1], a_cur[j], bfrag[s]);

@@ -237,3 +237,19 @@ def test_factored_tensor_tables(name, cuda_device):
             prod = t if prod is None else (prod[:, None, :] * t[None, :, :]).reshape(-1, t.shape[-1])
         assert prod.shape == ref.shape
         assert abs(prod - ref).max() <= 1e-12 * max(abs(ref).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", ["p8_tet", "p3_tri"])
+def test_nodality_at_lattice_nodes(name, cuda_device):
+    """test_fiat.py:446-470 in tabulated form: at its own nodes a Lagrange basis is the identity, on
+    the product-form kernel and on the general kernels (points on vertices, edges and faces)."""
+    from conftest import load_desc
+    from fiat_b200.api import Tabulator, FORCE_GENERAL
+    desc = load_desc(name)
+    tab = Tabulator(desc, cuda_device)
+    nodes = numpy.asarray(desc["nodes"])
+    sd = nodes.shape[1]
+    eye = torch.eye(len(nodes), dtype=torch.float64, device=cuda_device)
+    for flags, tol in ((0, 1e-13), (FORCE_GENERAL, 1e-10)):
+        vals = tab.tabulate(0, nodes, flags=flags)[(0,) * sd]
+        assert (vals - eye).abs().max().item() <= tol
