@@ -20,13 +20,14 @@ class SimplexProgramStruct(ctypes.Structure):
         ("sd", c_i32), ("degree", c_i32), ("order", c_i32), ("na", c_i32), ("expansion", c_i32),
         ("ncells", c_i32), ("nslots", c_i32), ("nrows", c_i32), ("ncomp", c_i32), ("unique", c_i32),
         ("nsteps", c_i32), ("nlevels", c_i32), ("nfix", c_i32), ("nfixgrp", c_i32), ("line_n", c_i32),
+        ("start_slot", c_i32),
         ("step_idx", p_i32), ("step_abc", p_dbl), ("nat_abc", p_dbl), ("level_ptr", p_i32),
         ("fix_idx", p_i32), ("fix_w", p_dbl), ("fix_grp", p_i32),
         ("geom", p_dbl), ("bary", p_dbl), ("ccell", p_dbl), ("ccell_morton", p_dbl),
         ("low1", p_i32), ("mul1", p_dbl), ("low2", p_i32), ("mul2", p_dbl),
         ("line_tab", p_dbl), ("line_tab_len", c_i64),
         ("nrb", c_i32), ("kpad", c_i32), ("nblk", c_i32),
-        ("blk_ptr", p_i32), ("blk_kb", p_i32), ("blk_frag", p_dbl), ("rb_order", p_i32),
+        ("blk_ptr", p_i32), ("blk_kb", p_i32), ("blk_frag", p_dbl), ("rb_order", p_i32), ("row_perm", p_i32),
     ]
 
 
@@ -126,6 +127,7 @@ def simplex_struct(prog):
     s.ncomp = prog.nrows // max(prog.ndofs, 1)
     s.nsteps, s.nlevels, s.nfix, s.line_n = len(prog.step_idx), len(prog.level_ptr) - 1, len(prog.fix_idx), prog.line_n
     s.nfixgrp = len(prog.fix_grp)
+    s.start_slot = prog.start_slot
     s.step_idx, s.step_abc, s.level_ptr = i32(prog.step_idx), f64(prog.step_abc), i32(prog.level_ptr)
     s.nat_abc, s.ccell_morton = f64(prog.nat_abc), f64(prog.ccell_morton)
     s.fix_idx, s.fix_w, s.fix_grp = i32(prog.fix_idx), f64(prog.fix_w), i32(prog.fix_grp)
@@ -134,6 +136,7 @@ def simplex_struct(prog):
     s.line_tab, s.line_tab_len = f64(prog.line_tab), int(numpy.size(prog.line_tab))
     s.nrb, s.kpad, s.nblk = len(prog.blk_ptr) - 1, prog.kpad, len(prog.blk_kb)
     s.blk_ptr, s.blk_kb, s.blk_frag, s.rb_order = i32(prog.blk_ptr), i32(prog.blk_kb), f64(prog.blk_frag), i32(prog.rb_order)
+    s.row_perm = i32(prog.row_perm if len(prog.row_perm) else numpy.arange(prog.nrows))
     return s, keep
 
 

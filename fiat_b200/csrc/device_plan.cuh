@@ -22,6 +22,7 @@ struct StepRec {
 
 struct RecTab {
     int nsteps, nlevels, nfix, nfixgrp;
+    int start_slot;                 // slot of member 0
     short level_ptr[FB_MAX_LEVELS + 2];
     short fix_tgt[FB_MAX_FIX], fix_first[FB_MAX_FIX], fix_cnt[FB_MAX_FIX];   // per distinct target
     short fix_src[FB_MAX_FIX];
@@ -30,6 +31,7 @@ struct RecTab {
     int nrb;                        // block-sparse coefficient matrix: row blocks, longest first
     short rb_order[FB_MAX_RB];
     int blk_ptr[FB_MAX_RB + 1];
+    short row_perm[FB_MAX_RB * 8];  // packed row -> table row (-1: padding)
     StepRec steps[FB_MAX_STEPS];    // sorted by total degree of the member produced
 };
 

@@ -271,8 +271,9 @@ __device__ __forceinline__ void dubiner_point(const DevSimplex& P, const RecTab&
                                               int slot_stride, int comp_stride, int na) {
     double fa[3], fb[3];
     recurrence_factors<SD>(xref, fa, fb);
-    T[0] = start;
-    for (int a = 1; a < na; ++a) T[a * comp_stride] = 0.0;
+    double* T0 = T + (size_t)tab.start_slot * slot_stride;
+    T0[0] = start;
+    for (int a = 1; a < na; ++a) T0[a * comp_stride] = 0.0;
     for (int s = 0; s < tab.nsteps; ++s)
         run_step<SD, ORDER>(P, tab.steps[s], geom, fa, fb, T, slot_stride, comp_stride, na);
     for (int gi = 0; gi < tab.nfixgrp; ++gi) {

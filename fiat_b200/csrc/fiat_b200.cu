@@ -409,6 +409,8 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     }
     RecTab& R = plan->tab;
     R.nsteps = h->nsteps; R.nlevels = h->nlevels; R.nfix = h->nfix; R.nfixgrp = h->nfixgrp;
+    R.start_slot = h->start_slot;
+    if (h->start_slot < 0 || h->start_slot >= h->nslots) { delete plan; return fail(FIATB200_ERR_ARG, "start slot out of range"); }
     for (int i = 0; i <= h->nlevels; ++i) R.level_ptr[i] = (short)h->level_ptr[i];
     for (int i = 0; i < h->nsteps; ++i) {
         StepRec& r = R.steps[i];
@@ -427,6 +429,7 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
         R.nrb = h->nrb;
         for (int i = 0; i < h->nrb; ++i) R.rb_order[i] = (short)h->rb_order[i];
         for (int i = 0; i <= h->nrb; ++i) R.blk_ptr[i] = h->blk_ptr[i];
+        for (int i = 0; i < h->nrb * 8; ++i) R.row_perm[i] = (short)(i < h->nrows ? h->row_perm[i] : -1);
     }
     memset(&plan->small_tab, 0, sizeof(plan->small_tab));
     for (int i = 0; i < h->nsteps && i < FB_SMALL_MAX_STEPS; ++i)

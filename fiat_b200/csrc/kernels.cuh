@@ -190,7 +190,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             s_fb[c * PT + tid] = fb[c];
         }
         const double start = tab.geom0[12];
-        double* t0 = T + (tid / PW) * (PW * NA) + (tid % PW);
+        double* t0 = T + (size_t)tab.start_slot * G.ldT + (tid / PW) * (PW * NA) + (tid % PW);
 #pragma unroll
         for (int a = 0; a < NA; ++a) t0[a * PW] = (a == 0) ? start : 0.0;
     }
@@ -293,7 +293,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             for (int j = 0; j < CH; ++j) a_cur[j] = a_nxt[j];
             kb_cur = kb_nxt;
         }
-        const int row = rb * 8 + g;
+        const int row = tab.row_perm[rb * 8 + g];           // table row of this lane's packed row (-1: padding)
         const long long p0 = base + oct0 * 8 + 2 * t;
         // warp-uniform: a full 8-row x GO-octet tile with aligned rows and no placement map
         const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows;
@@ -301,8 +301,8 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             // trade fragments between lane groups g and g^4 so that one store instruction covers
             // 4 rows x 128 contiguous bytes (two octets) instead of 8 rows x 64 bytes
             const bool lo = g < 4;
-            double* row_lo = out + (size_t)(rb * 8 + (g & 3)) * ostride + base + oct0 * 8 + 2 * t;       // rows 0..3
-            double* row_hi = row_lo + 4 * ostride;                                                       // rows 4..7
+            double* row_lo = out + (size_t)tab.row_perm[rb * 8 + (g & 3)] * ostride + base + oct0 * 8 + 2 * t;     // packed rows 0..3
+            double* row_hi = out + (size_t)tab.row_perm[rb * 8 + 4 + (g & 3)] * ostride + base + oct0 * 8 + 2 * t; // packed rows 4..7
 #pragma unroll
             for (int s = 0; s < NA; ++s) {
 #pragma unroll
@@ -319,7 +319,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                     *reinterpret_cast<double2*>(row_hi + (size_t)s * astride + ocol) = second;
                 }
             }
-        } else if (row < P.nrows) {
+        } else if (row >= 0) {
             double sgn;
             const size_t orow = fb_map_row(M, row, sgn);
             if (!M.identity) {

@@ -204,6 +204,7 @@ class SimplexProgram:
     step_idx: numpy.ndarray     # (nsteps, 4) int32: next, cur, prev(-1 = first of chain), codim; level order
     step_abc: numpy.ndarray     # (nsteps, 3) Jacobi recurrence coefficients a, b, c
     nat_abc: numpy.ndarray      # (nsteps, 3) the same coefficients in generation order (pass, sub-index, i)
+    start_slot: int             # slot of member 0 (the constant function the recurrence starts from)
     ccell_morton: numpy.ndarray  # (ncells, nrows, nslots) coefficients on Morton-numbered members, fix-ups folded
     level_ptr: numpy.ndarray    # (degree + 1,) int32: steps producing degree d+1 are [level_ptr[d], level_ptr[d+1])
     fix_idx: numpy.ndarray      # (nfix, 2) int32 target, source slots
@@ -221,10 +222,11 @@ class SimplexProgram:
     blk_kb: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))
     blk_frag: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0))
     rb_order: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))
+    row_perm: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))   # packed row -> table row
     kpad: int = 0
 
 
-def _dubiner_tables(desc, order):
+def _dubiner_tables(desc, order, slot_perm=None):
     sd, n, variant = int(desc["sd"]), int(desc["degree"]), desc["variant"]
     ncells = int(desc["ncells"])
     c0 = bool(desc["c0"])
@@ -235,6 +237,11 @@ def _dubiner_tables(desc, order):
         entity_order, fix_pairs = list(range(nmem)), []
     slot_of = numpy.empty(nmem, dtype=numpy.int64)       # Morton member -> slot (output position)
     slot_of[entity_order] = numpy.arange(nmem)
+    if slot_perm is not None:
+        # renumber the slots: new slot j holds what used to be slot slot_perm[j]
+        inverse = numpy.empty(nmem, dtype=numpy.int64)
+        inverse[numpy.asarray(slot_perm)] = numpy.arange(nmem)
+        slot_of = inverse[slot_of]
 
     # steps, pass by pass (expansions.py:202-249)
     step_idx, step_abc, step_level = [], [], []
@@ -289,7 +296,9 @@ def _dubiner_tables(desc, order):
             fix_w.append(norm[s] / norm[t])
     fold_by_slot = numpy.empty(nmem)
     fold_by_slot[slot_of] = fold
+    pos_of_slot = numpy.arange(nmem) if slot_perm is None else numpy.asarray(slot_perm, dtype=numpy.int64)
     return dict(nslots=nmem, step_idx=step_idx, step_abc=step_abc, nat_abc=nat_abc, slot_of=slot_of,
+                start_slot=int(slot_of[0]), pos_of_slot=pos_of_slot,
                 geom=geom, level_ptr=level_ptr,
                 fix_idx=numpy.array(fix_idx, dtype=numpy.int32).reshape(-1, 2),
                 fix_w=numpy.array(fix_w, dtype=float), fold_by_slot=fold_by_slot)
@@ -332,6 +341,46 @@ def _line_tables(desc, order):
     return dict(nslots=nn, geom=geom, line_tab=tab, line_n=nn)
 
 
+def _greedy_groups(support, group):
+    """Order the rows of a boolean (items x features) matrix so that each run of `group` consecutive
+    items has a small feature union: start from the widest remaining item, keep adding the item
+    that enlarges the union least (ties: largest overlap)."""
+    left = list(range(support.shape[0]))
+    order = []
+    while left:
+        seed = max(left, key=lambda r: int(support[r].sum()))
+        left.remove(seed)
+        grp, sup = [seed], support[seed].copy()
+        while len(grp) < group and left:
+            sub = support[left]
+            grow = (sub & ~sup).sum(axis=1)
+            share = (sub & sup).sum(axis=1)
+            r = left.pop(int(numpy.lexsort((-share, grow))[0]))
+            grp.append(r)
+            sup |= support[r]
+        order.extend(grp)
+    return numpy.array(order, dtype=numpy.int64)
+
+
+def cluster_rows(C, drop_tol=0.0):
+    """Row order such that each group of 8 consecutive rows touches few 4-wide column blocks
+    (fewer stored 8x4 blocks = fewer DMMAs in the tile kernel)."""
+    nrows, K = C.shape
+    nkb = -(-K // 4)
+    z = numpy.zeros((nrows, nkb * 4), dtype=bool)
+    z[:, :K] = numpy.abs(C) > drop_tol
+    return _greedy_groups(z.reshape(nrows, nkb, 4).any(axis=2), 8)
+
+
+def cluster_cols(C, drop_tol=0.0):
+    """Column order such that each group of 4 consecutive columns touches few 8-row blocks."""
+    nrows, K = C.shape
+    nrb = -(-nrows // 8)
+    z = numpy.zeros((nrb * 8, K), dtype=bool)
+    z[:nrows] = numpy.abs(C) > drop_tol
+    return _greedy_groups(z.reshape(nrb, 8, K).any(axis=1).T, 4)
+
+
 def pack_blocks(C, drop_tol=0.0):
     """8x4 block-sparse packing of a (nrows, K) matrix in mma.m8n8k4 A-fragment order.
 
@@ -371,11 +420,33 @@ def compile_simplex(desc, order):
 
     if desc["expansion"] == "dubiner":
         t = _dubiner_tables(desc, order)
+        if ncells == 1 and nrows * nexp_total >= 1024:
+            # Large single-cell elements go to the tile kernel, whose cost is the number of stored
+            # 8x4 coefficient blocks: renumber the member slots (a free choice) so that groups of 4
+            # slots are used by few row blocks, if that stores fewer blocks.
+            def folded_matrix(tabs):
+                base = C[:, cnm[0][tabs["pos_of_slot"]]] * tabs["fold_by_slot"][None, :]
+                out = base.copy()
+                for (tgt, src), w in zip(tabs["fix_idx"], tabs["fix_w"]):
+                    out[:, src] -= w * base[:, tgt]
+                return out
+
+            def stored_blocks(mat):
+                tol = 1e-14 * numpy.abs(mat).max()
+                return len(pack_blocks(mat[cluster_rows(mat, tol)], tol)[1])
+
+            f0 = folded_matrix(t)
+            tol0 = 1e-14 * numpy.abs(f0).max()
+            cols = cluster_cols(f0[cluster_rows(f0, tol0)], tol0)
+            t_alt = _dubiner_tables(desc, order, slot_perm=cols)
+            if stored_blocks(folded_matrix(t_alt)) < stored_blocks(f0):
+                t = t_alt
         fold = t["fold_by_slot"]
         line_tab, line_n = numpy.zeros(0), 0
     else:
         t = _line_tables(desc, order)
         fold = numpy.ones(t["nslots"])
+        t["pos_of_slot"] = numpy.arange(t["nslots"])
         line_tab, line_n = t["line_tab"], t["line_n"]
         t.update(step_idx=numpy.zeros((0, 4), numpy.int32), step_abc=numpy.zeros((0, 3)), nat_abc=numpy.zeros((0, 3)),
                  slot_of=numpy.arange(t["nslots"]),
@@ -386,7 +457,8 @@ def compile_simplex(desc, order):
         raise ValueError("cell -> member map does not match the expansion set")
     ccell = numpy.empty((ncells, nrows, nslots))
     for c in range(ncells):
-        ccell[c] = C[:, cnm[c]] * fold[None, :]
+        # slot s holds the member the reference lists at position pos_of_slot[s] of the cell
+        ccell[c] = C[:, cnm[c][t["pos_of_slot"]]] * fold[None, :]
 
     # fix-ups sorted by target, with one (first, count) record per distinct target
     fix_idx, fix_w = t["fix_idx"], t["fix_w"]
@@ -414,7 +486,7 @@ def compile_simplex(desc, order):
         value_shape=tuple(int(s) for s in desc["value_shape"]),
         unique=int(bool(desc["c0"]) and order == 0),
         geom=t["geom"], bary=bary, step_idx=t["step_idx"], step_abc=t["step_abc"], level_ptr=t["level_ptr"],
-        nat_abc=t["nat_abc"], ccell_morton=ccell_morton,
+        nat_abc=t["nat_abc"], ccell_morton=ccell_morton, start_slot=int(t.get("start_slot", 0)),
         fix_idx=t["fix_idx"], fix_w=t["fix_w"],
         fix_grp=fix_grp, ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
     if ncells == 1:
@@ -423,7 +495,15 @@ def compile_simplex(desc, order):
         for (tgt, src), w in zip(prog.fix_idx, prog.fix_w):
             folded[:, src] -= w * ccell[0][:, tgt]
         scale = numpy.abs(folded).max() if folded.size else 0.0
-        (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = pack_blocks(folded, 1e-14 * scale)
+        # row blocks of the packed matrix are clusters of rows with similar column support
+        order = cluster_rows(folded, 1e-14 * scale)
+        natural = pack_blocks(folded, 1e-14 * scale)
+        clustered = pack_blocks(folded[order], 1e-14 * scale)
+        if len(clustered[1]) < len(natural[1]):
+            packed, prog.row_perm = clustered, order.astype(numpy.int32)
+        else:
+            packed, prog.row_perm = natural, numpy.arange(nrows, dtype=numpy.int32)
+        (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = packed
     return prog
 
 

@@ -50,6 +50,7 @@ typedef struct {
     int32_t ncomp;         /* prod(value_shape) */
     int32_t unique;        /* 1: first matching subcell wins (expansions.py:452,805-807) */
     int32_t nsteps, nlevels, nfix, nfixgrp, line_n;
+    int32_t start_slot;    /* slot of expansion member 0, where the recurrence starts */
     const int32_t* step_idx;   /* nsteps x 4: next, cur, prev (-1 first of chain), codim; sorted by the total
                                   degree of the member produced (wavefront order) */
     const double* step_abc;    /* nsteps x 3 Jacobi recurrence coefficients (expansions.py:24-40) */
@@ -76,6 +77,8 @@ typedef struct {
     const int32_t* blk_kb;     /* nblk */
     const double* blk_frag;    /* nblk x 32 */
     const int32_t* rb_order;   /* nrb, longest row block first */
+    const int32_t* row_perm;   /* nrows: packed row i holds table row row_perm[i] (rows are clustered by column
+                                  support so that fewer blocks are stored) */
 } fiatb200_simplex_program;
 
 /* Entity transform x_cell = x_entity * C + offset (FIAT/reference_element.py:570-609);

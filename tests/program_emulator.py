@@ -11,7 +11,7 @@ def _jets(prog, cell, x):
     sd, na = prog.sd, prog.na
     npts = x.shape[1]
     T = numpy.zeros((prog.nslots, na, npts))
-    T[0, 0] = prog.geom[cell, 12]
+    T[prog.start_slot, 0] = prog.geom[cell, 12]
     X = [x[i] for i in range(sd)] + [-numpy.ones(npts), -numpy.ones(npts)]
     pairs = [(d1, d2) for d1 in range(sd) for d2 in range(d1, sd)]
     g = prog.geom[cell]
@@ -72,7 +72,9 @@ def blocks_to_dense(prog):
         for q in range(prog.blk_ptr[rb], prog.blk_ptr[rb + 1]):
             kb = prog.blk_kb[q]
             C[rb * 8:rb * 8 + 8, kb * 4:kb * 4 + 4] = prog.blk_frag[q * 32:(q + 1) * 32].reshape(8, 4)
-    return C[:prog.nrows, :prog.nslots]
+    out = numpy.zeros((prog.nrows, prog.nslots))
+    out[prog.row_perm] = C[:prog.nrows, :prog.nslots]          # packed row i is table row row_perm[i]
+    return out
 
 
 def keys(prog):
