@@ -220,6 +220,8 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
             const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
             if (bytes <= limit) {
                 G->PT = pt;
+                G->logPT = 0;
+                while ((1 << G->logPT) < pt) ++G->logPT;
                 G->ldT = ld;
                 G->maxlev = maxlev;
                 G->skip = 0;

@@ -140,6 +140,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 struct MmaGeom {
     int PT;        // points per tile (multiple of 8)
     int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)
+    int logPT;     // log2(PT)
     int maxlev;    // most recurrence steps in one wavefront level
     int skip;      // profiling only: bit 0 skips the recurrence, bit 1 the contraction
 };
@@ -220,7 +221,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         }
         const int items = nst * PT;
         for (int it = tid; it < items; it += NT) {
-            const int sl = it / PT, pl = it % PT;
+            const int sl = it >> G.logPT, pl = it & (PT - 1);
             const double fa[3] = {s_fa[pl], s_fa[PT + pl], s_fa[2 * PT + pl]};
             const double fb[3] = {s_fb[pl], s_fb[PT + pl], s_fb[2 * PT + pl]};
             const StepRec r = rec[sl];
