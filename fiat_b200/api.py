@@ -30,6 +30,7 @@ __all__ = ["tabulate", "tabulate_into", "tabulate_host", "locate_subcells", "Tab
 FORCE_THREAD_PER_POINT = 1
 FORCE_DMMA = 2
 FORCE_GENERAL = 4          # do not use the product-form (lattice) kernel
+NO_VALUE_TABLE = 8         # do not use the value-table kernel (derivative-folded coefficients)
 
 
 def _resolve_simplex_entity(desc, entity):
@@ -203,7 +204,7 @@ class Tabulator:
         launch without a row map, wrapper elements one per part."""
         if order < 0:
             raise ValueError("order must be non-negative")
-        ckey = ("resolved", order, None if entity is None else str(entity), flags & 7)
+        ckey = ("resolved", order, None if entity is None else str(entity), flags & 15)
         hit = self._plans.get(ckey)
         if hit is not None:
             return hit
@@ -288,7 +289,7 @@ class Tabulator:
             return
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ld = pts.stride(0) if pts.shape[1] else 0
-        cflags = flags & 3
+        cflags = flags & 11
         with torch.cuda.device(self.device):
             if zero is not None:
                 _lib.check(self.lib.fiatb200_zero_rows(out.data_ptr(), row_stride, npts, out.shape[1], out.shape[0],
@@ -314,7 +315,7 @@ class Tabulator:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.fiatb200_tabulate_host(
                     p.handle, ctypes.byref(ent) if ent is not None else None, pts.ctypes.data, npts, pdim,
-                    out.ctypes.data, chunk_pts, flags & 3))
+                    out.ctypes.data, chunk_pts, flags & 11))
         elif npts:
             # wrapper elements: chunks through the device path, one device buffer
             for start in range(0, npts, chunk_pts):

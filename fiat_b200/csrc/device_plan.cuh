@@ -53,6 +53,8 @@ struct DevSimplex {
     const int* blk_kb;
     const double* blk_frag;
     const int* rb_order;
+    const double* cderiv;       // derivative-folded coefficients of the value-table kernel (ncp == 0: absent)
+    int cderiv_len, ncp;
 };
 
 // Placement of a kernel's rows inside a larger table (wrapper elements: enriched, mixed, H(div)/H(curl)
@@ -101,6 +103,21 @@ struct DevTensor {
     int total_doubles;          // per point: scratch + all leaf tables
     DevTensorLeaf leaf[FB_MAX_LEAVES];
     const int* alpha_leaf;      // nalpha x FB_MAX_LEAVES: alpha index of every leaf for each product alpha
+};
+
+// register / value-table kernels: recurrence coefficients and barycentric rows as a kernel parameter
+#define FB_SMALL_MAX_STEPS 35
+
+struct SmallTab {
+    double abc[FB_SMALL_MAX_STEPS][3];     // generation order: pass, sub-index (last entry outermost), i
+    double bary[33 * 16];                  // rescaled barycentric rows of <= 32 subcells + parent (constant bank)
+};
+
+// product-form (lattice) plan
+struct DevLattice {
+    int sd, degree, order, na, ndofs;
+    const int* rowmap;       // loop index (a0, a1[, a2]) -> dof row
+    const double* recip;     // 1 / (k + 1), k = 0..degree-1
 };
 
 __host__ __device__ constexpr int fb_binom(int n, int k) {

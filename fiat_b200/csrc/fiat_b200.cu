@@ -1,60 +1,17 @@
 // C ABI of the B200 tabulation library (see include/fiat_b200.h).
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-#include <stdlib.h>
-
-#include <algorithm>
-#include <atomic>
-#include <mutex>
-#include <string>
-#include <vector>
-
+#include "host_plan.cuh"
 #include "kernels.cuh"
 #include "lattice.cuh"
-#include "small.cuh"
 
 namespace {
-
 thread_local std::string g_error;
-std::atomic<long long> g_launches{0};
+}
+std::atomic<long long> fb_launches{0};
 
-int fail(int code, const std::string& msg) {
+int fb_fail(int code, const std::string& msg) {
     g_error = msg;
     return code;
 }
-
-#define FB_CUDA(expr)                                                                       \
-    do {                                                                                    \
-        cudaError_t e_ = (expr);                                                            \
-        if (e_ != cudaSuccess)                                                              \
-            return fail(FIATB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
-
-enum PlanKind { PLAN_SIMPLEX = 1, PLAN_TENSOR = 2, PLAN_LATTICE = 3 };
-
-}  // namespace
-
-struct fiatb200_plan {
-    int kind;
-    int device;
-    void* blob;             // one device allocation holding every table
-    DevSimplex simplex;
-    RecTab tab;             // host copy, passed to kernels by value
-    SmallTab small_tab;     // generation-order coefficients for the register kernel
-    DevTensor tensor;
-    DevLattice lattice;
-    int max_smem_optin;
-    int num_sms;
-    // staging for fiatb200_tabulate_host: two streams with one points/result buffer each, kept
-    // across calls so that the end-to-end path issues no allocation or stream creation per call
-    std::mutex host_mutex;
-    cudaStream_t host_stream[2];
-    double* host_pts[2];
-    double* host_out[2];
-    size_t host_pts_cap, host_out_cap;
-};
 
 namespace {
 
@@ -105,13 +62,6 @@ DevRowMap make_row_map(const fiatb200_row_map* m, int ncomp, int nrows) {
     return d;
 }
 
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024)
-        FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return FIATB200_OK;
-}
-
 // ---- thread-per-point launch -----------------------------------------------------------------
 template <int SD, int ORDER>
 int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
@@ -128,12 +78,12 @@ int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double*
     const int tables_in_smem = (table_bytes <= 32 * 1024 && smem + table_bytes <= (size_t)plan->max_smem_optin) ? 1 : 0;
     if (tables_in_smem) smem += table_bytes;
     if (smem > (size_t)plan->max_smem_optin)
-        return fail(FIATB200_ERR_UNSUPPORTED, "expansion table of one point tile does not fit in shared memory");
-    int rc = set_smem(k_cellwise<SD, ORDER>, smem);
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "expansion table of one point tile does not fit in shared memory");
+    int rc = fb_set_smem(k_cellwise<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
     k_cellwise<SD, ORDER><<<grid, bp, smem, st>>>(P, plan->tab, E, pts, npts, ldp, out, ostride, tables_in_smem, M);
-    g_launches++;
+    fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
@@ -148,52 +98,6 @@ int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const doubl
         case 3: return launch_cellwise<SD, 3>(plan, E, pts, npts, ldp, out, ostride, M, st);
         default: return launch_cellwise<SD, -1>(plan, E, pts, npts, ldp, out, ostride, M, st);
     }
-}
-
-// ---- register kernel for low-degree elements ------------------------------------------------------
-template <int SD, int N, int ORDER>
-int launch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
-                 double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    const DevSimplex& P = plan->simplex;
-    const size_t smem = ((size_t)P.ncells * P.nrows * P.nslots + (size_t)P.ncells * FB_GEOM_DOUBLES) * sizeof(double);
-    int rc = set_smem(k_small<SD, N, ORDER>, smem);
-    if (rc) return rc;
-    const int bp = 128;
-    const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_small<SD, N, ORDER><<<grid, bp, smem, st>>>(P, plan->small_tab, E, pts, npts, ldp, out, ostride, M);
-    g_launches++;
-    FB_CUDA(cudaGetLastError());
-    return FIATB200_OK;
-}
-
-// (sd, degree, order) combinations whose expansion table fits in registers (members x alphas <= 64)
-bool small_applicable(const fiatb200_plan* plan) {
-    const DevSimplex& P = plan->simplex;
-    if (P.expansion != 0 || P.order > 3 || P.degree < 1 || P.sd < 2) return false;
-    if (P.order == 3 && !(P.sd == 2 && P.degree <= 2)) return false;
-    if ((size_t)P.nslots * P.na > 64) return false;
-    if (P.sd == 2 && P.degree > 4) return false;
-    if (P.sd == 3 && P.degree > 3) return false;
-    const size_t smem = ((size_t)P.ncells * P.nrows * P.nslots + (size_t)P.ncells * FB_GEOM_DOUBLES) * sizeof(double);
-    return smem <= 64 * 1024;
-}
-
-#define FB_SMALL_CASE(SD_, N_, O_)                                                        \
-    if (P.sd == SD_ && P.degree == N_ && P.order == O_)                                   \
-        return launch_small<SD_, N_, O_>(plan, E, pts, npts, ldp, out, ostride, M, st);
-
-int dispatch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
-                   double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    const DevSimplex& P = plan->simplex;
-    FB_SMALL_CASE(2, 1, 0) FB_SMALL_CASE(2, 1, 1) FB_SMALL_CASE(2, 1, 2)
-    FB_SMALL_CASE(2, 2, 0) FB_SMALL_CASE(2, 2, 1) FB_SMALL_CASE(2, 2, 2)
-    FB_SMALL_CASE(2, 3, 0) FB_SMALL_CASE(2, 3, 1) FB_SMALL_CASE(2, 3, 2)
-    FB_SMALL_CASE(2, 4, 0) FB_SMALL_CASE(2, 4, 1)
-    FB_SMALL_CASE(2, 1, 3) FB_SMALL_CASE(2, 2, 3)
-    FB_SMALL_CASE(3, 1, 0) FB_SMALL_CASE(3, 1, 1) FB_SMALL_CASE(3, 1, 2)
-    FB_SMALL_CASE(3, 2, 0) FB_SMALL_CASE(3, 2, 1)
-    FB_SMALL_CASE(3, 3, 0)
-    return fail(FIATB200_ERR_UNSUPPORTED, "register kernel not instantiated for this element");
 }
 
 // ---- tile / DMMA launch ------------------------------------------------------------------------
@@ -237,7 +141,7 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
 template <int SD, int ORDER, int PW>
 int launch_mma_pw(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                   long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    int rc = set_smem(k_mma<SD, ORDER, PW>, smem);
+    int rc = fb_set_smem(k_mma<SD, ORDER, PW>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
     int threads = FB_MMA_THREADS;
@@ -246,7 +150,7 @@ int launch_mma_pw(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& 
     if (smem <= 110 * 1024) threads = 256;
     if (const char* env = getenv("FIATB200_MMA_THREADS")) threads = atoi(env) >= 512 ? 512 : 256;   // tuning override
     k_mma<SD, ORDER, PW><<<grid, threads, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
-    g_launches++;
+    fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
@@ -273,16 +177,19 @@ int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entit
                      long long ldp, double* out, long long ostride, const DevRowMap& M, uint32_t flags, cudaStream_t st) {
     const DevSimplex& P = plan->simplex;
     const DevEntity E = make_entity(entity, P.sd);
-    if (E.dim < 0 || E.dim > 3) return fail(FIATB200_ERR_ARG, "entity dimension out of range");
+    if (E.dim < 0 || E.dim > 3) return fb_fail(FIATB200_ERR_ARG, "entity dimension out of range");
     MmaGeom G;
     size_t smem = 0;
     bool use_mma = mma_geometry(plan, &G, &smem);
     // the tensor-pipe path pays off once the contraction dominates; tiny elements stay per-thread
     if (use_mma && !(flags & 2u) && (long long)P.nrows * P.nslots < 256) use_mma = false;
     if (flags & 1u) use_mma = false;
-    if ((flags & 2u) && !use_mma) return fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
-    // low-degree elements (and all split-cell ones of low degree): everything in registers
-    if (!(flags & 3u) && small_applicable(plan)) return dispatch_small(plan, E, pts, npts, ldp, out, ostride, M, st);
+    if ((flags & 2u) && !use_mma) return fb_fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
+    // low-degree elements (and all split-cell ones of low degree): value table in registers,
+    // derivatives through host-folded coefficient matrices
+    if (!(flags & 11u) && fb_vals_applicable(plan) && (!use_mma || fb_small_applicable(plan)))
+        return fb_dispatch_vals(plan, E, pts, npts, ldp, out, ostride, M, st);
+    if (!(flags & 3u) && fb_small_applicable(plan)) return fb_dispatch_small(plan, E, pts, npts, ldp, out, ostride, M, st);
     if (use_mma) {
         switch (P.sd) {
             case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
@@ -305,12 +212,22 @@ int tabulate_tensor(const fiatb200_plan* plan, const double* pts, long long npts
     while (bp > 32 && (size_t)Q.total_doubles * bp * sizeof(double) > 96 * 1024) bp >>= 1;
     const size_t smem = (size_t)Q.total_doubles * bp * sizeof(double);
     if (smem > (size_t)plan->max_smem_optin)
-        return fail(FIATB200_ERR_UNSUPPORTED, "factor tables of one point tile do not fit in shared memory");
-    int rc = set_smem(k_tensor, smem);
-    if (rc) return rc;
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "factor tables of one point tile do not fit in shared memory");
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
-    k_tensor<<<grid, bp, smem, st>>>(Q, pts, npts, ldp, out, ostride, M);
-    g_launches++;
+    int rc = FIATB200_OK;
+#define FB_TENSOR_LAUNCH(O_)                                                          \
+    rc = fb_set_smem(k_tensor<O_>, smem);                                                \
+    if (rc) return rc;                                                                \
+    k_tensor<O_><<<grid, bp, smem, st>>>(Q, pts, npts, ldp, out, ostride, M);
+    switch (Q.order) {
+        case 0: FB_TENSOR_LAUNCH(0) break;
+        case 1: FB_TENSOR_LAUNCH(1) break;
+        case 2: FB_TENSOR_LAUNCH(2) break;
+        case 3: FB_TENSOR_LAUNCH(3) break;
+        default: FB_TENSOR_LAUNCH(-1) break;
+    }
+#undef FB_TENSOR_LAUNCH
+    fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
@@ -324,12 +241,12 @@ int launch_lattice(const fiatb200_plan* plan, const DevEntity& E, const double* 
     while (bp > 32 && per_point * bp > 56 * 1024) bp >>= 1;          // keep >= 4 CTAs per SM resident
     const size_t smem = per_point * bp;
     if (smem > (size_t)plan->max_smem_optin)
-        return fail(FIATB200_ERR_UNSUPPORTED, "lattice factor tables do not fit in shared memory");
-    int rc = set_smem(k_lattice<SD, ORDER>, smem);
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "lattice factor tables do not fit in shared memory");
+    int rc = fb_set_smem(k_lattice<SD, ORDER>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
     k_lattice<SD, ORDER><<<grid, bp, smem, st>>>(L, E, pts, npts, ldp, out, ostride, M);
-    g_launches++;
+    fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
@@ -392,14 +309,14 @@ int fiatb200_version(void) { return 1; }
 
 const char* fiatb200_last_error(void) { return g_error.c_str(); }
 
-int64_t fiatb200_launch_count(void) { return g_launches.load(); }
+int64_t fiatb200_launch_count(void) { return fb_launches.load(); }
 
 int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_plan** out) {
-    if (!h || !out) return fail(FIATB200_ERR_ARG, "null argument");
-    if (h->sd < 1 || h->sd > 3) return fail(FIATB200_ERR_UNSUPPORTED, "spatial dimension must be 1, 2 or 3");
-    if (h->ncells < 1 || h->ncells > 32) return fail(FIATB200_ERR_UNSUPPORTED, "at most 32 subcells are supported");
-    if (h->na < 1 || h->na > FB_NA_MAX) return fail(FIATB200_ERR_UNSUPPORTED, "derivative order too high");
-    if (h->expansion != 0 && h->sd != 1) return fail(FIATB200_ERR_ARG, "line expansion on a non-line cell");
+    if (!h || !out) return fb_fail(FIATB200_ERR_ARG, "null argument");
+    if (h->sd < 1 || h->sd > 3) return fb_fail(FIATB200_ERR_UNSUPPORTED, "spatial dimension must be 1, 2 or 3");
+    if (h->ncells < 1 || h->ncells > 32) return fb_fail(FIATB200_ERR_UNSUPPORTED, "at most 32 subcells are supported");
+    if (h->na < 1 || h->na > FB_NA_MAX) return fb_fail(FIATB200_ERR_UNSUPPORTED, "derivative order too high");
+    if (h->expansion != 0 && h->sd != 1) return fb_fail(FIATB200_ERR_ARG, "line expansion on a non-line cell");
     fiatb200_plan* plan = new_plan();
     plan->kind = PLAN_SIMPLEX;
     int rc = device_limits(plan);
@@ -407,12 +324,12 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
 
     if (h->nsteps > FB_MAX_STEPS || h->nlevels > FB_MAX_LEVELS || h->nfix > FB_MAX_FIX || h->nfixgrp > FB_MAX_FIX) {
         delete plan;
-        return fail(FIATB200_ERR_UNSUPPORTED, "expansion degree too high for the device recurrence tables");
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "expansion degree too high for the device recurrence tables");
     }
     RecTab& R = plan->tab;
     R.nsteps = h->nsteps; R.nlevels = h->nlevels; R.nfix = h->nfix; R.nfixgrp = h->nfixgrp;
     R.start_slot = h->start_slot;
-    if (h->start_slot < 0 || h->start_slot >= h->nslots) { delete plan; return fail(FIATB200_ERR_ARG, "start slot out of range"); }
+    if (h->start_slot < 0 || h->start_slot >= h->nslots) { delete plan; return fb_fail(FIATB200_ERR_ARG, "start slot out of range"); }
     for (int i = 0; i <= h->nlevels; ++i) R.level_ptr[i] = (short)h->level_ptr[i];
     for (int i = 0; i < h->nsteps; ++i) {
         StepRec& r = R.steps[i];
@@ -453,13 +370,15 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     const size_t o_blk_kb = A.add(h->blk_kb, sizeof(int32_t) * h->nblk);
     const size_t o_blk_frag = A.add(h->blk_frag, sizeof(double) * 32 * (size_t)h->nblk);
     const size_t o_rb_order = A.add(h->rb_order, sizeof(int32_t) * h->nrb);
+    const bool has_cderiv = h->ncp > 0 && h->cderiv && h->cderiv_len > 0;
+    const size_t o_cderiv = A.add(h->cderiv, has_cderiv ? sizeof(double) * (size_t)h->cderiv_len : 0);
 
     cudaError_t e = cudaMalloc(&plan->blob, A.host.size() + 256);
     if (e == cudaSuccess) e = cudaMemcpy(plan->blob, A.host.data(), A.host.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         if (plan->blob) cudaFree(plan->blob);
         delete plan;
-        return fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+        return fb_fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
     }
     DevSimplex& P = plan->simplex;
     P.sd = h->sd; P.degree = h->degree; P.order = h->order; P.na = h->na; P.expansion = h->expansion;
@@ -482,15 +401,18 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     P.blk_kb = at<int>(b, o_blk_kb);
     P.blk_frag = at<double>(b, o_blk_frag);
     P.rb_order = at<int>(b, o_rb_order);
+    P.cderiv = at<double>(b, o_cderiv);
+    P.cderiv_len = has_cderiv ? (int)h->cderiv_len : 0;
+    P.ncp = has_cderiv ? h->ncp : 0;
     *out = plan;
     return FIATB200_OK;
 }
 
 int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nleaf, int32_t order,
                                 fiatb200_plan** out) {
-    if (!leaves || !out) return fail(FIATB200_ERR_ARG, "null argument");
+    if (!leaves || !out) return fb_fail(FIATB200_ERR_ARG, "null argument");
     if (nleaf < 1 || nleaf > FB_MAX_LEAVES)
-        return fail(FIATB200_ERR_UNSUPPORTED, "tensor-product elements with 1..4 scalar factors are supported");
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "tensor-product elements with 1..4 scalar factors are supported");
     fiatb200_plan* plan = new_plan();
     plan->kind = PLAN_TENSOR;
     int rc = device_limits(plan);
@@ -504,7 +426,7 @@ int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nlea
         const fiatb200_plan* lp = leaves[l].plan;
         if (!lp || lp->kind != PLAN_SIMPLEX || lp->simplex.order != order) {
             delete plan;
-            return fail(FIATB200_ERR_ARG, "tensor leaves must be simplex plans of the same derivative order");
+            return fb_fail(FIATB200_ERR_ARG, "tensor leaves must be simplex plans of the same derivative order");
         }
         Q.leaf[l].prog = lp->simplex;
         Q.leaf[l].ent = make_entity(&leaves[l].entity, lp->simplex.sd);
@@ -525,7 +447,7 @@ int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nlea
     }
     if (nvector > 1) {
         delete plan;
-        return fail(FIATB200_ERR_UNSUPPORTED, "at most one vector-valued tensor-product factor (tensor_product.py:271-272)");
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "at most one vector-valued tensor-product factor (tensor_product.py:271-272)");
     }
     for (int l = nleaf - 1, stride = 1; l >= 0; --l) {
         Q.leaf[l].dof_stride = stride;
@@ -577,7 +499,7 @@ int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nlea
     if (e != cudaSuccess) {
         if (plan->blob) cudaFree(plan->blob);
         delete plan;
-        return fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+        return fb_fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
     }
     Q.alpha_leaf = static_cast<const int*>(plan->blob);
     *out = plan;
@@ -586,10 +508,10 @@ int fiatb200_tensor_plan_create(const fiatb200_tensor_leaf* leaves, int32_t nlea
 
 int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, const int32_t* rowmap, int32_t ndofs,
                                  fiatb200_plan** out) {
-    if (!rowmap || !out) return fail(FIATB200_ERR_ARG, "null argument");
+    if (!rowmap || !out) return fb_fail(FIATB200_ERR_ARG, "null argument");
     if ((sd != 2 && sd != 3) || order < 0 || order > 2 || degree < 1)
-        return fail(FIATB200_ERR_UNSUPPORTED, "lattice plans cover sd 2..3, order <= 2, degree >= 1");
-    if (ndofs != fb_binom(degree + sd, sd)) return fail(FIATB200_ERR_ARG, "ndofs does not match the lattice");
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "lattice plans cover sd 2..3, order <= 2, degree >= 1");
+    if (ndofs != fb_binom(degree + sd, sd)) return fb_fail(FIATB200_ERR_ARG, "ndofs does not match the lattice");
     fiatb200_plan* plan = new_plan();
     plan->kind = PLAN_LATTICE;
     int rc = device_limits(plan);
@@ -604,7 +526,7 @@ int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, cons
     if (e != cudaSuccess) {
         if (plan->blob) cudaFree(plan->blob);
         delete plan;
-        return fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+        return fb_fail(FIATB200_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
     }
     DevLattice& L = plan->lattice;
     L.sd = sd; L.degree = degree; L.order = order; L.na = fb_binom(sd + order, order); L.ndofs = ndofs;
@@ -623,7 +545,7 @@ int fiatb200_plan_destroy(fiatb200_plan* plan) {
 }
 
 int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalpha) {
-    if (!plan) return fail(FIATB200_ERR_ARG, "null plan");
+    if (!plan) return fb_fail(FIATB200_ERR_ARG, "null plan");
     if (plan->kind == PLAN_SIMPLEX) {
         if (nrows) *nrows = plan->simplex.nrows;
         if (nalpha) *nalpha = plan->simplex.na;
@@ -640,10 +562,10 @@ int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalp
 int fiatb200_tabulate_mapped(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,
                              int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride,
                              const fiatb200_row_map* map, uint32_t flags, void* stream) {
-    if (!plan) return fail(FIATB200_ERR_ARG, "null plan");
-    if (npts < 0 || out_row_stride < npts) return fail(FIATB200_ERR_ARG, "bad point count / row stride");
+    if (!plan) return fb_fail(FIATB200_ERR_ARG, "null plan");
+    if (npts < 0 || out_row_stride < npts) return fb_fail(FIATB200_ERR_ARG, "bad point count / row stride");
     if (npts == 0) return FIATB200_OK;
-    if (!out_dev || (!pts_dev && pts_ld != 0)) return fail(FIATB200_ERR_ARG, "null device pointer");
+    if (!out_dev || (!pts_dev && pts_ld != 0)) return fb_fail(FIATB200_ERR_ARG, "null device pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int ncomp = 1;
     int64_t nrows = 0;
@@ -652,12 +574,12 @@ int fiatb200_tabulate_mapped(const fiatb200_plan* plan, const fiatb200_entity_ma
     else { ncomp = plan->tensor.ncomp; nrows = plan->tensor.nrows; }
     if (map) {
         if (map->nc_in != ncomp || map->nc_in < 1 || map->nc_in > 9 || map->nc_out < 1)
-            return fail(FIATB200_ERR_ARG, "row map does not match the plan's components");
+            return fb_fail(FIATB200_ERR_ARG, "row map does not match the plan's components");
         for (int k = 0; k < map->nc_in; ++k)
             if (map->comp_out[k] < 0 || map->comp_out[k] >= map->nc_out)
-                return fail(FIATB200_ERR_ARG, "row map component out of range");
+                return fb_fail(FIATB200_ERR_ARG, "row map component out of range");
         if ((int64_t)(map->dof_base + nrows / ncomp) * map->nc_out > map->total_rows)
-            return fail(FIATB200_ERR_ARG, "row map exceeds the output table");
+            return fb_fail(FIATB200_ERR_ARG, "row map exceeds the output table");
     }
     const DevRowMap M = make_row_map(map, ncomp, (int)nrows);
     if (plan->kind == PLAN_SIMPLEX)
@@ -676,20 +598,20 @@ int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* enti
 int fiatb200_zero_rows(double* out_dev, int64_t out_row_stride, int64_t npts, int64_t total_rows, int32_t nalpha,
                        const int32_t* rows_dev, int32_t nrows, void* stream) {
     if (npts == 0 || nrows == 0) return FIATB200_OK;
-    if (!out_dev || !rows_dev || out_row_stride < npts) return fail(FIATB200_ERR_ARG, "bad arguments");
+    if (!out_dev || !rows_dev || out_row_stride < npts) return fb_fail(FIATB200_ERR_ARG, "bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)((npts + 127) / 128);
     k_zero_rows<<<grid, 128, 0, st>>>(out_dev, out_row_stride, npts, total_rows, nalpha, rows_dev, nrows);
-    g_launches++;
+    fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
 
 int fiatb200_locate_subcells(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts_dev,
                              int64_t npts, int64_t pts_ld, int32_t unique, uint32_t* mask_out_dev, void* stream) {
-    if (!plan || plan->kind != PLAN_SIMPLEX) return fail(FIATB200_ERR_ARG, "a simplex plan is required");
+    if (!plan || plan->kind != PLAN_SIMPLEX) return fb_fail(FIATB200_ERR_ARG, "a simplex plan is required");
     if (npts == 0) return FIATB200_OK;
-    if (!mask_out_dev || (!pts_dev && pts_ld != 0)) return fail(FIATB200_ERR_ARG, "null device pointer");
+    if (!mask_out_dev || (!pts_dev && pts_ld != 0)) return fb_fail(FIATB200_ERR_ARG, "null device pointer");
     const DevSimplex& P = plan->simplex;
     const DevEntity E = make_entity(entity, P.sd);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -699,17 +621,17 @@ int fiatb200_locate_subcells(const fiatb200_plan* plan, const fiatb200_entity_ma
         case 2: k_locate<2><<<grid, 128, 0, st>>>(P, E, pts_dev, npts, pts_ld, unique, mask_out_dev); break;
         default: k_locate<3><<<grid, 128, 0, st>>>(P, E, pts_dev, npts, pts_ld, unique, mask_out_dev); break;
     }
-    g_launches++;
+    fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
 
 int fiatb200_tabulate_host(const fiatb200_plan* cplan, const fiatb200_entity_map* entity, const double* pts_host,
                            int64_t npts, int64_t pts_ld, double* out_host, int64_t chunk_pts, uint32_t flags) {
-    if (!cplan) return fail(FIATB200_ERR_ARG, "null plan");
+    if (!cplan) return fb_fail(FIATB200_ERR_ARG, "null plan");
     if (npts == 0) return FIATB200_OK;
     if ((!pts_host && pts_ld != 0) || !out_host || chunk_pts <= 0)
-        return fail(FIATB200_ERR_ARG, "bad host buffers / chunk size");
+        return fb_fail(FIATB200_ERR_ARG, "bad host buffers / chunk size");
     fiatb200_plan* plan = const_cast<fiatb200_plan*>(cplan);
     std::lock_guard<std::mutex> guard(plan->host_mutex);
     int64_t nrows = 0, nalpha = 0;
@@ -746,7 +668,7 @@ int fiatb200_tabulate_host(const fiatb200_plan* cplan, const fiatb200_entity_map
     }
     for (int i = 0; i < 2; ++i) {
         cudaError_t e = cudaStreamSynchronize(plan->host_stream[i]);
-        if (e != cudaSuccess && rc == FIATB200_OK) rc = fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
+        if (e != cudaSuccess && rc == FIATB200_OK) rc = fb_fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
     }
     return rc;
 }

@@ -356,7 +356,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
 // ---------------------------------------------------------------------------------------------
 // tensor-product kernel
 // ---------------------------------------------------------------------------------------------
-template <int SD>
+template <int SD, int ORDER>
 __device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double* __restrict__ pt, double* scratch,
                                            double* table, int BP) {
     const DevSimplex& P = L.prog;
@@ -369,7 +369,7 @@ __device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double*
     while (mask) {
         const int cell = __ffs(mask) - 1;
         mask &= mask - 1;
-        expansion_point<SD, -1>(P, *P.tab, P.geom + cell * FB_GEOM_DOUBLES, cell, inv_mult, x, scratch, na * BP, BP, na);
+        expansion_point<SD, ORDER>(P, *P.tab, P.geom + cell * FB_GEOM_DOUBLES, cell, inv_mult, x, scratch, na * BP, BP, na);
         const double* C = P.ccell + (size_t)cell * P.nrows * P.nslots;
         for (int r = 0; r < P.nrows; ++r) {
             for (int a = 0; a < na; ++a) {
@@ -431,6 +431,7 @@ __device__ __forceinline__ void emit_products(double f, int dofacc, int comp, co
     }
 }
 
+template <int ORDER>
 __global__ void __launch_bounds__(128)
 k_tensor(const DevTensor Q, const double* __restrict__ pts, long long npts, long long ldp,
          double* __restrict__ out, long long ostride, const __grid_constant__ DevRowMap M) {
@@ -444,9 +445,9 @@ k_tensor(const DevTensor Q, const double* __restrict__ pts, long long npts, long
     for (int l = 0; l < Q.nleaf; ++l) {
         const DevTensorLeaf& L = Q.leaf[l];
         double* table = smem + (size_t)L.table_off * BP + tid;
-        if (L.prog.sd == 1) leaf_table<1>(L, pt, scratch, table, BP);
-        else if (L.prog.sd == 2) leaf_table<2>(L, pt, scratch, table, BP);
-        else leaf_table<3>(L, pt, scratch, table, BP);
+        if (L.prog.sd == 1) leaf_table<1, ORDER>(L, pt, scratch, table, BP);
+        else if (L.prog.sd == 2) leaf_table<2, ORDER>(L, pt, scratch, table, BP);
+        else leaf_table<3, ORDER>(L, pt, scratch, table, BP);
     }
     for (int al = 0; al < Q.nalpha; ++al) {
         const int* aidx = Q.alpha_leaf + al * FB_MAX_LEAVES;

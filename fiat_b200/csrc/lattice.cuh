@@ -19,11 +19,6 @@
 #pragma once
 #include "expansion.cuh"
 
-struct DevLattice {
-    int sd, degree, order, na, ndofs;
-    const int* rowmap;       // loop index (a0, a1[, a2]) -> dof row
-    const double* recip;     // 1 / (k + 1), k = 0..degree-1
-};
 
 template <int SD, int ORDER>
 __global__ void __launch_bounds__(128)

@@ -9,12 +9,6 @@
 #pragma once
 #include "expansion.cuh"
 
-#define FB_SMALL_MAX_STEPS 35
-
-struct SmallTab {
-    double abc[FB_SMALL_MAX_STEPS][3];     // generation order: pass, sub-index (last entry outermost), i
-    double bary[33 * 16];                  // rescaled barycentric rows of <= 32 subcells + parent (constant bank)
-};
 
 __host__ __device__ constexpr int fb_morton2(int p, int q) { return (p + q) * (p + q + 1) / 2 + q; }
 __host__ __device__ constexpr int fb_morton3(int p, int q, int r) {

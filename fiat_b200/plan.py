@@ -224,6 +224,10 @@ class SimplexProgram:
     rb_order: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))
     row_perm: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))   # packed row -> table row
     kpad: int = 0
+    # derivative-folded coefficients for the value-table kernel (see derivative_coefficients)
+    cderiv: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0))
+    ncp: int = 0                # subcell stride of cderiv (ncells padded to 1, 4 or 16); 0 = absent
+    slot_of: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int64))    # Morton member -> slot
 
 
 def _dubiner_tables(desc, order, slot_perm=None):
@@ -406,6 +410,92 @@ def pack_blocks(C, drop_tol=0.0):
     return blk_ptr, numpy.array(blk_kb, dtype=numpy.int32), frags, rb_order, nkb * 4
 
 
+def _member_degree(m, sd):
+    """Total degree of the Morton-numbered member m (members are numbered degree by degree)."""
+    k = 0
+    while math.comb(k + sd, sd) <= m:
+        k += 1
+    return k
+
+
+def _member_values(t, sd, x):
+    """Un-normalised, Morton-numbered members (start value 1) at default-simplex points x (sd, npts).
+    Works on complex points too, which is how the gradients are taken (complex step)."""
+    T = numpy.zeros((t["nslots"],) + x.shape[1:], dtype=x.dtype)
+    T[t["start_slot"]] = 1.0
+    minus = numpy.zeros_like(x[0]) - 1.0
+    X = [x[i] for i in range(sd)] + [minus, minus]
+    for (nxt, cur, prv, codim), (a, b, c) in zip(t["step_idx"], t["step_abc"]):
+        fb = 0.5 * (X[codim + 1] + X[codim + 2])
+        fa = X[codim] + (fb + 1.0)
+        v = (a * fa - b * fb) * T[cur]
+        if prv >= 0:
+            v = v - c * (fb * fb) * T[prv]
+        T[nxt] = v
+    return T[t["slot_of"]]
+
+
+def _derivative_matrices(t, sd, n):
+    """D[i][m, m'] with  d psi_m / d xi_i = sum_m' D[i][m, m'] psi_m'  for the un-normalised Morton-numbered
+    members on the default simplex.  The members of degree <= k span P_k, so row m only involves members
+    of lower degree; each degree level is fitted on its own (well-conditioned) lower-degree block.
+    Gradients are exact to rounding (complex step on the polynomial recurrence)."""
+    nmem = t["nslots"]
+    lat = n + 3
+    idx = numpy.array([i for i in numpy.ndindex(*([lat + 1] * sd)) if sum(i) <= lat], dtype=float)
+    pts = (2.0 * idx / lat - 1.0).T                                     # (sd, npts), vertices (-1,..), (1,-1,..)
+    V = _member_values(t, sd, pts)
+    scale = numpy.abs(V).max(axis=1)
+    Vs = V / scale[:, None]
+    deg = numpy.array([_member_degree(m, sd) for m in range(nmem)])
+    D = numpy.zeros((sd, nmem, nmem))
+    h = 1e-40
+    for i in range(sd):
+        xc = pts.astype(complex)
+        xc[i] += 1j * h
+        Gs = _member_values(t, sd, xc).imag / h / scale[:, None]
+        for k in range(1, n + 1):
+            rows = numpy.flatnonzero(deg == k)
+            nlow = math.comb(k - 1 + sd, sd)
+            sol = numpy.linalg.lstsq(Vs[:nlow].T, Gs[rows].T, rcond=None)[0]      # (nlow, len(rows))
+            D[i][rows[:, None], numpy.arange(nlow)[None, :]] = sol.T * scale[rows][:, None] / scale[None, :nlow]
+    return D
+
+
+def derivative_coefficients(desc, t, ccell_morton, order):
+    """Coefficient tables of the value-table kernel: out_alpha = C_alpha[cell] . psi(x), where psi are the
+    member VALUES only.  D^alpha of a member of degree k is a combination of the members of degree
+    <= k - |alpha| (FIAT itself relies on this: ExpansionSet.get_dmats, expansions.py:577-599), so the
+    derivative jets of the recurrence (expansions.py:66-137) are replaced by host-side matrix products
+    and the contraction for |alpha| = k only runs over C(n - k + sd, sd) members.
+
+    Returns (flat, ncp): flat[(off_a + r * nm_k + m) * ncp + cell], alphas in mis order (the subcell index
+    fastest keeps the lanes of a warp, whose points lie in different subcells, on distinct shared-memory
+    banks), or (None, 0)."""
+    sd, n = int(desc["sd"]), int(desc["degree"])
+    ncells, nrows, nmem = ccell_morton.shape
+    if n < 1 or sd < 2 or order > 3 or ncells > 16 or n > (6 if sd == 2 else 4):
+        return None, 0          # outside the kernel's instantiations (small.cuh)
+    ncp = 1 if ncells == 1 else (4 if ncells <= 4 else 16)
+    D = _derivative_matrices(t, sd, n)
+    alphas = alpha_list(sd, order)
+    blocks = []
+    for alpha in alphas:
+        k = sum(alpha)
+        nm = math.comb(n - k + sd, sd) if k <= n else 0
+        blk = numpy.zeros((nrows, nm, ncp))
+        for c in range(ncells):
+            A = numpy.asarray(desc["cell_A"][c], dtype=float)          # xi = A x + b
+            Dx = [sum(A[i, j] * D[i] for i in range(sd)) for j in range(sd)]
+            Da = numpy.eye(nmem)
+            for j in range(sd):
+                for _ in range(alpha[j]):
+                    Da = Da @ Dx[j]
+            blk[:, :, c] = (ccell_morton[c] @ Da)[:, :nm]
+        blocks.append(blk.reshape(-1))
+    return numpy.concatenate(blocks) if blocks else numpy.zeros(0), ncp
+
+
 def compile_simplex(desc, order):
     """Build the SimplexProgram of a `kind == "simplex"` description for one derivative order."""
     sd, n = int(desc["sd"]), int(desc["degree"])
@@ -489,6 +579,11 @@ def compile_simplex(desc, order):
         nat_abc=t["nat_abc"], ccell_morton=ccell_morton, start_slot=int(t.get("start_slot", 0)),
         fix_idx=t["fix_idx"], fix_w=t["fix_w"],
         fix_grp=fix_grp, ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
+    if desc["expansion"] == "dubiner":
+        cder, ncp = derivative_coefficients(desc, t, ccell_morton, order)
+        if cder is not None:
+            prog.cderiv, prog.ncp = cder, ncp
+        prog.slot_of = numpy.asarray(t["slot_of"], dtype=numpy.int64)
     if ncells == 1:
         # the tile kernel has no fix-up phase: T' = X T  =>  C T' = (C X) T
         folded = ccell[0].copy()

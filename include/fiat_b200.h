@@ -79,6 +79,14 @@ typedef struct {
     const int32_t* rb_order;   /* nrb, longest row block first */
     const int32_t* row_perm;   /* nrows: packed row i holds table row row_perm[i] (rows are clustered by column
                                   support so that fewer blocks are stored) */
+    /* Derivative-folded coefficients for the value-table kernel (optional, ncp == 0: absent).  D^alpha of an
+     * expansion member of degree k lies in the span of the members of degree <= k - |alpha| (the fact behind
+     * ExpansionSet.get_dmats, FIAT/expansions.py:577-599), so out_alpha = C_alpha[cell] . (member values):
+     * cderiv[(off_alpha + row * nm_k + m) * ncp + cell], nm_k = C(degree - |alpha| + sd, sd), alphas in mis
+     * order, Morton-numbered un-normalised members, C0 fix-ups / normalisation / chain rule folded in. */
+    const double* cderiv;
+    int64_t cderiv_len;
+    int32_t ncp;               /* subcell stride: ncells padded to 1, 4 or 16 */
 } fiatb200_simplex_program;
 
 /* Entity transform x_cell = x_entity * C + offset (FIAT/reference_element.py:570-609);
@@ -138,7 +146,8 @@ int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalp
 /* Tabulate at npts device-resident points (row-major, leading dimension pts_ld doubles).
  * = CiarletElement.tabulate (FIAT/finite_element.py:181-197) / TensorProductElement.tabulate.
  * `entity` may be NULL for tensor plans (their leaves carry the factor entities).
- * flags: bit 0 forces the thread-per-point kernel, bit 1 forces the block-sparse DMMA kernel
+ * flags: bit 0 forces the thread-per-point kernel, bit 1 forces the block-sparse DMMA kernel, bit 3
+ *        disables the value-table kernel (derivative-folded coefficients)
  *        (testing / profiling); 0 lets the library choose. */
 int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* entity,
                       const double* pts_dev, int64_t npts, int64_t pts_ld,

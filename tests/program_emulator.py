@@ -64,6 +64,39 @@ def run_simplex(prog, pts, near):
     return out
 
 
+def run_value_table(prog, pts, near):
+    """The value-table kernel: member values only (no jets, no fix-ups), derivative-folded coefficients."""
+    import math
+    sd, n = prog.sd, prog.degree
+    npts = len(pts)
+    out = numpy.zeros((prog.na, prog.nrows, npts))
+    mult = near.sum(axis=0)
+    for c in range(prog.ncells):
+        ip = numpy.where(near[c])[0]
+        if len(ip) == 0:
+            continue
+        A = prog.geom[c, :sd * sd].reshape(sd, sd)
+        x = (pts[ip] @ A.T + prog.geom[c, 9:9 + sd]).T
+        # raw recurrence values in slot order, then Morton order
+        T = numpy.zeros((prog.nslots, len(ip)))
+        T[prog.start_slot] = prog.geom[c, 12]
+        X = [x[i] for i in range(sd)] + [-numpy.ones(len(ip))] * 2
+        for s, (nxt, cur, prv, codim) in enumerate(prog.step_idx):
+            a, b, cc = prog.step_abc[s]
+            fb = 0.5 * (X[codim + 1] + X[codim + 2])
+            fa = X[codim] + (fb + 1.0)
+            T[nxt] = (a * fa - b * fb) * T[cur] - (cc * (fb * fb) * T[prv] if prv >= 0 else 0.0)
+        T = T[prog.slot_of]
+        off = 0
+        for j, alpha in enumerate(alpha_list(sd, prog.order)):
+            k = sum(alpha)
+            nm = math.comb(n - k + sd, sd) if k <= n else 0
+            blk = prog.cderiv[off:off + prog.nrows * nm * prog.ncp].reshape(prog.nrows, nm, prog.ncp)[:, :, c]
+            off += prog.nrows * nm * prog.ncp
+            out[j][:, ip] += (blk @ T[:nm]) / (1.0 if prog.unique else mult[None, ip])
+    return out
+
+
 def blocks_to_dense(prog):
     """Rebuild the dense folded coefficient matrix from the 8x4 block packing."""
     nrb = len(prog.blk_ptr) - 1

@@ -50,6 +50,21 @@ def test_both_kernels_agree_with_oracle(name, cuda_device):
         _compare(desc, got, want)
 
 
+@pytest.mark.parametrize("name", golden_case_names())
+def test_value_table_and_jet_kernels_agree_with_golden(name, cuda_device):
+    """Low-degree (incl. split-cell) Dubiner elements: the value-table kernel (derivative-folded coefficients)
+    and the kernels that propagate derivative jets through the recurrence must both match the reference."""
+    from fiat_b200.api import Tabulator, FORCE_GENERAL, NO_VALUE_TABLE
+    case = load_case(name)
+    desc = case["desc"]
+    if desc["kind"] != "simplex" or desc["expansion"] != "dubiner" or case["order"] > 3:
+        pytest.skip("not a Dubiner simplex element")
+    tab = Tabulator(desc, cuda_device)
+    for flags in (FORCE_GENERAL, FORCE_GENERAL | NO_VALUE_TABLE):
+        got = tab.tabulate(case["order"], case["points"], case["entity"], flags=flags)
+        _compare(desc, got, case["ref"])
+
+
 @pytest.mark.parametrize("name", [n for n in golden_case_names()])
 def test_subcell_assignment_bit_exact(name, cuda_device):
     from fiat_b200.api import Tabulator

@@ -36,6 +36,29 @@ def test_program_reproduces_reference(name):
         assert abs(out[j] - ref).max() <= tolerance(desc, alpha) * scale, alpha
 
 
+@pytest.mark.parametrize("name", _simplex_dubiner_cases())
+def test_value_table_reproduces_reference(name):
+    """Derivative-folded coefficient tables (value-table kernel): out_alpha = C_alpha . member values."""
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    prog = planmod.compile_simplex(desc, order)
+    if prog.ncp == 0:
+        pytest.skip("outside the value-table kernel's range")
+    pts = numpy.asarray(case["points"], dtype=float)
+    tr = fiat_oracle.resolve_entity(desc, case["entity"])
+    if tr is not None:
+        pts = pts.reshape(len(pts), tr[0].shape[0]) @ tr[0] + tr[1]
+    near = fiat_oracle.locate_cells(desc, pts, unique=bool(prog.unique))
+    out = emu.run_value_table(prog, pts, near)
+    worst = 0.0
+    for j, alpha in enumerate(emu.keys(prog)):
+        ref = case["ref"][alpha].reshape(prog.nrows, -1)
+        scale = max(abs(ref).max(), 1e-300)
+        worst = max(worst, abs(out[j] - ref).max() / scale)
+        assert abs(out[j] - ref).max() <= tolerance(desc, alpha) * scale, alpha
+    print(name, "worst relative error", worst)
+
+
 def test_mis_order_matches_reference_keys():
     for name in golden_case_names():
         case = load_case(name)
