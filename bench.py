@@ -307,9 +307,14 @@ def main():
             hbm_peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
         except Exception:
             hbm_peak, peak_src = FALLBACK_HBM_GBS, "fallback"
-        ms_launch = ms / max(launches, 1)
+        # a step is one tabulation of the batch: one kernel launch, or one launch per derivative table when
+        # the element is split into per-alpha derived elements (plan.alpha_split); the roofline line is
+        # quoted on all launches of a step together (algorithmic bytes of the step / time of the step)
+        per_step = max(launches, 1) / args.steps
+        ms_launch = ms / args.steps
         achieved = bytes_per_point * batch / (ms_launch * 1e-3) / 1e9
         kernel = tab.kernel_path(order, args.flags)
+        kernels = tab.kernel_names(order, None, args.flags)
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
                 f"{args.workload}|{kernel}|{batch}", {}).get("bytes")
@@ -325,14 +330,14 @@ def main():
                        "l2": "every step streams %.1f GB of output through L2 (126 MB), which also evicts the %.0f MB of "
                              "input points between steps; no separate flush" % (8 * vpp * batch / 1e9, 8 * sd * batch / 1e6),
                        "sharding": "contiguous point shards, one rank per GPU, no collective",
-                       "kernel": kernel},
+                       "kernel": kernel, "kernels_per_step": kernels},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "values/s", "h2d_bytes_per_step": int(ne * sd * 8),
                     "d2h_bytes_per_step": int(ne * vpp * 8), "points_per_step": ne},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_point": bytes_per_point, "algorithmic_bytes_per_launch": bytes_per_point * batch,
-                         "kernel_ms": ms_launch, "kernel": kernel,
+                         "kernel_ms": ms_launch, "launches_per_step": per_step, "kernel": kernel,
                          "fp64_peak_tflops_measured": FP64_PEAK_TFLOPS},
             "clocks": clocks,
         }

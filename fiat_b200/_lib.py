@@ -63,7 +63,7 @@ _lib = None
 
 EXPORTS = [
     "fiatb200_version", "fiatb200_last_error", "fiatb200_simplex_plan_create", "fiatb200_tensor_plan_create",
-    "fiatb200_lattice_plan_create", "fiatb200_plan_destroy", "fiatb200_plan_shape", "fiatb200_tabulate", "fiatb200_tabulate_mapped", "fiatb200_zero_rows", "fiatb200_locate_subcells",
+    "fiatb200_lattice_plan_create", "fiatb200_plan_destroy", "fiatb200_plan_shape", "fiatb200_plan_kernel", "fiatb200_tabulate", "fiatb200_tabulate_mapped", "fiatb200_zero_rows", "fiatb200_locate_subcells",
     "fiatb200_tabulate_host", "fiatb200_launch_count",
 ]
 
@@ -84,6 +84,7 @@ def load():
     lib.fiatb200_tensor_plan_create.argtypes = [ctypes.POINTER(TensorLeafStruct), c_i32, c_i32, ctypes.POINTER(p_void)]
     lib.fiatb200_lattice_plan_create.argtypes = [c_i32, c_i32, c_i32, p_i32, c_i32, ctypes.POINTER(p_void)]
     lib.fiatb200_plan_destroy.argtypes = [p_void]
+    lib.fiatb200_plan_kernel.argtypes = [p_void, c_u32]
     lib.fiatb200_plan_shape.argtypes = [p_void, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     lib.fiatb200_tabulate.argtypes = [p_void, ctypes.POINTER(EntityMapStruct), p_void, c_i64, c_i64, p_void, c_i64,
                                       c_u32, p_void]

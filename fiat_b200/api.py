@@ -31,6 +31,8 @@ FORCE_THREAD_PER_POINT = 1
 FORCE_DMMA = 2
 FORCE_GENERAL = 4          # do not use the product-form (lattice) kernel
 NO_VALUE_TABLE = 8         # do not use the value-table kernel (derivative-folded coefficients)
+NO_ALPHA_SPLIT = 16        # do not split the tabulation into one derived order-0 element per alpha
+KERNEL_NAMES = {0: "none", 1: "cellwise", 2: "mma", 3: "small", 4: "vals", 5: "lattice", 6: "tensor"}
 
 
 def _resolve_simplex_entity(desc, entity):
@@ -143,6 +145,35 @@ class Tabulator:
         err = (a - b).abs().amax(dim=(1, 2)) / scale
         return bool((err <= 1e-13).all().item())
 
+    def _alpha_split_plans(self, desc, order, flags):
+        """Per-alpha derived order-0 plans (plan.alpha_split) when the element would otherwise run on the DMMA
+        tile kernel (or, for derivative orders it does not cover, the thread-per-point kernel) and the split
+        stores fewer coefficient blocks; None otherwise.
+        -> [(alpha index, plan or None for an identically zero table)]"""
+        if flags & (FORCE_THREAD_PER_POINT | FORCE_DMMA | NO_ALPHA_SPLIT) or order < 1:
+            return None
+        key = ("split", id(desc), order)
+        with self._lock:
+            if key in self._plans:
+                return self._plans[key]
+        main, prog = self._simplex_plan(desc, order)
+        out = None
+        if self.lib.fiatb200_plan_kernel(main.handle, flags & 11) in (1, 2):      # thread-per-point or DMMA tile
+            derived = planmod.alpha_split(desc, order, prog)
+            if derived is not None:
+                out = []
+                for j, (alpha, d) in enumerate(derived):
+                    out.append((j, None if d is None else self._simplex_plan(d, 0)[0], d))
+        with self._lock:
+            self._plans[key] = out
+        return out
+
+    def kernel_names(self, order, entity=None, flags=0):
+        """Names of the kernels the launches of `tabulate(order, ...)` run on (diagnostics)."""
+        launches = self._resolve(order, entity, flags)[0]
+        return [KERNEL_NAMES.get(self.lib.fiatb200_plan_kernel(p.handle, flags & 11), "?") if p is not None else "zero"
+                for p, _, _, _ in launches]
+
     def kernel_path(self, order, flags=0):
         """Which device path `tabulate(order, ...)` takes: 'lattice', 'simplex' or 'tensor'."""
         if self.kind == "composite" or (self.kind == "flattened" and self.desc["element"]["kind"] == "composite"):
@@ -204,7 +235,7 @@ class Tabulator:
         launch without a row map, wrapper elements one per part."""
         if order < 0:
             raise ValueError("order must be non-negative")
-        ckey = ("resolved", order, None if entity is None else str(entity), flags & 15)
+        ckey = ("resolved", order, None if entity is None else str(entity), flags & 31)
         hit = self._plans.get(ckey)
         if hit is not None:
             return hit
@@ -221,14 +252,18 @@ class Tabulator:
         total_rows = ndofs * nc_out
         single = len(parts) == 1 and parts[0].dof_base == 0 and parts[0].comp_out == list(range(nc_out)) \
             and all(sg == 1.0 for sg in parts[0].sign)
-        launches, pdim = [], None
+        launches, pdim, zero_alpha_rows = [], None, []
         for part in parts:
             d = part.desc
+            split = None
             if d["kind"] == "simplex":
                 p, prog = self._simplex_plan(d, order)
+                fast = None
                 if not (flags & (FORCE_GENERAL | FORCE_THREAD_PER_POINT | FORCE_DMMA)):
                     fast = self._lattice_plan(d, order)
                     p = fast if fast is not None else p
+                if fast is None:
+                    split = self._alpha_split_plans(d, order, flags)
                 dim, tr = _resolve_simplex_entity(d, part.entity)
                 ent = _lib.entity_struct(prog.sd, tr)
             else:
@@ -239,8 +274,21 @@ class Tabulator:
             pdim = dim
             rmap = None if single else _lib.row_map_struct(len(part.comp_out), nc_out, part.dof_base, total_rows,
                                                             part.comp_out, part.sign)
-            launches.append((p, ent, rmap))
+            if split is None:
+                launches.append((p, ent, rmap, 0))
+            else:
+                # one derived order-0 element per alpha, written into that alpha's table
+                nd = planmod.num_dofs_of(d)
+                for j, sub, _ in split:
+                    if sub is not None:
+                        launches.append((sub, ent, rmap, j))
+                    else:
+                        rows = (numpy.arange(part.dof_base, part.dof_base + nd)[:, None] * nc_out
+                                + numpy.asarray(part.comp_out)[None, :]).reshape(-1)
+                        zero_alpha_rows.append((j, torch.as_tensor(rows.astype(numpy.int32), device=self.device)))
         zero = None
+        if zero_alpha_rows:
+            launches.extend((None, None, rows, j) for j, rows in zero_alpha_rows)
         if not single:
             key = ("zero", entity if entity is None else str(entity))
             with self._lock:
@@ -294,13 +342,19 @@ class Tabulator:
             if zero is not None:
                 _lib.check(self.lib.fiatb200_zero_rows(out.data_ptr(), row_stride, npts, out.shape[1], out.shape[0],
                                                         zero.data_ptr(), zero.numel(), stream))
-            for p, ent, rmap in launches:
+            for p, ent, rmap, aoff in launches:
+                # aoff: derivative table this launch writes (launches of per-alpha derived elements)
+                optr = out.data_ptr() + 8 * aoff * out.shape[1] * row_stride
+                if p is None:       # identically zero derivative table of a per-alpha split
+                    _lib.check(self.lib.fiatb200_zero_rows(optr, row_stride, npts, out.shape[1], 1,
+                                                            rmap.data_ptr(), rmap.numel(), stream))
+                    continue
                 _lib.check(self.lib.fiatb200_tabulate_mapped(
                     p.handle, ctypes.byref(ent) if ent is not None else None, pts.data_ptr(), npts, ld,
-                    out.data_ptr(), row_stride, ctypes.byref(rmap) if rmap is not None else None, cflags, stream))
+                    optr, row_stride, ctypes.byref(rmap) if rmap is not None else None, cflags, stream))
 
     def _launch(self, p, ent, pts, out, npts, flags, row_stride=None):
-        self._run([(p, ent, None)], None, pts, out, npts, npts if row_stride is None else row_stride, flags)
+        self._run([(p, ent, None, 0)], None, pts, out, npts, npts if row_stride is None else row_stride, flags)
 
     def tabulate_host(self, order, points, entity=None, chunk_pts=1 << 16, flags=0, out=None):
         """End-to-end with host (numpy) buffers: returns a dict of numpy arrays, like the reference."""
@@ -311,7 +365,7 @@ class Tabulator:
         if out is None:
             out = numpy.empty((len(alphas), nrows, npts))
         if npts and len(launches) == 1 and launches[0][2] is None:
-            p, ent, _ = launches[0]
+            p, ent, _, _ = launches[0]
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.fiatb200_tabulate_host(
                     p.handle, ctypes.byref(ent) if ent is not None else None, pts.ctypes.data, npts, pdim,

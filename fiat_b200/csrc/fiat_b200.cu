@@ -108,7 +108,7 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     const size_t budget = (size_t)plan->max_smem_optin - 1024;
     int pt_max = 128;
     if (const char* env = getenv("FIATB200_MMA_PT")) pt_max = std::max(8, atoi(env)) & ~7;   // tuning override
-    const int go = P.na >= 8 ? 1 : (P.na >= 5 ? 2 : 4);      // octets per contraction work item (kernels.cuh)
+    const int go = P.na >= 8 ? 1 : (P.na >= 5 ? 2 : (P.na >= 3 ? 4 : (P.na == 2 ? 8 : 16)));   // octets per contraction work item (kernels.cuh)
     int maxlev = 1;
     for (int l = 0; l < plan->tab.nlevels; ++l)
         maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
@@ -173,6 +173,54 @@ int dispatch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G
     }
 }
 
+enum KernelChoice { K_CELLWISE = 1, K_MMA = 2, K_SMALL = 3, K_VALS = 4, K_LATTICE = 5, K_TENSOR = 6 };
+
+// Which kernel a simplex plan runs on (flags: see include/fiat_b200.h).  Unless a flag forces one, the
+// applicable kernels are ranked by a per-SM cycle estimate for 32 points:
+//   HBM        32 points * 8 B * values/point at ~23.3 B per SM-cycle -- the floor of every kernel;
+//   DMMA tile  16 cycles per DMMA.8x8x4 on 4 tensor pipes, 4 octets, measured ~75 % busy, plus the jets;
+//   register / value-table kernels: one shared-memory wavefront per coefficient load (two when the lanes
+//              of a warp sit in different subcells) against 0.5 cycles per FP64 instruction.
+int choose_simplex_kernel(const fiatb200_plan* plan, uint32_t flags, MmaGeom* G, size_t* smem) {
+    const DevSimplex& P = plan->simplex;
+    bool use_mma = mma_geometry(plan, G, smem);
+    if (flags & 1u) use_mma = false;
+    if ((flags & 2u) && !use_mma) return 0;
+    if (flags & 2u) return K_MMA;
+    const bool vals_ok = !(flags & 11u) && fb_vals_applicable(plan);
+    const bool small_ok = !(flags & 3u) && fb_small_applicable(plan);
+    const double nmem = P.nslots, rows = P.nrows, na = P.na, steps = plan->tab.nsteps;
+    const double w = P.ncells > 1 ? 2.0 : 1.0;
+    const double hbm = 32.0 * 8.0 * na * rows / 23.3;
+    const double locate = P.ncells > 1 ? (P.ncells + 1.0) * (P.sd + 1) * (2 * P.sd + 3) : 0.0;
+    double best = 1e300;
+    int pick = K_CELLWISE;
+    if (use_mma && (long long)P.nrows * P.nslots >= 256) {
+        best = std::max(hbm, 16.0 * P.nblk * na / 0.75 + 0.5 * steps * 8.0 * na);
+        pick = K_MMA;
+    }
+    if (small_ok) {
+        const double c = std::max(hbm, std::max(w * rows * nmem, 0.5 * (rows * nmem * na + steps * 8.0 * na + locate)));
+        if (c <= best) { best = c; pick = K_SMALL; }
+    }
+    if (vals_ok) {
+        double c = 1e300;
+        for (int j = 0; j <= (P.order >= 1 ? 1 : 0); ++j) {
+            const double naj = fb_binom(P.sd + j, j);
+            double loads = rows * nmem, fma = rows * nmem * naj;
+            for (int k = j + 1; k <= P.order; ++k) {
+                const double work = (double)fb_binom(P.sd + k - 1, k) * rows * (k <= P.degree ? fb_binom(P.degree - k + P.sd, P.sd) : 0);
+                loads += work;
+                fma += work;
+            }
+            c = std::min(c, std::max(w * loads, 0.5 * (fma + steps * (3.0 + 5.0 * P.sd * j) + locate)));
+        }
+        c = std::max(c, hbm);
+        if (c <= best) { best = c; pick = K_VALS; }
+    }
+    return pick;
+}
+
 int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entity, const double* pts, long long npts,
                      long long ldp, double* out, long long ostride, const DevRowMap& M, uint32_t flags, cudaStream_t st) {
     const DevSimplex& P = plan->simplex;
@@ -180,22 +228,17 @@ int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entit
     if (E.dim < 0 || E.dim > 3) return fb_fail(FIATB200_ERR_ARG, "entity dimension out of range");
     MmaGeom G;
     size_t smem = 0;
-    bool use_mma = mma_geometry(plan, &G, &smem);
-    // the tensor-pipe path pays off once the contraction dominates; tiny elements stay per-thread
-    if (use_mma && !(flags & 2u) && (long long)P.nrows * P.nslots < 256) use_mma = false;
-    if (flags & 1u) use_mma = false;
-    if ((flags & 2u) && !use_mma) return fb_fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
-    // low-degree elements (and all split-cell ones of low degree): value table in registers,
-    // derivatives through host-folded coefficient matrices
-    if (!(flags & 11u) && fb_vals_applicable(plan) && (!use_mma || fb_small_applicable(plan)))
-        return fb_dispatch_vals(plan, E, pts, npts, ldp, out, ostride, M, st);
-    if (!(flags & 3u) && fb_small_applicable(plan)) return fb_dispatch_small(plan, E, pts, npts, ldp, out, ostride, M, st);
-    if (use_mma) {
-        switch (P.sd) {
-            case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-            case 2: return dispatch_mma<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-            default: return dispatch_mma<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-        }
+    switch (choose_simplex_kernel(plan, flags, &G, &smem)) {
+        case 0: return fb_fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
+        case K_VALS: return fb_dispatch_vals(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case K_SMALL: return fb_dispatch_small(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case K_MMA:
+            switch (P.sd) {
+                case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+                case 2: return dispatch_mma<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+                default: return dispatch_mma<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+            }
+        default: break;
     }
     switch (P.sd) {
         case 1: return dispatch_cellwise<1>(plan, E, pts, npts, ldp, out, ostride, M, st);
@@ -542,6 +585,15 @@ int fiatb200_plan_destroy(fiatb200_plan* plan) {
     if (plan->blob) cudaFree(plan->blob);
     delete plan;
     return FIATB200_OK;
+}
+
+int fiatb200_plan_kernel(const fiatb200_plan* plan, uint32_t flags) {
+    if (!plan) return 0;
+    if (plan->kind == PLAN_LATTICE) return K_LATTICE;
+    if (plan->kind == PLAN_TENSOR) return K_TENSOR;
+    MmaGeom G;
+    size_t smem = 0;
+    return choose_simplex_kernel(plan, flags, &G, &smem);
 }
 
 int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalpha) {

@@ -235,7 +235,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     // GO * NA DMMAs.  Fragments are fetched CH blocks ahead so that their L2 latency hides behind
     // the DMMAs of the current chunk; row-block tables come from the constant bank.
     constexpr int CH = 8;
-    constexpr int GO = NA >= 8 ? 1 : (NA >= 5 ? 2 : 4);
+    constexpr int GO = NA >= 8 ? 1 : (NA >= 5 ? 2 : (NA >= 3 ? 4 : (NA == 2 ? 8 : 16)));     // ~16 DMMAs per fragment
     const int lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int ngrp = PT / (8 * GO);

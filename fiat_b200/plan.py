@@ -286,8 +286,9 @@ def _dubiner_tables(desc, order, slot_perm=None):
             geom[c, 14 + 3 * codim:14 + 3 * codim + sd] = dfa
             geom[c, 23 + 3 * codim:23 + 3 * codim + sd] = dfb
 
-    # fold normalisation / sign / reordering into the coefficient columns
-    norm = _normalisation(sd, n, variant) if n > 0 else numpy.ones(nmem)
+    # fold normalisation / sign / reordering into the coefficient columns ("raw_members": the coefficients
+    # already refer to the un-normalised recurrence members -- derived elements of alpha_split)
+    norm = _normalisation(sd, n, variant) if (n > 0 and not desc.get("raw_members")) else numpy.ones(nmem)
     fold = norm.copy()
     fix_idx, fix_w = [], []
     if c0:
@@ -475,25 +476,90 @@ def derivative_coefficients(desc, t, ccell_morton, order):
     sd, n = int(desc["sd"]), int(desc["degree"])
     ncells, nrows, nmem = ccell_morton.shape
     if n < 1 or sd < 2 or order > 3 or ncells > 16 or n > (6 if sd == 2 else 4):
-        return None, 0          # outside the kernel's instantiations (small.cuh)
+        return None, 0          # outside the kernel's instantiations (vals.cuh)
     ncp = 1 if ncells == 1 else (4 if ncells <= 4 else 16)
-    D = _derivative_matrices(t, sd, n)
-    alphas = alpha_list(sd, order)
+    mats = alpha_matrices(desc, t, ccell_morton, order)
     blocks = []
-    for alpha in alphas:
+    for per_cell in mats:
+        blk = numpy.zeros((nrows, per_cell[0].shape[1], ncp))
+        for c in range(ncells):
+            blk[:, :, c] = per_cell[c]
+        blocks.append(blk.reshape(-1))
+    return numpy.concatenate(blocks) if blocks else numpy.zeros(0), ncp
+
+
+def alpha_matrices(desc, t, ccell_morton, order):
+    """[alpha][cell] -> (nrows, C(n - |alpha| + sd, sd)) matrix C_alpha with
+    D^alpha(table row) = C_alpha . (values of the un-normalised Morton-numbered members of degree <= n - |alpha|),
+    derivatives taken in the parent cell's coordinates (chain rule through the subcell map xi = A x + b)."""
+    sd, n = int(desc["sd"]), int(desc["degree"])
+    ncells, nrows, nmem = ccell_morton.shape
+    D = _derivative_matrices(t, sd, n)
+    out = []
+    for alpha in alpha_list(sd, order):
         k = sum(alpha)
         nm = math.comb(n - k + sd, sd) if k <= n else 0
-        blk = numpy.zeros((nrows, nm, ncp))
+        per_cell = []
         for c in range(ncells):
-            A = numpy.asarray(desc["cell_A"][c], dtype=float)          # xi = A x + b
+            A = numpy.asarray(desc["cell_A"][c], dtype=float)
             Dx = [sum(A[i, j] * D[i] for i in range(sd)) for j in range(sd)]
             Da = numpy.eye(nmem)
             for j in range(sd):
                 for _ in range(alpha[j]):
                     Da = Da @ Dx[j]
-            blk[:, :, c] = (ccell_morton[c] @ Da)[:, :nm]
-        blocks.append(blk.reshape(-1))
-    return numpy.concatenate(blocks) if blocks else numpy.zeros(0), ncp
+            per_cell.append((ccell_morton[c] @ Da)[:, :nm])
+        out.append(per_cell)
+    return out
+
+
+def alpha_split(desc, order, prog=None):
+    """Split the tabulation of a single-cell Dubiner element into one order-0 tabulation per derivative
+    multi-index: D^alpha of the element's functions is itself a set of polynomials of degree n - |alpha|,
+    i.e. a derived element whose coefficient matrix (on the un-normalised recurrence members) is
+    C_alpha = C . D_alpha (alpha_matrices).  The derived elements need no derivative jets and their
+    expansion shrinks with |alpha|; whether that beats the one-pass jet tabulation depends on how sparse
+    C . D_alpha stays, so the split is only proposed when it stores fewer 8x4 blocks in total than
+    (blocks of C) x (number of alphas), the tile kernel's cost measure.
+
+    Returns [(alpha, derived description or None for an identically zero table)] or None."""
+    if desc.get("kind") != "simplex" or desc.get("expansion") != "dubiner" or int(desc["ncells"]) != 1:
+        return None
+    if order < 1 or desc.get("raw_members"):
+        return None
+    sd, n = int(desc["sd"]), int(desc["degree"])
+    if sd < 2 or n < 2:
+        return None
+    if prog is None:
+        prog = compile_simplex(desc, order)
+    if len(prog.blk_kb) == 0:
+        return None
+    t = _dubiner_tables(desc, order)
+    mats = alpha_matrices(desc, t, prog.ccell_morton, order)
+    alphas = alpha_list(sd, order)
+    coeffs = numpy.asarray(desc["coeffs"])
+    ndofs, ncomp = coeffs.shape[0], coeffs.shape[1]
+
+    def stored_blocks(mat):
+        if mat.size == 0:
+            return 0
+        tol = 1e-14 * max(numpy.abs(mat).max(), 1e-300)
+        return len(pack_blocks(mat[cluster_rows(mat, tol)], tol)[1])
+
+    split_blocks = sum(stored_blocks(m[0]) for m in mats)
+    if split_blocks > 0.9 * len(prog.blk_kb) * len(alphas):
+        return None
+    out = []
+    for alpha, per_cell in zip(alphas, mats):
+        k, mat = sum(alpha), per_cell[0]
+        if mat.shape[1] == 0 or not numpy.abs(mat).max() > 0.0:
+            out.append((alpha, None))
+            continue
+        d = {key: val for key, val in desc.items() if key not in ("nodes", "coeffs", "cell_node_map", "degree", "c0")}
+        d.update(degree=n - k, c0=False, raw_members=True,
+                 coeffs=numpy.ascontiguousarray(mat.reshape(ndofs, ncomp, mat.shape[1])),
+                 cell_node_map=numpy.arange(mat.shape[1], dtype=numpy.int64)[None, :])
+        out.append((alpha, d))
+    return out
 
 
 def compile_simplex(desc, order):

@@ -140,6 +140,11 @@ int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, cons
 
 int fiatb200_plan_destroy(fiatb200_plan* plan);
 
+/* Which kernel fiatb200_tabulate would run for this plan and these flags: 1 thread-per-point, 2 DMMA tile,
+ * 3 register (jet) kernel, 4 value-table kernel, 5 product-form (lattice), 6 tensor product; 0 if the
+ * flags force a kernel that does not apply. */
+int fiatb200_plan_kernel(const fiatb200_plan* plan, uint32_t flags);
+
 /* Number of result rows per derivative multi-index, and number of multi-indices. */
 int fiatb200_plan_shape(const fiatb200_plan* plan, int64_t* nrows, int64_t* nalpha);
 

@@ -65,6 +65,21 @@ def test_value_table_and_jet_kernels_agree_with_golden(name, cuda_device):
         _compare(desc, got, case["ref"])
 
 
+@pytest.mark.parametrize("name", ["n2curl4_tet_o1", "ned2_tet_o2", "p5_tet_o3", "hermite3_tet_o2", "p6_tri_o4",
+                                  "p4_tet_face2_o2", "regge2_tet_o1", "argyris_tri_o2"])
+def test_alpha_split_matches_golden_and_jets(name, cuda_device):
+    """Mid-size single-cell elements are tabulated as one derived order-0 element per derivative multi-index
+    (plan.alpha_split); the one-pass jet tabulation must give the same tables."""
+    from fiat_b200.api import Tabulator, FORCE_GENERAL, NO_ALPHA_SPLIT
+    case = load_case(name)
+    tab = Tabulator(case["desc"], cuda_device)
+    split = tab.tabulate(case["order"], case["points"], case["entity"], flags=FORCE_GENERAL)
+    _compare(case["desc"], split, case["ref"])
+    whole = tab.tabulate(case["order"], case["points"], case["entity"], flags=FORCE_GENERAL | NO_ALPHA_SPLIT)
+    _compare(case["desc"], whole, case["ref"])
+    assert len(tab._resolve(case["order"], case["entity"], FORCE_GENERAL | NO_ALPHA_SPLIT)[0]) == 1
+
+
 @pytest.mark.parametrize("name", [n for n in golden_case_names()])
 def test_subcell_assignment_bit_exact(name, cuda_device):
     from fiat_b200.api import Tabulator
