@@ -371,13 +371,21 @@ class Tabulator:
                     p.handle, ctypes.byref(ent) if ent is not None else None, pts.ctypes.data, npts, pdim,
                     out.ctypes.data, chunk_pts, flags & 11))
         elif npts:
-            # wrapper elements: chunks through the device path, one device buffer
-            for start in range(0, npts, chunk_pts):
-                stop = min(npts, start + chunk_pts)
-                dpts = torch.as_tensor(pts[start:stop], device=self.device)
-                dout = torch.empty((len(alphas), nrows, stop - start), dtype=torch.float64, device=self.device)
-                self._run(launches, zero, dpts, dout, stop - start, stop - start, flags)
-                out[:, :, start:stop] = dout.cpu().numpy()
+            # wrapper elements / per-alpha splits: the launch list goes through the same staged pipeline
+            arr = (_lib.LaunchStruct * len(launches))()
+            for i, (p, ent, rmap, aoff) in enumerate(launches):
+                arr[i].alpha_offset = aoff
+                if p is None:
+                    arr[i].plan, arr[i].zero_rows_dev, arr[i].nzero_rows = None, rmap.data_ptr(), rmap.numel()
+                else:
+                    arr[i].plan = p.handle
+                    arr[i].entity = ctypes.pointer(ent) if ent is not None else None
+                    arr[i].map = ctypes.pointer(rmap) if rmap is not None else None
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fiatb200_tabulate_host_list(
+                    arr, len(launches), len(alphas), nrows, zero.data_ptr() if zero is not None else None,
+                    zero.numel() if zero is not None else 0, pts.ctypes.data, npts, pdim, out.ctypes.data, chunk_pts,
+                    flags & 11))
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
     def tabulate_factors(self, order, points, entity=None):

@@ -195,7 +195,9 @@ int choose_simplex_kernel(const fiatb200_plan* plan, uint32_t flags, MmaGeom* G,
     const double locate = P.ncells > 1 ? (P.ncells + 1.0) * (P.sd + 1) * (2 * P.sd + 3) : 0.0;
     double best = 1e300;
     int pick = K_CELLWISE;
-    if (use_mma && (long long)P.nrows * P.nslots >= 256) {
+    // (1-D sets with a handful of rows stay per-thread; in 2-D / 3-D the thread-per-point fallback, which keeps
+    // every member's jets in shared memory, is the slowest path for any element the tile kernel can take)
+    if (use_mma && ((P.sd >= 2 && P.degree >= 1) || (long long)P.nrows * P.nslots >= 256)) {
         best = std::max(hbm, 16.0 * P.nblk * na / 0.75 + 0.5 * steps * 8.0 * na);
         pick = K_MMA;
     }
@@ -678,6 +680,57 @@ int fiatb200_locate_subcells(const fiatb200_plan* plan, const fiatb200_entity_ma
     return FIATB200_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Host-buffer driver shared by fiatb200_tabulate_host and fiatb200_tabulate_host_list: chunks of points go
+// H2D, `run` enqueues the kernels of one chunk, the chunk's rows go D2H into their final place; two streams
+// with one staging buffer each (owned by `owner`, kept across calls) overlap copies and kernels.
+template <typename Run>
+int host_pipeline(fiatb200_plan* owner, int64_t rows, const double* pts_host, int64_t npts, int64_t pts_ld,
+                  double* out_host, int64_t chunk_pts, Run run) {
+    std::lock_guard<std::mutex> guard(owner->host_mutex);
+    chunk_pts = std::min<int64_t>(chunk_pts, npts);
+    chunk_pts = (chunk_pts + 7) & ~int64_t(7);
+    const size_t need_pts = sizeof(double) * chunk_pts * std::max<int64_t>(pts_ld, 1);
+    const size_t need_out = sizeof(double) * chunk_pts * rows;
+    if (!owner->host_stream[0] || need_pts > owner->host_pts_cap || need_out > owner->host_out_cap) {
+        free_staging(owner);
+        for (int i = 0; i < 2; ++i) {
+            FB_CUDA(cudaStreamCreateWithFlags(&owner->host_stream[i], cudaStreamNonBlocking));
+            FB_CUDA(cudaMalloc(&owner->host_pts[i], need_pts));
+            FB_CUDA(cudaMalloc(&owner->host_out[i], need_out));
+        }
+        owner->host_pts_cap = need_pts;
+        owner->host_out_cap = need_out;
+    }
+    int rc = FIATB200_OK;
+    int64_t done = 0;
+    for (int it = 0; done < npts && rc == FIATB200_OK; ++it, done += chunk_pts) {
+        const int b = it & 1;
+        cudaStream_t st = owner->host_stream[b];
+        const int64_t n = std::min<int64_t>(chunk_pts, npts - done);
+        if (pts_ld > 0)
+            FB_CUDA(cudaMemcpyAsync(owner->host_pts[b], pts_host + done * pts_ld, sizeof(double) * n * pts_ld,
+                                    cudaMemcpyHostToDevice, st));
+        rc = run(owner->host_pts[b], n, owner->host_out[b], chunk_pts, st);
+        if (rc) break;
+        // rows of the chunk land at column offset `done` of the (rows x npts) host result
+        FB_CUDA(cudaMemcpy2DAsync(out_host + done, sizeof(double) * npts, owner->host_out[b], sizeof(double) * chunk_pts,
+                                  sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaStreamSynchronize(owner->host_stream[i]);
+        if (e != cudaSuccess && rc == FIATB200_OK) rc = fb_fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
 int fiatb200_tabulate_host(const fiatb200_plan* cplan, const fiatb200_entity_map* entity, const double* pts_host,
                            int64_t npts, int64_t pts_ld, double* out_host, int64_t chunk_pts, uint32_t flags) {
     if (!cplan) return fb_fail(FIATB200_ERR_ARG, "null plan");
@@ -685,44 +738,43 @@ int fiatb200_tabulate_host(const fiatb200_plan* cplan, const fiatb200_entity_map
     if ((!pts_host && pts_ld != 0) || !out_host || chunk_pts <= 0)
         return fb_fail(FIATB200_ERR_ARG, "bad host buffers / chunk size");
     fiatb200_plan* plan = const_cast<fiatb200_plan*>(cplan);
-    std::lock_guard<std::mutex> guard(plan->host_mutex);
     int64_t nrows = 0, nalpha = 0;
     fiatb200_plan_shape(plan, &nrows, &nalpha);
-    const int64_t rows = nrows * nalpha;
-    chunk_pts = std::min<int64_t>(chunk_pts, npts);
-    chunk_pts = (chunk_pts + 7) & ~int64_t(7);
-    const size_t need_pts = sizeof(double) * chunk_pts * std::max<int64_t>(pts_ld, 1);
-    const size_t need_out = sizeof(double) * chunk_pts * rows;
-    if (!plan->host_stream[0] || need_pts > plan->host_pts_cap || need_out > plan->host_out_cap) {
-        free_staging(plan);
-        for (int i = 0; i < 2; ++i) {
-            FB_CUDA(cudaStreamCreateWithFlags(&plan->host_stream[i], cudaStreamNonBlocking));
-            FB_CUDA(cudaMalloc(&plan->host_pts[i], need_pts));
-            FB_CUDA(cudaMalloc(&plan->host_out[i], need_out));
-        }
-        plan->host_pts_cap = need_pts;
-        plan->host_out_cap = need_out;
+    return host_pipeline(plan, nrows * nalpha, pts_host, npts, pts_ld, out_host, chunk_pts,
+                         [&](const double* dpts, int64_t n, double* dout, int64_t stride, cudaStream_t st) {
+                             return fiatb200_tabulate(plan, entity, dpts, n, pts_ld, dout, stride, flags, st);
+                         });
+}
+
+int fiatb200_tabulate_host_list(const fiatb200_launch* launches, int32_t nlaunch, int32_t nalpha, int64_t total_rows,
+                                const int32_t* zero_rows_dev, int32_t nzero_rows, const double* pts_host, int64_t npts,
+                                int64_t pts_ld, double* out_host, int64_t chunk_pts, uint32_t flags) {
+    if (!launches || nlaunch < 1 || nalpha < 1 || total_rows < 1) return fb_fail(FIATB200_ERR_ARG, "empty launch list");
+    if (npts == 0) return FIATB200_OK;
+    if ((!pts_host && pts_ld != 0) || !out_host || chunk_pts <= 0)
+        return fb_fail(FIATB200_ERR_ARG, "bad host buffers / chunk size");
+    fiatb200_plan* owner = nullptr;
+    for (int i = 0; i < nlaunch; ++i) {
+        if (launches[i].alpha_offset < 0 || launches[i].alpha_offset >= nalpha)
+            return fb_fail(FIATB200_ERR_ARG, "launch writes a derivative table that does not exist");
+        if (launches[i].plan && !owner) owner = const_cast<fiatb200_plan*>(launches[i].plan);
     }
-    int rc = FIATB200_OK;
-    int64_t done = 0;
-    for (int it = 0; done < npts && rc == FIATB200_OK; ++it, done += chunk_pts) {
-        const int b = it & 1;
-        cudaStream_t st = plan->host_stream[b];
-        const int64_t n = std::min<int64_t>(chunk_pts, npts - done);
-        if (pts_ld > 0)
-            FB_CUDA(cudaMemcpyAsync(plan->host_pts[b], pts_host + done * pts_ld, sizeof(double) * n * pts_ld,
-                                    cudaMemcpyHostToDevice, st));
-        rc = fiatb200_tabulate(plan, entity, plan->host_pts[b], n, pts_ld, plan->host_out[b], chunk_pts, flags, st);
-        if (rc) break;
-        // rows of the chunk land at column offset `done` of the (rows x npts) host result
-        FB_CUDA(cudaMemcpy2DAsync(out_host + done, sizeof(double) * npts, plan->host_out[b], sizeof(double) * chunk_pts,
-                                  sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st));
-    }
-    for (int i = 0; i < 2; ++i) {
-        cudaError_t e = cudaStreamSynchronize(plan->host_stream[i]);
-        if (e != cudaSuccess && rc == FIATB200_OK) rc = fb_fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
-    }
-    return rc;
+    if (!owner) return fb_fail(FIATB200_ERR_ARG, "launch list without a plan");
+    return host_pipeline(owner, total_rows * nalpha, pts_host, npts, pts_ld, out_host, chunk_pts,
+                         [&](const double* dpts, int64_t n, double* dout, int64_t stride, cudaStream_t st) {
+                             int rc = FIATB200_OK;
+                             if (zero_rows_dev && nzero_rows > 0)
+                                 rc = fiatb200_zero_rows(dout, stride, n, total_rows, nalpha, zero_rows_dev, nzero_rows, st);
+                             for (int i = 0; i < nlaunch && rc == FIATB200_OK; ++i) {
+                                 const fiatb200_launch& L = launches[i];
+                                 double* o = dout + (size_t)L.alpha_offset * total_rows * stride;
+                                 if (!L.plan)
+                                     rc = fiatb200_zero_rows(o, stride, n, total_rows, 1, L.zero_rows_dev, L.nzero_rows, st);
+                                 else
+                                     rc = fiatb200_tabulate_mapped(L.plan, L.entity, dpts, n, pts_ld, o, stride, L.map, flags, st);
+                             }
+                             return rc;
+                         });
 }
 
 }  // extern "C"

@@ -184,6 +184,26 @@ int fiatb200_tabulate_host(const fiatb200_plan* plan, const fiatb200_entity_map*
                            const double* pts_host, int64_t npts, int64_t pts_ld,
                            double* out_host, int64_t chunk_pts, uint32_t flags);
 
+/* One kernel launch of a tabulation that is made of several plans: the parts of a wrapper element
+ * (FIAT/enriched.py:88-113, FIAT/mixed.py:61-92, FIAT/hdivcurl.py) and/or the per-derivative derived elements of
+ * a split single-cell element.  plan == NULL zero-fills `zero_rows_dev` of derivative table `alpha_offset`. */
+typedef struct {
+    const fiatb200_plan* plan;
+    const fiatb200_entity_map* entity;   /* NULL for tensor plans / the default cell entity */
+    const fiatb200_row_map* map;         /* NULL: rows in place */
+    int32_t alpha_offset;                /* derivative table that the plan's first table is written to */
+    const int32_t* zero_rows_dev;        /* plan == NULL only: device array of row numbers */
+    int32_t nzero_rows;
+} fiatb200_launch;
+
+/* fiatb200_tabulate_host for a list of launches that together fill a (nalpha x total_rows x npts) result:
+ * every chunk of points is staged once, all launches of the list run on it, and the chunk's rows are copied
+ * to their place in out_host.  zero_rows_dev / nzero_rows (may be NULL / 0): rows of every derivative table
+ * that no launch writes.  Synchronous. */
+int fiatb200_tabulate_host_list(const fiatb200_launch* launches, int32_t nlaunch, int32_t nalpha, int64_t total_rows,
+                                const int32_t* zero_rows_dev, int32_t nzero_rows, const double* pts_host,
+                                int64_t npts, int64_t pts_ld, double* out_host, int64_t chunk_pts, uint32_t flags);
+
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t fiatb200_launch_count(void);
 

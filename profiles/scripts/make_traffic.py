@@ -1,0 +1,37 @@
+"""Summaries (profiles/r01_ncu_*.txt) and profiles/traffic.json from the `ncu --set full` reports pulled into
+gpurun_out/ by capture_r1.sh.  traffic = dram__bytes_read.sum + dram__bytes_write.sum over the launches of one
+step, keyed workload|kernel path|points per launch like bench.py looks it up."""
+import csv, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CAPS = {  # report -> (workload, kernel path, batch)
+    "lattice_p8": ("p8_tet_o2", "lattice", 1 << 20), "mma_p8": ("p8_tet_o2", "simplex", 1 << 20),
+    "mma_n2curl_split": ("n2curl4_tet_o1", "simplex", 1 << 20), "vals_hct": ("hct_o2", "simplex", 10_000_000),
+    "vals_ps6": ("ps6_o2", "simplex", 10_000_000), "vals_ps12": ("ps12_o2", "simplex", 10_000_000),
+    "tensor_hex": ("gll_q10_hex_o1", "tensor", 1 << 20),
+}
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step from `ncu --set full` "
+                       "captures (profiles/r01_ncu_*.txt); key = workload|kernel path|points per launch"}
+for name, (workload, path, batch) in CAPS.items():
+    rep = os.path.join(ROOT, "gpurun_out", f"r01_raw_{name}.csv")
+    if not os.path.exists(rep):
+        print("missing", rep)
+        continue
+    summary = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "scripts", "ncu_summary.py"), rep],
+                             capture_output=True, text=True).stdout
+    out = os.path.join(ROOT, "profiles", f"r01_ncu_{name}.txt")
+    with open(out, "w") as f:
+        f.write(f"# ncu --set full --clock-control none, the launches of one bench step ({workload}, {batch} points); "
+                f"raw metric page: r01_raw_{name}.csv (gpurun_out/, not tracked)\n" + summary)
+    raw = open(rep).read()
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    total = 0.0
+    for r in rows[2:]:
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            total += float(r[i]) * UNIT[units[i]]
+    traffic[f"{workload}|{path}|{batch}"] = {"bytes": int(total), "launches": len(rows) - 2,
+                                             "source": os.path.relpath(out, ROOT)}
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+print(json.dumps(traffic, indent=1))

@@ -94,7 +94,12 @@ def membership(complex_, pts, unique):
     return near
 
 
+ONLY = None        # set by `--only name1,name2`: write just these cases (the rng stream is still consumed in order)
+
+
 def write_case(name, element, order, pts, entity=None, with_cells=False):
+    if ONLY is not None and name not in ONLY:
+        return
     desc = describe_element(element)
     ref = element.tabulate(order, pts, entity)
     case = {
@@ -256,12 +261,17 @@ def main():
         ("p1xrt1_vector_b_o1", TPE(P1, FIAT.RaviartThomas(T2, 1)), 1,
          numpy.concatenate([rng.random((11, 1)), simplex_points(rng, 11, 2)], axis=1), None),
         ("dg_wrapped_p2_tri_o2", FIAT.DiscontinuousElement(FIAT.Lagrange(T2, 2)), 2, simplex_points(rng, 11, 2), None),
+        # wrapper elements whose parts are mid-size single-cell elements (per-alpha split + row placement)
+        ("n2curl3_p3_mixed_tet_o1", FIAT.MixedElement([FIAT.NedelecSecondKind(T3, 3), FIAT.Lagrange(T3, 3, variant="spectral")]), 1,
+         simplex_points(rng, 11, 3), None),
+        ("enriched_p4s_bubble5_tet_o2", FIAT.EnrichedElement(FIAT.Lagrange(T3, 4, variant="spectral"), FIAT.Bubble(T3, 5)), 2,
+         simplex_points(rng, 11, 3), None),
     ]
     for nm, el, order, pts, ent in wrappers:
         write_case(nm, el, order, pts, entity=ent)
 
     # element descriptions alone, for bench.py and full-size GPU tests
-    for nm, el in (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),
+    for nm, el in () if ONLY is not None else (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),
                    ("hct", FIAT.HsiehCloughTocher(T2)), ("ps6", FIAT.QuadraticPowellSabin6(T2)),
                    ("ps12", FIAT.QuadraticPowellSabin12(T2)), ("gll_q10_hex", hexa),
                    ("p3_tri", FIAT.Lagrange(T2, 3))):
@@ -271,4 +281,6 @@ def main():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":
+        ONLY = set(sys.argv[2].split(","))
     main()

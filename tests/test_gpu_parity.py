@@ -94,7 +94,8 @@ def test_subcell_assignment_bit_exact(name, cuda_device):
         assert numpy.array_equal(mask, want)
 
 
-@pytest.mark.parametrize("name", ["p3_tri_o1", "hct_o2", "gll_q3_hex_face4_o2", "n2curl4_tet_o1"])
+@pytest.mark.parametrize("name", ["p3_tri_o1", "hct_o2", "gll_q3_hex_face4_o2", "n2curl4_tet_o1", "rtcf1_quad_o1",
+                                  "mini_tri_o2", "n2curl3_p3_mixed_tet_o1", "enriched_p4s_bubble5_tet_o2", "p6_tri_o4"])
 def test_host_buffer_call(name, cuda_device):
     from fiat_b200.api import Tabulator
     case = load_case(name)
