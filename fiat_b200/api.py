@@ -32,6 +32,7 @@ FORCE_DMMA = 2
 FORCE_GENERAL = 4          # do not use the product-form (lattice) kernel
 NO_VALUE_TABLE = 8         # do not use the value-table kernel (derivative-folded coefficients)
 NO_ALPHA_SPLIT = 16        # do not split the tabulation into one derived order-0 element per alpha
+NO_MERGED_SPLIT = 32       # keep the derived elements of a split as separate launches
 KERNEL_NAMES = {0: "none", 1: "cellwise", 2: "mma", 3: "small", 4: "vals", 5: "lattice", 6: "tensor"}
 
 
@@ -164,6 +165,11 @@ class Tabulator:
                 out = []
                 for j, (alpha, d) in enumerate(derived):
                     out.append((j, None if d is None else self._simplex_plan(d, 0)[0], d))
+                # all derived elements stacked into one (rows = the derivative tables one after the other):
+                # one launch, one value recurrence; usable when the part's rows are written in place
+                merged = planmod.merged_split(desc, order, derived)
+                if merged is not None:
+                    out.append(("merged", self._simplex_plan(merged, 0)[0], merged))
         with self._lock:
             self._plans[key] = out
         return out
@@ -235,7 +241,7 @@ class Tabulator:
         launch without a row map, wrapper elements one per part."""
         if order < 0:
             raise ValueError("order must be non-negative")
-        ckey = ("resolved", order, None if entity is None else str(entity), flags & 31)
+        ckey = ("resolved", order, None if entity is None else str(entity), flags & 63)
         hit = self._plans.get(ckey)
         if hit is not None:
             return hit
@@ -276,7 +282,10 @@ class Tabulator:
                                                             part.comp_out, part.sign)
             if split is None:
                 launches.append((p, ent, rmap, 0))
+            elif single and split[-1][0] == "merged" and not (flags & NO_MERGED_SPLIT):
+                launches.append((split[-1][1], ent, None, 0))
             else:
+                split = [item for item in split if item[0] != "merged"]
                 # one derived order-0 element per alpha, written into that alpha's table
                 nd = planmod.num_dofs_of(d)
                 for j, sub, _ in split:

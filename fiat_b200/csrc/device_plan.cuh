@@ -13,7 +13,7 @@
 #define FB_MAX_STEPS 455      // C(12+3,3) - 1: degree 12 on a tetrahedron
 #define FB_MAX_LEVELS 30
 #define FB_MAX_FIX 128
-#define FB_MAX_RB 160        // row blocks of 8 (ndofs * components <= 1280)
+#define FB_MAX_RB 256        // row blocks of 8 (rows <= 2048; stacked per-alpha elements: nalpha * ndofs * components)
 
 struct StepRec {
     short nxt, cur, prv, codim;     // member slots; prv < 0: first step of a chain

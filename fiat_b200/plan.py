@@ -20,11 +20,13 @@ Everything that does not depend on the evaluation point is worked out here, once
 * for tensor-product elements the flattened list of leaf factors (`FIAT/tensor_product.py:231-292`).
 """
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy
 
 __all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf", "lattice_rowmap",
+           "alpha_split", "merged_split",
            "resolve_parts", "Part", "value_shape_of", "num_dofs_of"]
 
 EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
@@ -512,6 +514,9 @@ def alpha_matrices(desc, t, ccell_morton, order):
     return out
 
 
+MAX_MERGED_ROWS = 2048        # row blocks of 8 the tile kernel's constant tables hold (FB_MAX_RB in device_plan.cuh)
+
+
 def alpha_split(desc, order, prog=None):
     """Split the tabulation of a single-cell Dubiner element into one order-0 tabulation per derivative
     multi-index: D^alpha of the element's functions is itself a set of polynomials of degree n - |alpha|,
@@ -521,7 +526,8 @@ def alpha_split(desc, order, prog=None):
     C . D_alpha stays, so the split is only proposed when it stores fewer 8x4 blocks in total than
     (blocks of C) x (number of alphas), the tile kernel's cost measure.
 
-    Returns [(alpha, derived description or None for an identically zero table)] or None."""
+    Returns [(alpha, derived description or None for an identically zero table)] or None.
+    `merged_split` stacks the derived elements into one."""
     if desc.get("kind") != "simplex" or desc.get("expansion") != "dubiner" or int(desc["ncells"]) != 1:
         return None
     if order < 1 or desc.get("raw_members"):
@@ -545,8 +551,12 @@ def alpha_split(desc, order, prog=None):
         tol = 1e-14 * max(numpy.abs(mat).max(), 1e-300)
         return len(pack_blocks(mat[cluster_rows(mat, tol)], tol)[1])
 
+    # stacked into one launch (merged_split) the split also saves the jets of the recurrence, which is worth a few
+    # more blocks; as separate launches it must store clearly fewer
+    mergeable = len(alphas) * ndofs * ncomp <= MAX_MERGED_ROWS
     split_blocks = sum(stored_blocks(m[0]) for m in mats)
-    if split_blocks > 0.9 * len(prog.blk_kb) * len(alphas):
+    limit = float(os.environ.get("FIATB200_SPLIT_RATIO", 1.3)) if mergeable else 0.9       # env: tuning override
+    if split_blocks > limit * len(prog.blk_kb) * len(alphas):
         return None
     out = []
     for alpha, per_cell in zip(alphas, mats):
@@ -710,6 +720,28 @@ def lattice_rowmap(desc):
                 for a2 in range(n + 1 - a0 - a1):
                     rowmap.append(where[(a0, a1, a2, n - a0 - a1 - a2)])
     return numpy.array(rowmap, dtype=numpy.int32)
+
+
+def merged_split(desc, order, split):
+    """The derived elements of `alpha_split` stacked into ONE order-0 element with nalpha * nrows rows: its table
+    rows are exactly the element's derivative tables one after the other (the output layout), the columns a
+    level does not use are zero and cost nothing in the block-sparse packing, and the value recurrence runs once
+    for all alphas.  None if the stack exceeds the tile kernel's row tables."""
+    coeffs = numpy.asarray(desc["coeffs"])
+    ndofs, ncomp = coeffs.shape[0], coeffs.shape[1]
+    if len(split) * ndofs * ncomp > MAX_MERGED_ROWS:
+        return None
+    width = max((d["coeffs"].shape[2] for _, d in split if d is not None), default=0)
+    if width == 0:
+        return None
+    top = next(d for _, d in split if d is not None and d["coeffs"].shape[2] == width)
+    stacked = numpy.zeros((len(split) * ndofs, ncomp, width))
+    for j, (_, d) in enumerate(split):
+        if d is not None:
+            stacked[j * ndofs:(j + 1) * ndofs, :, :d["coeffs"].shape[2]] = d["coeffs"]
+    out = dict(top)
+    out["coeffs"] = stacked
+    return out
 
 
 @dataclass

@@ -70,11 +70,13 @@ def test_value_table_and_jet_kernels_agree_with_golden(name, cuda_device):
 def test_alpha_split_matches_golden_and_jets(name, cuda_device):
     """Mid-size single-cell elements are tabulated as one derived order-0 element per derivative multi-index
     (plan.alpha_split); the one-pass jet tabulation must give the same tables."""
-    from fiat_b200.api import Tabulator, FORCE_GENERAL, NO_ALPHA_SPLIT
+    from fiat_b200.api import Tabulator, FORCE_GENERAL, NO_ALPHA_SPLIT, NO_MERGED_SPLIT
     case = load_case(name)
     tab = Tabulator(case["desc"], cuda_device)
     split = tab.tabulate(case["order"], case["points"], case["entity"], flags=FORCE_GENERAL)
     _compare(case["desc"], split, case["ref"])
+    separate = tab.tabulate(case["order"], case["points"], case["entity"], flags=FORCE_GENERAL | NO_MERGED_SPLIT)
+    _compare(case["desc"], separate, case["ref"])
     whole = tab.tabulate(case["order"], case["points"], case["entity"], flags=FORCE_GENERAL | NO_ALPHA_SPLIT)
     _compare(case["desc"], whole, case["ref"])
     assert len(tab._resolve(case["order"], case["entity"], FORCE_GENERAL | NO_ALPHA_SPLIT)[0]) == 1
