@@ -127,6 +127,33 @@ def test_tabulate_into_streaming(cuda_device):
     assert torch.isnan(buf[:, :, 200:]).all()
 
 
+@pytest.mark.parametrize("name", ["hct_o2", "ps12_o2", "n2curl4_tet_o1", "p8_tet_o2", "regge2_tet_o1", "gn_tet_o2",
+                                  "gll_q3_hex_face4_o2", "p5_tet_o3", "mini_tri_o2", "n2curl3_p3_mixed_tet_o1",
+                                  "p4_line_o2", "argyris_tri_o2"])
+@pytest.mark.parametrize("npts", [1, 37, 203])
+def test_no_write_outside_the_table(name, npts, cuda_device):
+    """Guard bands around and inside the caller's buffer (row stride > npts, odd point counts that leave partial
+    warps, octets and vector stores): every kernel path must leave them untouched and fill exactly its table."""
+    from fiat_b200.api import Tabulator, FORCE_GENERAL
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    pts0 = numpy.asarray(case["points"], dtype=float)
+    pts = pts0[numpy.arange(npts) % len(pts0)]
+    want = fiat_oracle.tabulate(desc, order, pts, case["entity"])
+    na = len(want)
+    nrows = int(numpy.prod(next(iter(want.values())).shape[:-1]))
+    stride, pad = 256, 64
+    for flags in (0, FORCE_GENERAL):
+        tab = Tabulator(desc, cuda_device)
+        raw = torch.full((pad + na * nrows * stride + pad,), float("nan"), dtype=torch.float64, device=cuda_device)
+        buf = raw[pad:pad + na * nrows * stride].view(na, nrows, stride)
+        assert tab.tabulate_into(buf, order, torch.as_tensor(pts, device=cuda_device), case["entity"], flags=flags) == npts
+        assert torch.isnan(raw[:pad]).all() and torch.isnan(raw[-pad:]).all()
+        assert torch.isnan(buf[:, :, npts:]).all()
+        got = {alpha: buf[j, :, :npts].reshape(want[alpha].shape) for j, alpha in enumerate(want)}
+        _compare(desc, got, want)
+
+
 @pytest.mark.parametrize("name,expect", [("p8_tet_o2", "lattice"), ("p3_tri_o1", "lattice"), ("p1_tri_o2", "lattice"),
                                          ("p4_tet_face2_o2", "lattice"), ("p5_tet_o3", "simplex"),
                                          ("dg3_tri_o1", "lattice"), ("cr_tri_o1", "simplex"), ("n2curl4_tet_o1", "simplex"),
