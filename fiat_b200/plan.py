@@ -438,11 +438,15 @@ def _member_values(t, sd, x):
     return T[t["slot_of"]]
 
 
+DMAT_RESIDUAL_LIMIT = 2e-13    # fitted derivative matrices must reproduce exact gradients this well, else jets are kept
+
+
 def _derivative_matrices(t, sd, n):
     """D[i][m, m'] with  d psi_m / d xi_i = sum_m' D[i][m, m'] psi_m'  for the un-normalised Morton-numbered
     members on the default simplex.  The members of degree <= k span P_k, so row m only involves members
     of lower degree; each degree level is fitted on its own (well-conditioned) lower-degree block.
-    Gradients are exact to rounding (complex step on the polynomial recurrence)."""
+    Gradients are exact to rounding (complex step on the polynomial recurrence).  Returns None if the fit fails
+    its self-check at independent points (very high degrees); callers then keep the derivative jets."""
     nmem = t["nslots"]
     lat = n + 3
     idx = numpy.array([i for i in numpy.ndindex(*([lat + 1] * sd)) if sum(i) <= lat], dtype=float)
@@ -462,6 +466,22 @@ def _derivative_matrices(t, sd, n):
             nlow = math.comb(k - 1 + sd, sd)
             sol = numpy.linalg.lstsq(Vs[:nlow].T, Gs[rows].T, rcond=None)[0]      # (nlow, len(rows))
             D[i][rows[:, None], numpy.arange(nlow)[None, :]] = sol.T * scale[rows][:, None] / scale[None, :nlow]
+    # self-check at independent points: gradients reproduced from values, relative to each member's largest gradient
+    rng = numpy.random.default_rng(20261018)
+    u = numpy.sort(rng.random((64, sd)), axis=1)
+    chk = (2.0 * numpy.diff(numpy.concatenate([numpy.zeros((64, 1)), u], axis=1), axis=1) - 1.0).T
+    Vc = _member_values(t, sd, chk)
+    residual = 0.0
+    for i in range(sd):
+        xc = chk.astype(complex)
+        xc[i] += 1j * h
+        G = _member_values(t, sd, xc).imag / h
+        big = numpy.abs(G).max(axis=1)
+        ok = big > 0
+        if ok.any():
+            residual = max(residual, float((numpy.abs(G - D[i] @ Vc).max(axis=1)[ok] / big[ok]).max()))
+    if residual > DMAT_RESIDUAL_LIMIT:
+        return None
     return D
 
 
@@ -481,6 +501,8 @@ def derivative_coefficients(desc, t, ccell_morton, order):
         return None, 0          # outside the kernel's instantiations (vals.cuh)
     ncp = 1 if ncells == 1 else (4 if ncells <= 4 else 16)
     mats = alpha_matrices(desc, t, ccell_morton, order)
+    if mats is None:
+        return None, 0
     blocks = []
     for per_cell in mats:
         blk = numpy.zeros((nrows, per_cell[0].shape[1], ncp))
@@ -497,6 +519,8 @@ def alpha_matrices(desc, t, ccell_morton, order):
     sd, n = int(desc["sd"]), int(desc["degree"])
     ncells, nrows, nmem = ccell_morton.shape
     D = _derivative_matrices(t, sd, n)
+    if D is None:
+        return None
     out = []
     for alpha in alpha_list(sd, order):
         k = sum(alpha)
@@ -541,6 +565,8 @@ def alpha_split(desc, order, prog=None):
         return None
     t = _dubiner_tables(desc, order)
     mats = alpha_matrices(desc, t, prog.ccell_morton, order)
+    if mats is None:
+        return None
     alphas = alpha_list(sd, order)
     coeffs = numpy.asarray(desc["coeffs"])
     ndofs, ncomp = coeffs.shape[0], coeffs.shape[1]

@@ -59,6 +59,39 @@ def test_value_table_reproduces_reference(name):
     print(name, "worst relative error", worst)
 
 
+@pytest.mark.parametrize("name", ["n2curl4_tet_o1", "p8_tet_o2", "p5_tet_o3", "hermite3_tet_o2", "p6_tri_o4",
+                                  "p4_tet_face2_o2", "p10_tri_o2", "argyris_tri_o2"])
+def test_alpha_split_reproduces_reference(name):
+    """Per-alpha derived order-0 elements (plan.alpha_split) and their stacked form (plan.merged_split):
+    their order-0 tabulation is the reference's derivative table."""
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    split = planmod.alpha_split(desc, order)
+    assert split is not None and [a for a, _ in split] == planmod.alpha_list(int(desc["sd"]), order)
+    pts = numpy.asarray(case["points"], dtype=float)
+    tr = fiat_oracle.resolve_entity(desc, case["entity"])
+    if tr is not None:
+        pts = pts.reshape(len(pts), tr[0].shape[0]) @ tr[0] + tr[1]
+    near = numpy.ones((1, len(pts)), dtype=bool)
+    for alpha, derived in split:
+        ref = case["ref"][alpha].reshape(-1, len(pts))
+        if derived is None:
+            assert not ref.any()
+            continue
+        prog = planmod.compile_simplex(derived, 0)
+        out = emu.run_simplex(prog, pts, near)[0]
+        assert abs(out - ref).max() <= tolerance(desc, alpha) * max(abs(ref).max(), 1e-300), alpha
+    merged = planmod.merged_split(desc, order, split)
+    assert merged is not None
+    prog = planmod.compile_simplex(merged, 0)
+    out = emu.run_simplex(prog, pts, near)[0]
+    nrows = out.shape[0] // len(split)
+    for j, (alpha, _) in enumerate(split):
+        ref = case["ref"][alpha].reshape(-1, len(pts))
+        assert abs(out[j * nrows:(j + 1) * nrows] - ref).max() <= tolerance(desc, alpha) * max(abs(ref).max(), 1e-300), alpha
+    assert prog.kpad % 4 == 0 and emu.blocks_to_dense(prog).shape == (prog.nrows, prog.nslots)
+
+
 def test_mis_order_matches_reference_keys():
     for name in golden_case_names():
         case = load_case(name)
