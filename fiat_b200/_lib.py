@@ -28,7 +28,7 @@ class SimplexProgramStruct(ctypes.Structure):
         ("line_tab", p_dbl), ("line_tab_len", c_i64),
         ("nrb", c_i32), ("kpad", c_i32), ("nblk", c_i32),
         ("blk_ptr", p_i32), ("blk_kb", p_i32), ("blk_frag", p_dbl), ("rb_order", p_i32), ("row_perm", p_i32),
-        ("cderiv", p_dbl), ("cderiv_len", c_i64), ("ncp", c_i32),
+        ("cderiv", p_dbl), ("cderiv_len", c_i64), ("ncp", c_i32), ("blk_cells", c_i32),
     ]
 
 
@@ -143,7 +143,9 @@ def simplex_struct(prog):
     s.geom, s.bary, s.ccell = f64(prog.geom), f64(prog.bary), f64(prog.ccell)
     s.low1, s.mul1, s.low2, s.mul2 = i32(prog.low1), f64(prog.mul1), i32(prog.low2), f64(prog.mul2)
     s.line_tab, s.line_tab_len = f64(prog.line_tab), int(numpy.size(prog.line_tab))
-    s.nrb, s.kpad, s.nblk = len(prog.blk_ptr) - 1, prog.kpad, len(prog.blk_kb)
+    s.blk_cells = int(prog.blk_cells)
+    s.nrb = len(prog.blk_ptr) // prog.blk_cells - 1 if prog.blk_cells > 1 else len(prog.blk_ptr) - 1
+    s.kpad, s.nblk = prog.kpad, len(prog.blk_kb)
     s.blk_ptr, s.blk_kb, s.blk_frag, s.rb_order = i32(prog.blk_ptr), i32(prog.blk_kb), f64(prog.blk_frag), i32(prog.rb_order)
     s.row_perm = i32(prog.row_perm if len(prog.row_perm) else numpy.arange(prog.nrows))
     s.cderiv, s.cderiv_len, s.ncp = f64(prog.cderiv), int(numpy.size(prog.cderiv)), int(prog.ncp)

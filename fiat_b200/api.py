@@ -33,7 +33,8 @@ FORCE_GENERAL = 4          # do not use the product-form (lattice) kernel
 NO_VALUE_TABLE = 8         # do not use the value-table kernel (derivative-folded coefficients)
 NO_ALPHA_SPLIT = 16        # do not split the tabulation into one derived order-0 element per alpha
 NO_MERGED_SPLIT = 32       # keep the derived elements of a split as separate launches
-KERNEL_NAMES = {0: "none", 1: "cellwise", 2: "mma", 3: "small", 4: "vals", 5: "lattice", 6: "tensor"}
+NO_MACRO_MERGED = 64       # do not use the split-cell tile kernel (derived element of plan.macro_merged)
+KERNEL_NAMES = {0: "none", 1: "cellwise", 2: "mma", 3: "small", 4: "vals", 5: "lattice", 6: "tensor", 7: "mma_cells"}
 
 
 def _resolve_simplex_entity(desc, entity):
@@ -174,6 +175,27 @@ class Tabulator:
             self._plans[key] = out
         return out
 
+    def _macro_merged_plan(self, desc, order, flags):
+        """Derived order-0 plan of a split-cell element for the split-cell tile kernel (plan.macro_merged), when
+        the element would otherwise run thread-per-point; None otherwise."""
+        if flags & (FORCE_THREAD_PER_POINT | FORCE_DMMA | NO_MACRO_MERGED) or int(desc.get("ncells", 1)) < 2:
+            return None
+        key = ("macro", id(desc), order)
+        with self._lock:
+            if key in self._plans:
+                return self._plans[key][0]
+        main, prog = self._simplex_plan(desc, order)
+        out, derived = None, None
+        if self.lib.fiatb200_plan_kernel(main.handle, flags & 11) == 1:
+            derived = planmod.macro_merged(desc, order, prog)
+            if derived is not None:
+                cand = self._simplex_plan(derived, 0)[0]
+                if self.lib.fiatb200_plan_kernel(cand.handle, 0) == 7:
+                    out = cand
+        with self._lock:
+            self._plans[key] = (out, derived)
+        return out
+
     def kernel_names(self, order, entity=None, flags=0):
         """Names of the kernels the launches of `tabulate(order, ...)` run on (diagnostics)."""
         launches = self._resolve(order, entity, flags)[0]
@@ -241,7 +263,7 @@ class Tabulator:
         launch without a row map, wrapper elements one per part."""
         if order < 0:
             raise ValueError("order must be non-negative")
-        ckey = ("resolved", order, None if entity is None else str(entity), flags & 63)
+        ckey = ("resolved", order, None if entity is None else str(entity), flags & 127)
         hit = self._plans.get(ckey)
         if hit is not None:
             return hit
@@ -270,6 +292,9 @@ class Tabulator:
                     p = fast if fast is not None else p
                 if fast is None:
                     split = self._alpha_split_plans(d, order, flags)
+                    macro = self._macro_merged_plan(d, order, flags) if single else None
+                    if macro is not None:
+                        p = macro
                 dim, tr = _resolve_simplex_entity(d, part.entity)
                 ent = _lib.entity_struct(prog.sd, tr)
             else:

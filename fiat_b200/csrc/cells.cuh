@@ -1,0 +1,243 @@
+// Split-cell tile kernel: FP64 tensor-pipe contraction for elements on split (macro) complexes.
+//
+// Input is the order-0 *derived* element of fiat_b200/plan.py: macro_merged: its rows are the original
+// element's derivative tables one after the other, and for every subcell c there is one block-sparse
+// coefficient matrix C_c on the un-normalised recurrence members of that subcell
+// (FIAT/expansions.py:449-490 scatters per-cell tables into a zero-padded global table through
+// cell_node_map; here the zeros are never formed).  A CTA owns a tile of PT points:
+//   phase 0  locate every point's subcell (bit-exact binning, FIAT/expansions.py:771-811) and sort the
+//            tile's columns by subcell, each subcell's range padded to a multiple of 8 columns;
+//   phase 1  value recurrence (FIAT/expansions.py:202-249, no derivative jets) level by level for all
+//            columns, each column in its own subcell's reference coordinates;
+//   phase 2  out[:, columns of c] = C_c . T[:, columns of c] with mma.sync.m8n8k4.f64; a warp owns one 8-row
+//            block for all columns of the tile, un-permutes it through shared memory and stores full rows;
+//   phase 3  points on interior facets (several subcells, measure zero for random points) are finished
+//            by their own thread: one value column per subcell, dense per-subcell rows from global
+//            memory, tables divided by the multiplicity and accumulated (FIAT/expansions.py:467-489).
+#pragma once
+#include "expansion.cuh"
+
+struct CellsGeom {
+    int PT;        // points per tile
+    int PTS;       // column capacity: PT + 8 * ncells (subcell ranges padded to octets), multiple of 8
+    int ldT;       // doubles between member rows of T (>= PTS, = 4 or 12 mod 16)
+    int maxlev;    // most recurrence steps in one wavefront level
+    int threads;   // 256: two CTAs per SM; 512: one CTA with the whole shared memory (wider tile)
+};
+
+#define FB_CELLS_THREADS 512   // upper bound; launched with 256 (two CTAs per SM) or 512 (one)
+#define FB_CELLS_GO 8          // octets of one subcell per column chunk
+
+template <int SD>
+__global__ void __launch_bounds__(FB_CELLS_THREADS, 1)
+k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid_constant__ SmallTab st,
+            const DevEntity E, const CellsGeom G, const double* __restrict__ pts, long long npts, long long ldp,
+            double* __restrict__ out, long long ostride) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int PT = G.PT, PTS = G.PTS, ldT = G.ldT;
+    double* T = smem;                                        // kpad x ldT
+    double* s_fa = T + (size_t)P.kpad * ldT;                 // 3 x PTS
+    double* s_fb = s_fa + 3 * PTS;                           // 3 x PTS
+    StepRec* s_rec = reinterpret_cast<StepRec*>(s_fb + 3 * PTS);         // 2 x maxlev
+    int* s_perm = reinterpret_cast<int*>(s_rec + 2 * G.maxlev);          // PTS: column -> point of the tile (-1 padding)
+    double* s_stage = reinterpret_cast<double*>(s_perm + PTS);           // warps x 8 rows x PT (PTS is even)
+    int* s_ptr = reinterpret_cast<int*>(s_stage + (size_t)(NT / 32) * 8 * PT);   // ncells x (nrb + 1) block offsets
+    int* s_chunk = s_ptr + P.ncells * (tab.nrb + 1);                     // PTS / 8 entries: cell | oct0 << 8 | noct << 20
+    __shared__ int s_cnt[32], s_off[33], s_fill[32], s_next, s_cols, s_nchunk;
+    const long long base = (long long)blockIdx.x * PT;
+
+    // ---- phase 0: subcell of every point, columns sorted by subcell -----------------------------
+    if (tid < 32) { s_cnt[tid] = 0; s_fill[tid] = 0; }
+    if (tid == 0) s_next = 0;
+    for (int j = tid; j < PTS; j += NT) {
+        s_perm[j] = -1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { s_fa[c * PTS + j] = 0.0; s_fb[c * PTS + j] = 0.0; }
+    }
+    for (int i = tid; i < P.kpad * ldT; i += NT) T[i] = 0.0;
+    for (int i = tid; i < P.ncells * (tab.nrb + 1); i += NT) s_ptr[i] = __ldg(P.blk_ptr + i);
+    __syncthreads();
+    double x[3] = {0.0, 0.0, 0.0};
+    unsigned mask = 0;
+    const long long p = base + tid;
+    const bool valid = tid < PT && p < npts;
+    if (valid) {
+        apply_entity<SD>(E, pts + p * ldp, x);
+        mask = locate_cells<SD>(st.bary, P.ncells, P.unique, x);
+    }
+    const int mult = __popc(mask);
+    const int cell = mult == 1 ? __ffs(mask) - 1 : -1;
+    if (cell >= 0) atomicAdd(&s_cnt[cell], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int off = 0, nchunk = 0;
+        for (int c = 0; c < P.ncells; ++c) {
+            s_off[c] = off;
+            const int noct = (s_cnt[c] + 7) >> 3;
+            for (int o = 0; o < noct; o += FB_CELLS_GO)
+                s_chunk[nchunk++] = c | ((off / 8 + o) << 8) | (min(FB_CELLS_GO, noct - o) << 20);
+            off += noct * 8;
+        }
+        s_off[P.ncells] = off;
+        s_cols = off;
+        s_nchunk = nchunk;
+    }
+    __syncthreads();
+    if (cell >= 0) {
+        const int col = s_off[cell] + atomicAdd(&s_fill[cell], 1);
+        s_perm[col] = tid;
+        const double* geom = P.geom + cell * FB_GEOM_DOUBLES;
+        double xr[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < SD; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < SD; ++d) s = fma(x[d], __ldg(geom + i * SD + d), s);
+            xr[i] = s + __ldg(geom + 9 + i);
+        }
+        double fa[3], fb[3];
+        recurrence_factors<SD>(xr, fa, fb);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            s_fa[c * PTS + col] = fa[c];
+            s_fb[c * PTS + col] = fb[c];
+        }
+        T[(size_t)tab.start_slot * ldT + col] = __ldg(geom + 12);
+    }
+    {
+        const int n0 = tab.level_ptr[1] - tab.level_ptr[0];
+        for (int i = tid; i < n0 * 4; i += NT)
+            reinterpret_cast<double*>(s_rec)[i] = reinterpret_cast<const double*>(&tab.steps[tab.level_ptr[0]])[i];
+    }
+    __syncthreads();
+    const int ncols = s_cols;
+
+    // ---- phase 1: value recurrence, wavefront order ----------------------------------------------
+    for (int lev = 0; lev < tab.nlevels; ++lev) {
+        const int l0 = tab.level_ptr[lev];
+        const int nst = tab.level_ptr[lev + 1] - l0;
+        const StepRec* rec = s_rec + (lev & 1) * G.maxlev;
+        if (lev + 1 < tab.nlevels) {
+            const int l1 = tab.level_ptr[lev + 1];
+            const int n1 = tab.level_ptr[lev + 2] - l1;
+            double* dst = reinterpret_cast<double*>(s_rec + ((lev + 1) & 1) * G.maxlev);
+            for (int i = tid; i < n1 * 4; i += NT) dst[i] = reinterpret_cast<const double*>(&tab.steps[l1])[i];
+        }
+        for (int it = tid; it < nst * ncols; it += NT) {
+            const int sl = it / ncols, col = it - sl * ncols;
+            const double fa[3] = {s_fa[col], s_fa[PTS + col], s_fa[2 * PTS + col]};
+            const double fb[3] = {s_fb[col], s_fb[PTS + col], s_fb[2 * PTS + col]};
+            run_step<SD, 0>(P, rec[sl], tab.geom0, fa, fb, T + col, ldT, 1, 1);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: block-sparse contraction on the FP64 tensor pipe -----------------------------------
+    // Work item = one 8-row block, for ALL columns of the tile: the warp walks the tile's column chunks (<= GO octets
+    // of one subcell each), streams that subcell's blocks of the row block through the DMMAs and scatters the
+    // fragments through the column permutation into its staging buffer; the finished 8 x PT piece of the table then
+    // leaves as full-width coalesced row stores.  (Storing 8-byte pieces straight through the permutation ran at
+    // 0.10-0.17 of the HBM peak: every sector is then written four times, partially.)  The loops are kept rolled:
+    // a fully unrolled variant was 23 000 SASS instructions and instruction-fetch bound.
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nrb = tab.nrb;
+    const int nchunk = s_nchunk;
+    const double* Tlane = T + (size_t)t * ldT + g;
+    const size_t kb_stride = (size_t)4 * ldT;
+    double* stage = s_stage + (size_t)warp * 8 * PT;                 // 8 rows x PT points
+    const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0) && base + PT <= npts;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&s_next, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nrb) break;
+        const int rb = tab.rb_order[item];
+#pragma unroll 1
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int chunk = s_chunk[ch];
+            const int c = chunk & 255, oct0 = (chunk >> 8) & 4095, noct = chunk >> 20;
+            const int q0 = s_ptr[c * (nrb + 1) + rb], q1 = s_ptr[c * (nrb + 1) + rb + 1];
+            double acc[FB_CELLS_GO][2];
+#pragma unroll
+            for (int o = 0; o < FB_CELLS_GO; ++o) acc[o][0] = acc[o][1] = 0.0;
+            const double* Tchunk = Tlane + oct0 * 8;
+            // fragments and column-block numbers are fetched four blocks ahead (register ring, loop stays rolled)
+            const double* fp = P.blk_frag + (size_t)q0 * 32 + lane;
+            const int* kp = P.blk_kb + q0;
+            const int nq = q1 - q0;
+            double a0 = __ldg(fp), a1 = nq > 1 ? __ldg(fp + 32) : 0.0, a2 = nq > 2 ? __ldg(fp + 64) : 0.0,
+                   a3 = nq > 3 ? __ldg(fp + 96) : 0.0;
+            int m0 = __ldg(kp), m1 = nq > 1 ? __ldg(kp + 1) : 0, m2 = nq > 2 ? __ldg(kp + 2) : 0, m3 = nq > 3 ? __ldg(kp + 3) : 0;
+#pragma unroll 1
+            for (int i = 0; i < nq; ++i) {
+                const double a = a0;
+                const double* Tb = Tchunk + (m0 & 0xffff) * kb_stride;
+                a0 = a1; a1 = a2; a2 = a3;
+                m0 = m1; m1 = m2; m2 = m3;
+                if (i + 4 < nq) {
+                    a3 = __ldg(fp + (size_t)(i + 4) * 32);
+                    m3 = __ldg(kp + i + 4);
+                }
+                // exactly noct DMMAs: a fall-through switch, because `if (o < noct)` in an unrolled loop is turned into
+                // predicated DMMAs that still occupy the tensor pipe (measured: 3.2x the useful DMMA count)
+                switch (noct) {
+                    case 8: dmma_8x8x4(acc[7][0], acc[7][1], a, Tb[56]);
+                    case 7: dmma_8x8x4(acc[6][0], acc[6][1], a, Tb[48]);
+                    case 6: dmma_8x8x4(acc[5][0], acc[5][1], a, Tb[40]);
+                    case 5: dmma_8x8x4(acc[4][0], acc[4][1], a, Tb[32]);
+                    case 4: dmma_8x8x4(acc[3][0], acc[3][1], a, Tb[24]);
+                    case 3: dmma_8x8x4(acc[2][0], acc[2][1], a, Tb[16]);
+                    case 2: dmma_8x8x4(acc[1][0], acc[1][1], a, Tb[8]);
+                    default: dmma_8x8x4(acc[0][0], acc[0][1], a, Tb[0]);
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < FB_CELLS_GO; ++o) {
+                if (o < noct) {
+                    const int jc = (oct0 + o) * 8 + 2 * t;
+                    const int p0 = s_perm[jc], p1 = s_perm[jc + 1];
+                    if (p0 >= 0) stage[g * PT + p0] = acc[o][0];
+                    if (p1 >= 0) stage[g * PT + p1] = acc[o][1];
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+            const int row = tab.row_perm[rb * 8 + r];
+            if (row < 0) continue;
+            double* rowp = out + (size_t)row * ostride + base;
+            if (vec_ok) {
+                for (int i = lane * 2; i < PT; i += 64)
+                    *reinterpret_cast<double2*>(rowp + i) = *reinterpret_cast<const double2*>(stage + r * PT + i);
+            } else {
+                for (int i = lane; i < PT; i += 32)
+                    if (base + i < npts) rowp[i] = stage[r * PT + i];
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- phase 3: points shared by several subcells -------------------------------------------------
+    if (!__syncthreads_or(valid && mult > 1)) return;
+    if (valid && mult > 1) {
+        const double inv_mult = 1.0 / (double)mult;
+        double* Tcol = T + tid;                             // one private column per thread (tid < PT <= ldT)
+        bool first = true;
+        while (mask) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            expansion_point<SD, 0>(P, tab, P.geom + c * FB_GEOM_DOUBLES, c, inv_mult, x, Tcol, ldT, 1, 1);
+            const double* C = P.ccell + (size_t)c * P.nrows * P.nslots;
+            for (int r = 0; r < P.nrows; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < P.nslots; ++k) s = fma(__ldg(C + (size_t)r * P.nslots + k), Tcol[(size_t)k * ldT], s);
+                double* o = out + (size_t)r * ostride + p;
+                *o = first ? s : (*o + s);
+            }
+            first = false;
+        }
+    }
+}

@@ -1,0 +1,69 @@
+// Launcher of the split-cell tile kernel (cells.cuh); its own translation unit (parallel compilation).
+#include "host_plan.cuh"
+#include "cells.cuh"
+
+namespace {
+
+bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
+    const DevSimplex& P = plan->simplex;
+    if (P.blk_cells < 2 || P.blk_cells != P.ncells || P.expansion != 0 || P.order != 0 || P.nblk == 0 || plan->tab.nrb == 0)
+        return false;
+    if (P.sd < 2) return false;
+    int maxlev = 1;
+    for (int l = 0; l < plan->tab.nlevels; ++l)
+        maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
+    // first choice: two resident CTAs per SM (110 KB each); otherwise one with the whole shared memory
+    if (P.ncells > 32) return false;
+    // widest tile first (the per-block loop overhead is amortised over the octets a subcell has in the tile):
+    // 256 threads and two CTAs per SM, or 512 threads and one CTA with all of the shared memory
+    const size_t budget = (size_t)plan->max_smem_optin - 1024;
+    for (int pt = 128; pt >= 32; pt -= 32) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const int threads = pass == 0 ? 256 : 512;
+            const size_t limit = pass == 0 ? (size_t)110 * 1024 : budget;
+            const int pts_cap = pt + 8 * P.ncells;
+            int ld = pts_cap;
+            while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
+            const size_t bytes = ((size_t)P.kpad * ld + 6 * pts_cap) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec)
+                                 + (size_t)pts_cap * sizeof(int) + (size_t)(threads / 32) * 8 * pt * sizeof(double)
+                                 + ((size_t)P.ncells * (plan->tab.nrb + 1) + pts_cap / 8 + 32) * sizeof(int) + 64;
+            if (bytes <= limit) {
+                G->PT = pt; G->PTS = pts_cap; G->ldT = ld; G->maxlev = maxlev; G->threads = threads;
+                *smem_out = bytes;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+template <int SD>
+int launch_cells(const fiatb200_plan* plan, const DevEntity& E, const CellsGeom& G, size_t smem, const double* pts,
+                 long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
+    int rc = fb_set_smem(k_mma_cells<SD>, smem);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
+    k_mma_cells<SD><<<grid, G.threads, smem, st>>>(plan->simplex, plan->tab, plan->small_tab, E, G, pts, npts, ldp,
+                                                          out, ostride);
+    fb_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
+}  // namespace
+
+bool fb_cells_applicable(const fiatb200_plan* plan) {
+    CellsGeom G;
+    size_t smem = 0;
+    return cells_geometry(plan, &G, &smem);
+}
+
+int fb_dispatch_cells(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
+                      double* out, long long ostride, cudaStream_t st) {
+    CellsGeom G;
+    size_t smem = 0;
+    if (!cells_geometry(plan, &G, &smem))
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "split-cell tile kernel not applicable to this plan");
+    if (plan->simplex.sd == 2) return launch_cells<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+    return launch_cells<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+}

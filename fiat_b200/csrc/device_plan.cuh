@@ -55,6 +55,7 @@ struct DevSimplex {
     const int* rb_order;
     const double* cderiv;       // derivative-folded coefficients of the value-table kernel (ncp == 0: absent)
     int cderiv_len, ncp;
+    int blk_cells;              // > 1: blk_ptr is blk_cells x (nrb + 1), one block-sparse matrix per subcell
 };
 
 // Placement of a kernel's rows inside a larger table (wrapper elements: enriched, mixed, H(div)/H(curl)

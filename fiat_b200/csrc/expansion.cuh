@@ -14,6 +14,13 @@
 #pragma once
 #include "device_plan.cuh"
 
+// FP64 tensor-pipe MMA: D(8x8) += A(8x4) B(4x8); lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) .. +1]
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
 // ---------------------------------------------------------------------------------------------
 // entity transform: x_cell = x_entity * C + offset
 // ---------------------------------------------------------------------------------------------

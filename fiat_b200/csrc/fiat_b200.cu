@@ -173,7 +173,7 @@ int dispatch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G
     }
 }
 
-enum KernelChoice { K_CELLWISE = 1, K_MMA = 2, K_SMALL = 3, K_VALS = 4, K_LATTICE = 5, K_TENSOR = 6 };
+enum KernelChoice { K_CELLWISE = 1, K_MMA = 2, K_SMALL = 3, K_VALS = 4, K_LATTICE = 5, K_TENSOR = 6, K_MMA_CELLS = 7 };
 
 // Which kernel a simplex plan runs on (flags: see include/fiat_b200.h).  Unless a flag forces one, the
 // applicable kernels are ranked by a per-SM cycle estimate for 32 points:
@@ -187,6 +187,8 @@ int choose_simplex_kernel(const fiatb200_plan* plan, uint32_t flags, MmaGeom* G,
     if (flags & 1u) use_mma = false;
     if ((flags & 2u) && !use_mma) return 0;
     if (flags & 2u) return K_MMA;
+    // derived order-0 elements of split-cell complexes (plan.macro_merged): points binned by subcell, DMMA
+    if (!(flags & 1u) && fb_cells_applicable(plan)) return K_MMA_CELLS;
     const bool vals_ok = !(flags & 11u) && fb_vals_applicable(plan);
     const bool small_ok = !(flags & 3u) && fb_small_applicable(plan);
     const double nmem = P.nslots, rows = P.nrows, na = P.na, steps = plan->tab.nsteps;
@@ -233,6 +235,9 @@ int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entit
     switch (choose_simplex_kernel(plan, flags, &G, &smem)) {
         case 0: return fb_fail(FIATB200_ERR_UNSUPPORTED, "DMMA kernel not applicable to this plan");
         case K_VALS: return fb_dispatch_vals(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case K_MMA_CELLS:
+            if (M.identity) return fb_dispatch_cells(plan, E, pts, npts, ldp, out, ostride, st);
+            break;          // placed rows: thread-per-point
         case K_SMALL: return fb_dispatch_small(plan, E, pts, npts, ldp, out, ostride, M, st);
         case K_MMA:
             switch (P.sd) {
@@ -411,7 +416,9 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     const size_t o_low2 = A.add(h->low2, sizeof(int32_t) * 6 * h->na);
     const size_t o_mul2 = A.add(h->mul2, sizeof(double) * 6 * h->na);
     const size_t o_line = A.add(h->line_tab, sizeof(double) * h->line_tab_len);
-    const size_t o_blk_ptr = A.add(h->blk_ptr, sizeof(int32_t) * (h->nrb + 1));
+    const int blk_cells = h->blk_cells > 1 ? h->blk_cells : 1;
+    if (blk_cells > 1 && blk_cells != h->ncells) { delete plan; return fb_fail(FIATB200_ERR_ARG, "per-subcell block tables do not match the complex"); }
+    const size_t o_blk_ptr = A.add(h->blk_ptr, sizeof(int32_t) * (size_t)blk_cells * (h->nrb + 1));
     const size_t o_blk_kb = A.add(h->blk_kb, sizeof(int32_t) * h->nblk);
     const size_t o_blk_frag = A.add(h->blk_frag, sizeof(double) * 32 * (size_t)h->nblk);
     const size_t o_rb_order = A.add(h->rb_order, sizeof(int32_t) * h->nrb);
@@ -449,6 +456,7 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     P.cderiv = at<double>(b, o_cderiv);
     P.cderiv_len = has_cderiv ? (int)h->cderiv_len : 0;
     P.ncp = has_cderiv ? h->ncp : 0;
+    P.blk_cells = blk_cells > 1 ? blk_cells : 0;
     *out = plan;
     return FIATB200_OK;
 }

@@ -57,6 +57,9 @@ int fb_set_smem(K kernel, size_t bytes) {
 bool fb_small_applicable(const fiatb200_plan* plan);
 int fb_dispatch_small(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
                       double* out, long long ostride, const DevRowMap& M, cudaStream_t st);
+bool fb_cells_applicable(const fiatb200_plan* plan);
+int fb_dispatch_cells(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
+                      double* out, long long ostride, cudaStream_t st);
 bool fb_vals_applicable(const fiatb200_plan* plan);
 int fb_dispatch_vals(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
                      double* out, long long ostride, const DevRowMap& M, cudaStream_t st);

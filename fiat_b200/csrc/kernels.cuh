@@ -131,12 +131,6 @@ k_locate(const DevSimplex P, const DevEntity E, const double* __restrict__ pts, 
 // ---------------------------------------------------------------------------------------------
 // tile kernel with FP64 tensor-pipe contraction
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
 struct MmaGeom {
     int PT;        // points per tile (multiple of 8)
     int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)

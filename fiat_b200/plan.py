@@ -26,7 +26,7 @@ from dataclasses import dataclass, field
 import numpy
 
 __all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf", "lattice_rowmap",
-           "alpha_split", "merged_split",
+           "alpha_split", "merged_split", "macro_merged",
            "resolve_parts", "Part", "value_shape_of", "num_dofs_of"]
 
 EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
@@ -230,6 +230,7 @@ class SimplexProgram:
     cderiv: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0))
     ncp: int = 0                # subcell stride of cderiv (ncells padded to 1, 4 or 16); 0 = absent
     slot_of: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int64))    # Morton member -> slot
+    blk_cells: int = 0          # > 1: blk_ptr holds one (nrb + 1)-entry row per subcell (split-cell tile kernel)
 
 
 def _dubiner_tables(desc, order, slot_perm=None):
@@ -686,6 +687,35 @@ def compile_simplex(desc, order):
         if cder is not None:
             prog.cderiv, prog.ncp = cder, ncp
         prog.slot_of = numpy.asarray(t["slot_of"], dtype=numpy.int64)
+    if ncells > 1 and desc.get("raw_members") and desc["expansion"] == "dubiner":
+        # split-cell tile kernel (cells.cuh): one block-sparse matrix per subcell, common row order
+        scale = numpy.abs(ccell_morton).max() if ccell_morton.size else 0.0
+        tol = 1e-14 * scale
+        rows_order = cluster_rows(numpy.concatenate(list(ccell_morton), axis=1), tol)
+        # the kernel streams a subcell's blocks row block by row block: every row block gets at least one
+        # (possibly zero) block, and the last block of a row block is flagged in bit 16 of its column-block number;
+        # blk_ptr holds one (nrb + 1)-entry row per subcell
+        ptrs, kbs, frags, total, counts = [], [], [], 0, None
+        for c in range(ncells):
+            bp, bk, bf, _, kpad = pack_blocks(ccell_morton[c][rows_order], tol)
+            kb2, fr2, ptr2 = [], [], [0]
+            for rb in range(len(bp) - 1):
+                ks = [int(k) for k in bk[bp[rb]:bp[rb + 1]]] or [0]
+                fr2.append(bf[32 * bp[rb]:32 * bp[rb + 1]] if bp[rb + 1] > bp[rb] else numpy.zeros(32))
+                ks[-1] |= 1 << 16
+                kb2.extend(ks)
+                ptr2.append(len(kb2))
+            ptrs.append(numpy.array(ptr2, dtype=numpy.int64) + total)
+            kbs.append(numpy.array(kb2, dtype=numpy.int32))
+            frags.append(numpy.concatenate(fr2))
+            total += len(kb2)
+            counts = numpy.diff(ptr2) if counts is None else counts + numpy.diff(ptr2)
+        prog.blk_ptr = numpy.concatenate(ptrs).astype(numpy.int32)
+        prog.blk_kb = numpy.concatenate(kbs)
+        prog.blk_frag = numpy.concatenate(frags)
+        prog.rb_order = numpy.argsort(-counts, kind="stable").astype(numpy.int32)
+        prog.row_perm = rows_order.astype(numpy.int32)
+        prog.kpad, prog.blk_cells = kpad, ncells
     if ncells == 1:
         # the tile kernel has no fix-up phase: T' = X T  =>  C T' = (C X) T
         folded = ccell[0].copy()
@@ -768,6 +798,42 @@ def merged_split(desc, order, split):
     out = dict(top)
     out["coeffs"] = stacked
     return out
+
+
+def macro_merged(desc, order, prog=None):
+    """Split-cell counterpart of alpha_split + merged_split: ONE derived order-0 element on the same complex whose
+    rows are the element's derivative tables one after the other and whose per-subcell coefficient matrices
+    (on the un-normalised recurrence members of each subcell) are the stacked C_alpha[cell].  It is what the
+    split-cell tile kernel (cells.cuh) tabulates: value recurrence only, points of a tile binned by subcell.
+    None if the element does not qualify."""
+    if desc.get("kind") != "simplex" or desc.get("expansion") != "dubiner" or int(desc["ncells"]) < 2:
+        return None
+    if desc.get("raw_members"):
+        return None
+    sd, n, ncells = int(desc["sd"]), int(desc["degree"]), int(desc["ncells"])
+    coeffs = numpy.asarray(desc["coeffs"])
+    ndofs, ncomp = coeffs.shape[0], coeffs.shape[1]
+    alphas = alpha_list(sd, order)
+    if sd < 2 or n < 1 or len(alphas) * ndofs * ncomp > MAX_MERGED_ROWS:
+        return None
+    if prog is None:
+        prog = compile_simplex(desc, order)
+    mats = alpha_matrices(desc, _dubiner_tables(desc, order), prog.ccell_morton, order)
+    if mats is None:
+        return None
+    nmem = prog.nslots
+    stacked = numpy.zeros((len(alphas) * ndofs * ncomp, ncells * nmem))
+    nrows = ndofs * ncomp
+    for j, per_cell in enumerate(mats):
+        for c in range(ncells):
+            m = per_cell[c]
+            stacked[j * nrows:(j + 1) * nrows, c * nmem:c * nmem + m.shape[1]] = m
+    d = {key: val for key, val in desc.items() if key not in ("nodes", "coeffs", "cell_node_map", "c0")}
+    d.update(c0=False, raw_members=True,
+             coeffs=numpy.ascontiguousarray(stacked.reshape(len(alphas) * ndofs, ncomp, ncells * nmem)),
+             cell_node_map=(numpy.arange(nmem, dtype=numpy.int64)[None, :]
+                            + nmem * numpy.arange(ncells, dtype=numpy.int64)[:, None]))
+    return d
 
 
 @dataclass

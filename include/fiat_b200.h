@@ -87,6 +87,11 @@ typedef struct {
     const double* cderiv;
     int64_t cderiv_len;
     int32_t ncp;               /* subcell stride: ncells padded to 1, 4 or 16 */
+    /* Split-cell tile kernel (order-0 derived elements of fiat_b200.plan.macro_merged): blk_cells == ncells > 1
+     * means blk_ptr holds one (nrb + 1)-entry row per subcell (offsets into blk_kb / blk_frag; every row block has
+     * at least one, possibly zero, block), blk_kb[q] = column block | (last block of its row block) << 16, and all
+     * subcells share rb_order and row_perm; 0: single matrix as described above. */
+    int32_t blk_cells;
 } fiatb200_simplex_program;
 
 /* Entity transform x_cell = x_entity * C + offset (FIAT/reference_element.py:570-609);
@@ -141,8 +146,8 @@ int fiatb200_lattice_plan_create(int32_t sd, int32_t degree, int32_t order, cons
 int fiatb200_plan_destroy(fiatb200_plan* plan);
 
 /* Which kernel fiatb200_tabulate would run for this plan and these flags: 1 thread-per-point, 2 DMMA tile,
- * 3 register (jet) kernel, 4 value-table kernel, 5 product-form (lattice), 6 tensor product; 0 if the
- * flags force a kernel that does not apply. */
+ * 3 register (jet) kernel, 4 value-table kernel, 5 product-form (lattice), 6 tensor product, 7 split-cell DMMA
+ * tile; 0 if the flags force a kernel that does not apply. */
 int fiatb200_plan_kernel(const fiatb200_plan* plan, uint32_t flags);
 
 /* Number of result rows per derivative multi-index, and number of multi-indices. */

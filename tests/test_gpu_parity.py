@@ -82,6 +82,25 @@ def test_alpha_split_matches_golden_and_jets(name, cuda_device):
     assert len(tab._resolve(case["order"], case["entity"], FORCE_GENERAL | NO_ALPHA_SPLIT)[0]) == 1
 
 
+@pytest.mark.parametrize("name", ["gn_tet_o2", "walkington_tet_o2"])
+def test_split_cell_tile_kernel_matches_golden(name, cuda_device):
+    """Split-cell elements too large for the value-table kernel: points binned by subcell, DMMA contraction with
+    per-subcell matrices (cells.cuh) against the thread-per-point kernel and the reference, including the fixture's
+    points on interior facets (several subcells per point)."""
+    from fiat_b200.api import Tabulator, NO_MACRO_MERGED
+    case = load_case(name)
+    tab = Tabulator(case["desc"], cuda_device)
+    assert tab.kernel_names(case["order"], case["entity"]) == ["mma_cells"]
+    _compare(case["desc"], tab.tabulate(case["order"], case["points"], case["entity"]), case["ref"])
+    assert tab.kernel_names(case["order"], case["entity"], NO_MACRO_MERGED) == ["cellwise"]
+    _compare(case["desc"], tab.tabulate(case["order"], case["points"], case["entity"], flags=NO_MACRO_MERGED), case["ref"])
+    # uniform points at a size with partial tiles, against the oracle
+    rng = numpy.random.default_rng(3)
+    lam = numpy.diff(numpy.concatenate([numpy.zeros((1000, 1)), numpy.sort(rng.random((1000, 3)), axis=1)], axis=1), axis=1)
+    want = fiat_oracle.tabulate(case["desc"], case["order"], lam)
+    _compare(case["desc"], tab.tabulate(case["order"], lam), want)
+
+
 @pytest.mark.parametrize("name", [n for n in golden_case_names()])
 def test_subcell_assignment_bit_exact(name, cuda_device):
     from fiat_b200.api import Tabulator
@@ -127,7 +146,7 @@ def test_tabulate_into_streaming(cuda_device):
     assert torch.isnan(buf[:, :, 200:]).all()
 
 
-@pytest.mark.parametrize("name", ["hct_o2", "ps12_o2", "n2curl4_tet_o1", "p8_tet_o2", "regge2_tet_o1", "gn_tet_o2",
+@pytest.mark.parametrize("name", ["hct_o2", "ps12_o2", "n2curl4_tet_o1", "p8_tet_o2", "regge2_tet_o1", "gn_tet_o2", "walkington_tet_o2",
                                   "gll_q3_hex_face4_o2", "p5_tet_o3", "mini_tri_o2", "n2curl3_p3_mixed_tet_o1",
                                   "p4_line_o2", "argyris_tri_o2"])
 @pytest.mark.parametrize("npts", [1, 37, 203])
