@@ -11,6 +11,7 @@ for w in p8_tet_o2 n2curl4_tet_o1 hct_o2 ps6_o2 ps12_o2 gll_q10_hex_o1 p3_tri_o1
 done
 python bench.py --workload p8_tet_o2 --flags 4 --steps 30 2>/dev/null | tail -1 >> gpurun_out/r01_bench_all.jsonl
 python bench.py --workload n2curl4_tet_o1 --flags 16 --steps 30 --no-cpu 2>/dev/null | tail -1 >> gpurun_out/r01_bench_all.jsonl
+python bench.py --workload p8_tet_o2 --flags 20 --steps 30 --no-cpu 2>/dev/null | tail -1 >> gpurun_out/r01_bench_all.jsonl
 # launch list of the default command (short): the tabulation kernel's share of the step
 python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/plain_default.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_p8_lattice.csv \
@@ -25,7 +26,7 @@ cap() {  # name workload kernel-regex launches-per-step extra-flags launches-to-
 }
 cap lattice_p8 p8_tet_o2 k_lattice 1 "" 1      # launch 0 is the 96-point self-check of the product form
 cap mma_p8 p8_tet_o2 k_mma 1 "--flags 4"
-cap mma_n2curl_split n2curl4_tet_o1 k_mma 4 ""
+cap mma_n2curl_merged n2curl4_tet_o1 k_mma 1 ""
 cap vals_hct hct_o2 k_vals 1 ""
 cap vals_ps6 ps6_o2 k_vals 1 ""
 cap vals_ps12 ps12_o2 k_vals 1 ""

@@ -5,7 +5,7 @@ import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CAPS = {  # report -> (workload, kernel path, batch)
     "lattice_p8": ("p8_tet_o2", "lattice", 1 << 20), "mma_p8": ("p8_tet_o2", "simplex", 1 << 20),
-    "mma_n2curl_split": ("n2curl4_tet_o1", "simplex", 1 << 20), "vals_hct": ("hct_o2", "simplex", 10_000_000),
+    "mma_n2curl_merged": ("n2curl4_tet_o1", "simplex", 1 << 20), "vals_hct": ("hct_o2", "simplex", 10_000_000),
     "vals_ps6": ("ps6_o2", "simplex", 10_000_000), "vals_ps12": ("ps12_o2", "simplex", 10_000_000),
     "tensor_hex": ("gll_q10_hex_o1", "tensor", 1 << 20),
 }
