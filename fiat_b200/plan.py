@@ -677,7 +677,7 @@ def compile_simplex(desc, order):
         sd=sd, degree=n, order=order, na=na, expansion=EXPANSION_CODES[desc["expansion"]],
         ncells=ncells, nslots=nslots, nrows=nrows, ndofs=ndofs,
         value_shape=tuple(int(s) for s in desc["value_shape"]),
-        unique=int(bool(desc["c0"]) and order == 0),
+        unique=int(desc["unique"]) if "unique" in desc else int(bool(desc["c0"]) and order == 0),
         geom=t["geom"], bary=bary, step_idx=t["step_idx"], step_abc=t["step_abc"], level_ptr=t["level_ptr"],
         nat_abc=t["nat_abc"], ccell_morton=ccell_morton, start_slot=int(t.get("start_slot", 0)),
         fix_idx=t["fix_idx"], fix_w=t["fix_w"],
@@ -829,7 +829,9 @@ def macro_merged(desc, order, prog=None):
             m = per_cell[c]
             stacked[j * nrows:(j + 1) * nrows, c * nmem:c * nmem + m.shape[1]] = m
     d = {key: val for key, val in desc.items() if key not in ("nodes", "coeffs", "cell_node_map", "c0")}
-    d.update(c0=False, raw_members=True,
+    # first-match binning of the original tabulation (continuity is not None and order == 0, expansions.py:452)
+    # must survive: the derived element is always tabulated at order 0 and is not a C0 set
+    d.update(c0=False, raw_members=True, unique=int(bool(desc["c0"]) and order == 0),
              coeffs=numpy.ascontiguousarray(stacked.reshape(len(alphas) * ndofs, ncomp, ncells * nmem)),
              cell_node_map=(numpy.arange(nmem, dtype=numpy.int64)[None, :]
                             + nmem * numpy.arange(ncells, dtype=numpy.int64)[:, None]))

@@ -94,6 +94,11 @@ def test_split_cell_tile_kernel_matches_golden(name, cuda_device):
     _compare(case["desc"], tab.tabulate(case["order"], case["points"], case["entity"]), case["ref"])
     assert tab.kernel_names(case["order"], case["entity"], NO_MACRO_MERGED) == ["cellwise"]
     _compare(case["desc"], tab.tabulate(case["order"], case["points"], case["entity"], flags=NO_MACRO_MERGED), case["ref"])
+    # order 0 keeps the reference's first-match binning (exterior points near several subcells)
+    ext = numpy.asarray(case["points"], dtype=float) + 0.3
+    for pts in (ext, numpy.asarray(case["points"], dtype=float)):
+        _compare(case["desc"], tab.tabulate(0, pts), fiat_oracle.tabulate(case["desc"], 0, pts))
+        _compare(case["desc"], tab.tabulate(case["order"], pts), fiat_oracle.tabulate(case["desc"], case["order"], pts))
     # uniform points at a size with partial tiles, against the oracle
     rng = numpy.random.default_rng(3)
     lam = numpy.diff(numpy.concatenate([numpy.zeros((1000, 1)), numpy.sort(rng.random((1000, 3)), axis=1)], axis=1), axis=1)
