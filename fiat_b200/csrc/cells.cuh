@@ -28,6 +28,39 @@ struct CellsGeom {
 #define FB_CELLS_THREADS 512   // upper bound; launched with 256 (two CTAs per SM) or 512 (one)
 #define FB_CELLS_GO 8          // octets of one subcell per column chunk
 
+// One (row block, column chunk) segment: the subcell's blocks of the row block against NOCT octets of columns, then
+// the fragments go through the column permutation into the warp's staging rows.  Fragments and column-block
+// numbers are fetched two blocks ahead; the loop stays rolled (code size).
+template <int NOCT>
+__device__ __forceinline__ void cells_segment(const double* __restrict__ fp, const int* __restrict__ kp, int nq,
+                                              const double* __restrict__ Tchunk, size_t kb_stride,
+                                              const int* __restrict__ perm, double* __restrict__ srow) {
+    double acc[NOCT][2];
+#pragma unroll
+    for (int o = 0; o < NOCT; ++o) acc[o][0] = acc[o][1] = 0.0;
+    double a0 = __ldg(fp), a1 = nq > 1 ? __ldg(fp + 32) : 0.0;
+    int m0 = __ldg(kp), m1 = nq > 1 ? __ldg(kp + 1) : 0;
+#pragma unroll 1
+    for (int i = 0; i < nq; ++i) {
+        const double a = a0;
+        const double* Tb = Tchunk + (m0 & 0xffff) * kb_stride;
+        a0 = a1;
+        m0 = m1;
+        if (i + 2 < nq) {
+            a1 = __ldg(fp + (size_t)(i + 2) * 32);
+            m1 = __ldg(kp + i + 2);
+        }
+#pragma unroll
+        for (int o = 0; o < NOCT; ++o) dmma_8x8x4(acc[o][0], acc[o][1], a, Tb[o * 8]);
+    }
+#pragma unroll
+    for (int o = 0; o < NOCT; ++o) {
+        const int p0 = perm[o * 8], p1 = perm[o * 8 + 1];
+        if (p0 >= 0) srow[p0] = acc[o][0];
+        if (p1 >= 0) srow[p1] = acc[o][1];
+    }
+}
+
 template <int SD>
 __global__ void __launch_bounds__(FB_CELLS_THREADS, 1)
 k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid_constant__ SmallTab st,
@@ -159,48 +192,21 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
             const int chunk = s_chunk[ch];
             const int c = chunk & 255, oct0 = (chunk >> 8) & 4095, noct = chunk >> 20;
             const int q0 = s_ptr[c * (nrb + 1) + rb], q1 = s_ptr[c * (nrb + 1) + rb + 1];
-            double acc[FB_CELLS_GO][2];
-#pragma unroll
-            for (int o = 0; o < FB_CELLS_GO; ++o) acc[o][0] = acc[o][1] = 0.0;
-            const double* Tchunk = Tlane + oct0 * 8;
-            // fragments and column-block numbers are fetched four blocks ahead (register ring, loop stays rolled)
             const double* fp = P.blk_frag + (size_t)q0 * 32 + lane;
-            const int* kp = P.blk_kb + q0;
-            const int nq = q1 - q0;
-            double a0 = __ldg(fp), a1 = nq > 1 ? __ldg(fp + 32) : 0.0, a2 = nq > 2 ? __ldg(fp + 64) : 0.0,
-                   a3 = nq > 3 ? __ldg(fp + 96) : 0.0;
-            int m0 = __ldg(kp), m1 = nq > 1 ? __ldg(kp + 1) : 0, m2 = nq > 2 ? __ldg(kp + 2) : 0, m3 = nq > 3 ? __ldg(kp + 3) : 0;
-#pragma unroll 1
-            for (int i = 0; i < nq; ++i) {
-                const double a = a0;
-                const double* Tb = Tchunk + (m0 & 0xffff) * kb_stride;
-                a0 = a1; a1 = a2; a2 = a3;
-                m0 = m1; m1 = m2; m2 = m3;
-                if (i + 4 < nq) {
-                    a3 = __ldg(fp + (size_t)(i + 4) * 32);
-                    m3 = __ldg(kp + i + 4);
-                }
-                // exactly noct DMMAs: a fall-through switch, because `if (o < noct)` in an unrolled loop is turned into
-                // predicated DMMAs that still occupy the tensor pipe (measured: 3.2x the useful DMMA count)
-                switch (noct) {
-                    case 8: dmma_8x8x4(acc[7][0], acc[7][1], a, Tb[56]);
-                    case 7: dmma_8x8x4(acc[6][0], acc[6][1], a, Tb[48]);
-                    case 6: dmma_8x8x4(acc[5][0], acc[5][1], a, Tb[40]);
-                    case 5: dmma_8x8x4(acc[4][0], acc[4][1], a, Tb[32]);
-                    case 4: dmma_8x8x4(acc[3][0], acc[3][1], a, Tb[24]);
-                    case 3: dmma_8x8x4(acc[2][0], acc[2][1], a, Tb[16]);
-                    case 2: dmma_8x8x4(acc[1][0], acc[1][1], a, Tb[8]);
-                    default: dmma_8x8x4(acc[0][0], acc[0][1], a, Tb[0]);
-                }
-            }
-#pragma unroll
-            for (int o = 0; o < FB_CELLS_GO; ++o) {
-                if (o < noct) {
-                    const int jc = (oct0 + o) * 8 + 2 * t;
-                    const int p0 = s_perm[jc], p1 = s_perm[jc + 1];
-                    if (p0 >= 0) stage[g * PT + p0] = acc[o][0];
-                    if (p1 >= 0) stage[g * PT + p1] = acc[o][1];
-                }
+            const double* Tchunk = Tlane + oct0 * 8;
+            const int* perm = s_perm + oct0 * 8 + 2 * t;
+            double* srow = stage + g * PT;
+            // one specialisation per number of octets: exactly noct DMMAs per block (an `if (o < noct)` in an unrolled
+            // loop becomes predicated DMMAs that still occupy the tensor pipe) and no dispatch inside the block loop
+            switch (noct) {
+                case 1: cells_segment<1>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                case 2: cells_segment<2>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                case 3: cells_segment<3>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                case 4: cells_segment<4>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                case 5: cells_segment<5>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                case 6: cells_segment<6>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                case 7: cells_segment<7>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                default: cells_segment<8>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
             }
         }
         __syncwarp();
