@@ -1,6 +1,7 @@
 """Randomised parity sweep on the GPU: every golden element description, several point counts (odd
 sizes, tails, single points), orders 0..order, points inside and slightly outside the cell, every
 entity the fixture names -- CUDA path (through the C ABI) against the CPU oracle."""
+import os
 import zlib
 
 import numpy
@@ -35,7 +36,8 @@ def test_random_points_against_oracle(name, cuda_device):
     case = load_case(name)
     desc = case["desc"]
     tab = Tabulator(desc, cuda_device)
-    rng = numpy.random.default_rng(zlib.crc32(name.encode()))          # stable across processes (hash() is salted)
+    # stable across processes (hash() is salted); FIATB200_FUZZ_SEED varies the sweep
+    rng = numpy.random.default_rng(zlib.crc32(name.encode()) + int(os.environ.get("FIATB200_FUZZ_SEED", "0")))
     for n in (1, 7, 33, 257):
         pts = _points_like(case, n, rng)
         for order in sorted({0, case["order"]}):
