@@ -354,9 +354,10 @@ def _greedy_groups(support, group):
     items has a small feature union: start from the widest remaining item, keep adding the item
     that enlarges the union least (ties: largest overlap)."""
     left = list(range(support.shape[0]))
+    sizes = support.sum(axis=1).tolist()
     order = []
     while left:
-        seed = max(left, key=lambda r: int(support[r].sum()))
+        seed = max(left, key=sizes.__getitem__)
         left.remove(seed)
         grp, sup = [seed], support[seed].copy()
         while len(grp) < group and left:
