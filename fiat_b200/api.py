@@ -450,9 +450,13 @@ class Tabulator:
 
         Because tabulation is linear in the coefficient tensor (FIAT/polynomial_set.py:71), this is the
         tabulation of a derived element whose coefficient tensor is coefficients . coeffs; it runs
-        through the same kernels (general paths; Ciarlet elements only)."""
+        through the same kernels.  Scalar tensor-product elements take a kernel of their own that nests the sum over
+        the factors (`_evaluate_tensor`)."""
+        if self.kind in ("tensor", "flattened") and (self.kind == "tensor" or self.desc["element"]["kind"] == "tensor"):
+            return self._evaluate_tensor(coefficients, order, points, entity)
         if self.kind != "simplex":
-            raise UnsupportedElement("evaluate() is available for Ciarlet elements on simplices")
+            raise UnsupportedElement("evaluate() is available for Ciarlet elements on simplices and scalar "
+                                     "tensor-product elements")
         u = numpy.atleast_2d(numpy.asarray(coefficients, dtype=numpy.float64))
         coeffs = numpy.asarray(self.desc["coeffs"], dtype=numpy.float64)         # (ndofs, ncomp, nexp)
         if u.shape[1] != coeffs.shape[0]:
@@ -461,6 +465,28 @@ class Tabulator:
         derived["coeffs"] = numpy.einsum("fd,dck->fck", u, coeffs)
         derived.pop("nodes", None)                                               # no longer a nodal basis
         return Tabulator(derived, self.device).tabulate(order, points, entity)
+
+    def _evaluate_tensor(self, coefficients, order, points, entity):
+        """evaluate() on scalar tensor-product elements: nested partial sums over the factors in one kernel
+        (`fiatb200_evaluate_tensor`); the prod(n_l)-row table is never formed."""
+        if planmod.value_shape_of(self.desc):
+            raise UnsupportedElement("fused evaluation covers scalar tensor-product elements")
+        p, nrows, pdim = self._tensor_plan(self.desc, order, entity)
+        u = numpy.atleast_2d(numpy.asarray(coefficients, dtype=numpy.float64))
+        if u.shape[1] != nrows:
+            raise ValueError(f"expected {nrows} coefficients per function, got {u.shape[1]}")
+        pts = self._points(points, pdim)
+        npts = pts.shape[0]
+        alphas = self.alphas(order)
+        coef = torch.as_tensor(numpy.ascontiguousarray(u), device=self.device)
+        out = torch.empty((len(alphas), u.shape[0], npts), dtype=torch.float64, device=self.device)
+        if npts:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fiatb200_evaluate_tensor(p.handle, coef.data_ptr(), u.shape[0], pts.data_ptr(), npts,
+                                                              pts.stride(0) if pts.shape[1] else 0, out.data_ptr(), npts,
+                                                              stream))
+        return {a: out[j] for j, a in enumerate(alphas)}
 
     def locate_subcells(self, points, unique, entity=None):
         """Bitmask (uint32 as int64 tensor) of the subcells each point is binned to."""

@@ -657,6 +657,58 @@ int fiatb200_tabulate(const fiatb200_plan* plan, const fiatb200_entity_map* enti
     return fiatb200_tabulate_mapped(plan, entity, pts_dev, npts, pts_ld, out_dev, out_row_stride, nullptr, flags, stream);
 }
 
+int fiatb200_evaluate_tensor(const fiatb200_plan* plan, const double* coef_dev, int32_t nfunc, const double* pts_dev,
+                             int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride, void* stream) {
+    if (!plan || plan->kind != PLAN_TENSOR) return fb_fail(FIATB200_ERR_ARG, "a tensor-product plan is required");
+    if (plan->tensor.ncomp != 1) return fb_fail(FIATB200_ERR_UNSUPPORTED, "fused evaluation covers scalar tensor-product elements");
+    if (nfunc < 1 || npts < 0 || out_row_stride < npts) return fb_fail(FIATB200_ERR_ARG, "bad function / point count / row stride");
+    if (npts == 0) return FIATB200_OK;
+    if (!coef_dev || !out_dev || (!pts_dev && pts_ld != 0)) return fb_fail(FIATB200_ERR_ARG, "null device pointer");
+    const DevTensor& Q = plan->tensor;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int bp = 128;
+    while (bp > 32 && (size_t)Q.total_doubles * bp * sizeof(double) > 96 * 1024) bp >>= 1;
+    const size_t smem = (size_t)Q.total_doubles * bp * sizeof(double);
+    if (smem > (size_t)plan->max_smem_optin)
+        return fb_fail(FIATB200_ERR_UNSUPPORTED, "factor tables of one point tile do not fit in shared memory");
+    const unsigned grid = (unsigned)((npts + bp - 1) / bp);
+    int rc = FIATB200_OK;
+    // three scalar line factors of moderate size (quadrilateral x interval = hexahedron): sum-factorised kernel
+    bool hex = Q.nleaf == 3 && Q.order <= 2 && !getenv("FIATB200_EVAL_GENERIC");
+    for (int l = 0; l < Q.nleaf && hex; ++l)
+        hex = Q.leaf[l].prog.sd == 1 && Q.leaf[l].ncomp == 1 && Q.leaf[l].ndof <= FB_EVAL_NMAX;
+    if (hex) {
+#define FB_HEX_LAUNCH(O_)                                                             \
+        rc = fb_set_smem(k_hex_eval<O_>, smem);                                       \
+        if (rc) return rc;                                                            \
+        k_hex_eval<O_><<<grid, bp, smem, st>>>(Q, coef_dev, nfunc, pts_dev, npts, pts_ld, out_dev, out_row_stride);
+        switch (Q.order) {
+            case 0: FB_HEX_LAUNCH(0) break;
+            case 1: FB_HEX_LAUNCH(1) break;
+            default: FB_HEX_LAUNCH(2) break;
+        }
+#undef FB_HEX_LAUNCH
+        fb_launches++;
+        FB_CUDA(cudaGetLastError());
+        return FIATB200_OK;
+    }
+#define FB_EVAL_LAUNCH(O_)                                                            \
+    rc = fb_set_smem(k_tensor_eval<O_>, smem);                                        \
+    if (rc) return rc;                                                                \
+    k_tensor_eval<O_><<<grid, bp, smem, st>>>(Q, coef_dev, nfunc, pts_dev, npts, pts_ld, out_dev, out_row_stride);
+    switch (Q.order) {
+        case 0: FB_EVAL_LAUNCH(0) break;
+        case 1: FB_EVAL_LAUNCH(1) break;
+        case 2: FB_EVAL_LAUNCH(2) break;
+        case 3: FB_EVAL_LAUNCH(3) break;
+        default: FB_EVAL_LAUNCH(-1) break;
+    }
+#undef FB_EVAL_LAUNCH
+    fb_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
 int fiatb200_zero_rows(double* out_dev, int64_t out_row_stride, int64_t npts, int64_t total_rows, int32_t nalpha,
                        const int32_t* rows_dev, int32_t nrows, void* stream) {
     if (npts == 0 || nrows == 0) return FIATB200_OK;

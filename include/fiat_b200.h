@@ -169,6 +169,14 @@ int fiatb200_tabulate_mapped(const fiatb200_plan* plan, const fiatb200_entity_ma
                              double* out_dev, int64_t out_row_stride, const fiatb200_row_map* map,
                              uint32_t flags, void* stream);
 
+/* Fused consumer of a scalar tensor-product tabulation (point evaluation / interpolation):
+ * out[(alpha_index * nfunc + f) * out_row_stride + point] = sum_dof coef[f * ndofs + dof] * D^alpha phi_dof(point),
+ * i.e. coef . TensorProductElement.tabulate(order, points) (FIAT/tensor_product.py:231-292) without forming the
+ * (ndofs x npts) tables; the sum over the product dofs is nested over the factors.  coef_dev: nfunc x ndofs,
+ * row-major, on the device. */
+int fiatb200_evaluate_tensor(const fiatb200_plan* plan, const double* coef_dev, int32_t nfunc, const double* pts_dev,
+                             int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride, void* stream);
+
 /* Zero-fill the listed rows (device array of nrows row numbers) of every derivative table: the
  * entries of a wrapper element's table that none of its parts writes. */
 int fiatb200_zero_rows(double* out_dev, int64_t out_row_stride, int64_t npts, int64_t total_rows, int32_t nalpha,

@@ -106,6 +106,24 @@ def test_split_cell_tile_kernel_matches_golden(name, cuda_device):
     _compare(case["desc"], tab.tabulate(case["order"], lam), want)
 
 
+@pytest.mark.parametrize("name", ["gll_q10_hex_o1", "gll_q3_hex_face4_o2", "q2_quad_o2", "p2xp1_prism_o1", "dq32_quad_o2"])
+def test_fused_evaluation_on_tensor_products(name, cuda_device):
+    """evaluate() on scalar tensor-product elements (nested sums over the factors, no table) against
+    coefficients . reference table."""
+    from fiat_b200.api import Tabulator
+    case = load_case(name)
+    ref0 = next(iter(case["ref"].values()))
+    rng = numpy.random.default_rng(11)
+    u = rng.standard_normal((3, ref0.shape[0]))
+    got = Tabulator(case["desc"], cuda_device).evaluate(u, case["order"], case["points"], case["entity"])
+    assert [tuple(k) for k in got.keys()] == [tuple(k) for k in case["ref"].keys()]
+    for alpha, ref in case["ref"].items():
+        want = u @ ref
+        bound = (abs(u) @ abs(ref)).max()
+        assert got[alpha].shape == want.shape
+        assert abs(got[alpha].cpu().numpy() - want).max() <= 1e-12 * max(bound, 1e-300), alpha
+
+
 @pytest.mark.parametrize("name", [n for n in golden_case_names()])
 def test_subcell_assignment_bit_exact(name, cuda_device):
     from fiat_b200.api import Tabulator
