@@ -572,25 +572,27 @@ k_hex_eval(const DevTensor Q, const double* __restrict__ coef, int nfunc, const 
             for (int a1 = 0; a1 < NO; ++a1)
 #pragma unroll
                 for (int a2 = 0; a2 < NO; ++a2) mid[a1][a2] = 0.0;
+#pragma unroll 2
             for (int i1 = 0; i1 < n1; ++i1) {
                 const double* row = c + ((size_t)i0 * n1 + i1) * n2;
-                double inner[NO];
+                // the coefficient row is zero-padded in registers; even and odd members accumulate separately
+                // (two shorter dependent chains per derivative order)
+                double cv[FB_EVAL_NMAX];
 #pragma unroll
-                for (int a2 = 0; a2 < NO; ++a2) inner[a2] = 0.0;
+                for (int i2 = 0; i2 < FB_EVAL_NMAX; ++i2) cv[i2] = i2 < n2 ? __ldg(row + i2) : 0.0;
+                double inner[NO][2];
 #pragma unroll
-                for (int i2 = 0; i2 < FB_EVAL_NMAX; ++i2) {
-                    if (i2 < n2) {
-                        const double cv = __ldg(row + i2);
+                for (int a2 = 0; a2 < NO; ++a2) inner[a2][0] = inner[a2][1] = 0.0;
 #pragma unroll
-                        for (int a2 = 0; a2 < NO; ++a2) inner[a2] = fma(cv, T2[a2][i2], inner[a2]);
-                    }
-                }
+                for (int i2 = 0; i2 < FB_EVAL_NMAX; ++i2)
+#pragma unroll
+                    for (int a2 = 0; a2 < NO; ++a2) inner[a2][i2 & 1] = fma(cv[i2], T2[a2][i2], inner[a2][i2 & 1]);
 #pragma unroll
                 for (int a1 = 0; a1 < NO; ++a1) {
                     const double t1 = T1[(size_t)(a1 * n1 + i1) * BP];
 #pragma unroll
                     for (int a2 = 0; a2 < NO; ++a2)
-                        if (a1 + a2 <= ORDER) mid[a1][a2] = fma(t1, inner[a2], mid[a1][a2]);
+                        if (a1 + a2 <= ORDER) mid[a1][a2] = fma(t1, inner[a2][0] + inner[a2][1], mid[a1][a2]);
                 }
             }
 #pragma unroll
