@@ -92,6 +92,44 @@ def test_alpha_split_reproduces_reference(name):
     assert prog.kpad % 4 == 0 and emu.blocks_to_dense(prog).shape == (prog.nrows, prog.nslots)
 
 
+@pytest.mark.parametrize("name", ["gn_tet_o2", "walkington_tet_o2", "hct4_tri_o2", "hct_o2", "ps12_o2"])
+def test_macro_merged_reproduces_reference(name):
+    """Derived order-0 element of a split-cell element (plan.macro_merged): per-subcell stacked matrices on the
+    subcell's un-normalised members; its order-0 tabulation (with the reference's binning and multiplicities) is the
+    stack of the reference's derivative tables.  Also checks the per-subcell block packing the tile kernel streams."""
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    merged = planmod.macro_merged(desc, order)
+    assert merged is not None and merged["unique"] == int(bool(desc["c0"]) and order == 0)
+    prog = planmod.compile_simplex(merged, 0)
+    assert prog.blk_cells == prog.ncells == int(desc["ncells"]) and prog.unique == merged["unique"]
+    pts = numpy.asarray(case["points"], dtype=float)
+    near = fiat_oracle.locate_cells(desc, pts, unique=bool(prog.unique))
+    out = emu.run_simplex(prog, pts, near)[0]
+    alphas = planmod.alpha_list(int(desc["sd"]), order)
+    nrows = out.shape[0] // len(alphas)
+    for j, alpha in enumerate(alphas):
+        ref = case["ref"][alpha].reshape(-1, len(pts))
+        assert abs(out[j * nrows:(j + 1) * nrows] - ref).max() <= tolerance(desc, alpha) * max(abs(ref).max(), 1e-300), alpha
+    # block stream of every subcell: one (nrb + 1) pointer row per subcell, >= 1 block per row block, last-block flags
+    nrb = len(prog.blk_ptr) // prog.ncells - 1
+    assert len(prog.blk_ptr) == prog.ncells * (nrb + 1) and nrb == -(-prog.nrows // 8)
+    for c in range(prog.ncells):
+        ptr = prog.blk_ptr[c * (nrb + 1):(c + 1) * (nrb + 1)]
+        assert (numpy.diff(ptr) >= 1).all()
+        dense = numpy.zeros((nrb * 8, prog.kpad))
+        for rb in range(nrb):
+            flags = prog.blk_kb[ptr[rb]:ptr[rb + 1]] >> 16
+            assert flags[-1] == 1 and not flags[:-1].any()
+            for q in range(ptr[rb], ptr[rb + 1]):
+                kb = prog.blk_kb[q] & 0xffff
+                dense[rb * 8:rb * 8 + 8, kb * 4:kb * 4 + 4] += prog.blk_frag[q * 32:(q + 1) * 32].reshape(8, 4)
+        full = numpy.zeros((nrb * 8, prog.kpad))
+        full[:prog.nrows, :prog.nslots] = prog.ccell_morton[c][prog.row_perm]
+        # dropped blocks hold nothing above 1e-14 of the largest coefficient (round-off of the folded matrices)
+        assert abs(dense - full).max() <= 1e-14 * abs(prog.ccell_morton).max()
+
+
 def test_mis_order_matches_reference_keys():
     for name in golden_case_names():
         case = load_case(name)
