@@ -12,7 +12,6 @@ bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
     int maxlev = 1;
     for (int l = 0; l < plan->tab.nlevels; ++l)
         maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
-    // first choice: two resident CTAs per SM (110 KB each); otherwise one with the whole shared memory
     if (P.ncells > 32) return false;
     // widest tile first (the per-block loop overhead is amortised over the octets a subcell has in the tile):
     // 256 threads and two CTAs per SM, or 512 threads and one CTA with all of the shared memory
