@@ -74,8 +74,9 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     double* s_fb = s_fa + 3 * PTS;                           // 3 x PTS
     StepRec* s_rec = reinterpret_cast<StepRec*>(s_fb + 3 * PTS);         // 2 x maxlev
     int* s_perm = reinterpret_cast<int*>(s_rec + 2 * G.maxlev);          // PTS: column -> point of the tile (-1 padding)
-    double* s_stage = reinterpret_cast<double*>(s_perm + PTS);           // warps x 8 rows x PT (PTS is even)
-    int* s_ptr = reinterpret_cast<int*>(s_stage + (size_t)(NT / 32) * 8 * PT);   // ncells x (nrb + 1) block offsets
+    double* s_stage = reinterpret_cast<double*>(s_perm + PTS);           // warps x 8 rows x (PT + 2) (PTS is even)
+    const int SP = PT + 2;      // staging row stride: rows of a fragment (same column, 8 rows) land in 8 different banks
+    int* s_ptr = reinterpret_cast<int*>(s_stage + (size_t)(NT / 32) * 8 * SP);   // ncells x (nrb + 1) block offsets
     int* s_chunk = s_ptr + P.ncells * (tab.nrb + 1);                     // PTS / 8 entries: cell | oct0 << 8 | noct << 20
     __shared__ int s_cnt[32], s_off[33], s_fill[32], s_next, s_cols, s_nchunk;
     const long long base = (long long)blockIdx.x * PT;
@@ -179,7 +180,7 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     const int nchunk = s_nchunk;
     const double* Tlane = T + (size_t)t * ldT + g;
     const size_t kb_stride = (size_t)4 * ldT;
-    double* stage = s_stage + (size_t)warp * 8 * PT;                 // 8 rows x PT points
+    double* stage = s_stage + (size_t)warp * 8 * SP;                 // 8 rows x PT points (+ 2 padding)
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0) && base + PT <= npts;
     for (;;) {
         int item = 0;
@@ -195,7 +196,7 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
             const double* fp = P.blk_frag + (size_t)q0 * 32 + lane;
             const double* Tchunk = Tlane + oct0 * 8;
             const int* perm = s_perm + oct0 * 8 + 2 * t;
-            double* srow = stage + g * PT;
+            double* srow = stage + g * SP;
             // one specialisation per number of octets: exactly noct DMMAs per block (an `if (o < noct)` in an unrolled
             // loop becomes predicated DMMAs that still occupy the tensor pipe) and no dispatch inside the block loop
             switch (noct) {
@@ -217,10 +218,10 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
             double* rowp = out + (size_t)row * ostride + base;
             if (vec_ok) {
                 for (int i = lane * 2; i < PT; i += 64)
-                    *reinterpret_cast<double2*>(rowp + i) = *reinterpret_cast<const double2*>(stage + r * PT + i);
+                    *reinterpret_cast<double2*>(rowp + i) = *reinterpret_cast<const double2*>(stage + r * SP + i);
             } else {
                 for (int i = lane; i < PT; i += 32)
-                    if (base + i < npts) rowp[i] = stage[r * PT + i];
+                    if (base + i < npts) rowp[i] = stage[r * SP + i];
             }
         }
         __syncwarp();

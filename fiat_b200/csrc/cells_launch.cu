@@ -24,7 +24,7 @@ bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
             int ld = pts_cap;
             while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
             const size_t bytes = ((size_t)P.kpad * ld + 6 * pts_cap) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec)
-                                 + (size_t)pts_cap * sizeof(int) + (size_t)(threads / 32) * 8 * pt * sizeof(double)
+                                 + (size_t)pts_cap * sizeof(int) + (size_t)(threads / 32) * 8 * (pt + 2) * sizeof(double)
                                  + ((size_t)P.ncells * (plan->tab.nrb + 1) + pts_cap / 8 + 32) * sizeof(int) + 64;
             if (bytes <= limit) {
                 G->PT = pt; G->PTS = pts_cap; G->ldT = ld; G->maxlev = maxlev; G->threads = threads;
