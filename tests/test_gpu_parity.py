@@ -148,6 +148,37 @@ def test_host_buffer_call(name, cuda_device):
     _compare(case["desc"], got, case["ref"])
 
 
+def test_point_containers_and_error_contract(cuda_device):
+    """The reference accepts any iterable of coordinate tuples or an ndarray (float32 is promoted), returns zero
+    tables for derivative orders above the degree, and raises for bad orders / entities."""
+    from fiat_b200.api import Tabulator
+    case = load_case("p3_tri_o1")
+    tab = Tabulator(case["desc"], cuda_device)
+    pts = numpy.asarray(case["points"], dtype=float)[:16]
+    base = tab.tabulate(1, pts)
+    as_list = tab.tabulate(1, [tuple(p) for p in pts])
+    strided = torch.as_tensor(numpy.concatenate([pts, pts], axis=1), device=cuda_device)[:, :2]     # row stride 4
+    from_strided = tab.tabulate(1, strided)
+    pts32 = pts.astype(numpy.float32)
+    from32 = tab.tabulate(1, pts32)
+    want32 = fiat_oracle.tabulate(case["desc"], 1, pts32.astype(numpy.float64))
+    for alpha in base:
+        assert torch.equal(base[alpha], as_list[alpha]) and torch.equal(base[alpha], from_strided[alpha])
+    _compare(case["desc"], from32, want32)
+    high = tab.tabulate(5, pts)                      # cubic element: orders 4 and 5 vanish identically
+    assert len(high) == 21
+    for alpha, v in high.items():
+        if sum(alpha) > 3:
+            assert not v.any()
+    _compare(case["desc"], {a: v for a, v in high.items() if sum(a) <= 1}, {a: case["ref"][a][:, :16] for a in base})
+    with pytest.raises(ValueError):
+        tab.tabulate(-1, pts)
+    with pytest.raises(KeyError):
+        tab.tabulate(1, pts[:, :1], entity=(1, 7))
+    with pytest.raises(NotImplementedError):
+        tab.tabulate(1, numpy.array([[object(), object()]], dtype=object))
+
+
 def test_empty_point_set(cuda_device):
     from fiat_b200.api import Tabulator
     case = load_case("p3_tri_o1")
