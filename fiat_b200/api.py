@@ -15,6 +15,7 @@ loaded from a file), which is how the GPU box runs without FIAT installed.  Plan
 are cached per element and order.  There is no CPU fallback: unsupported elements raise
 `NotImplementedError`, a missing CUDA library or device raises.
 """
+import collections
 import ctypes
 import threading
 import weakref
@@ -154,7 +155,7 @@ class Tabulator:
         -> [(alpha index, plan or None for an identically zero table)]"""
         if flags & (FORCE_THREAD_PER_POINT | FORCE_DMMA | NO_ALPHA_SPLIT) or order < 1:
             return None
-        key = ("split", id(desc), order)
+        key = ("split", id(desc), order, flags & 11)      # the result depends on the kernel the flags select
         with self._lock:
             if key in self._plans:
                 return self._plans[key]
@@ -180,7 +181,7 @@ class Tabulator:
         the element would otherwise run thread-per-point; None otherwise."""
         if flags & (FORCE_THREAD_PER_POINT | FORCE_DMMA | NO_MACRO_MERGED) or int(desc.get("ncells", 1)) < 2:
             return None
-        key = ("macro", id(desc), order)
+        key = ("macro", id(desc), order, flags & 11)
         with self._lock:
             if key in self._plans:
                 return self._plans[key][0]
@@ -399,6 +400,10 @@ class Tabulator:
         alphas = self.alphas(order)
         if out is None:
             out = numpy.empty((len(alphas), nrows, npts))
+        elif not (isinstance(out, numpy.ndarray) and out.dtype == numpy.float64 and out.flags.c_contiguous
+                  and out.flags.writeable and out.shape == (len(alphas), nrows, npts)):
+            # the library writes (nalpha * nrows) rows of npts doubles through the raw pointer
+            raise ValueError(f"out must be a writeable C-contiguous float64 ndarray of shape {(len(alphas), nrows, npts)}")
         if npts and len(launches) == 1 and launches[0][2] is None:
             p, ent, _, _ = launches[0]
             with torch.cuda.device(self.device):
@@ -508,7 +513,8 @@ class Tabulator:
 
 _cache_lock = threading.Lock()
 _by_element = weakref.WeakKeyDictionary()
-_by_desc = {}
+_by_desc = collections.OrderedDict()        # description dicts are not weak-referenceable: bounded LRU instead
+MAX_CACHED_DESCRIPTIONS = 64
 
 
 def get_tabulator(element, device=None):
@@ -521,6 +527,10 @@ def get_tabulator(element, device=None):
             if hit is None or hit[0] is not element:
                 hit = (element, Tabulator(element, dev))
                 _by_desc[key] = hit
+                while len(_by_desc) > MAX_CACHED_DESCRIPTIONS:
+                    _by_desc.popitem(last=False)
+            else:
+                _by_desc.move_to_end(key)
             return hit[1]
     with _cache_lock:
         try:

@@ -11,7 +11,7 @@
 //            columns, each column in its own subcell's reference coordinates;
 //   phase 2  out[:, columns of c] = C_c . T[:, columns of c] with mma.sync.m8n8k4.f64; a warp owns one 8-row
 //            block for all columns of the tile, un-permutes it through shared memory and stores full rows;
-//   phase 3  points on interior facets (several subcells, measure zero for random points) are finished
+//   phase 3  points on interior facets (several subcells, measure zero for random points) or in no subcell are finished
 //            by their own thread: one value column per subcell, dense per-subcell rows from global
 //            memory, tables divided by the multiplicity and accumulated (FIAT/expansions.py:467-489).
 #pragma once
@@ -228,7 +228,10 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     }
 
     // ---- phase 3: points shared by several subcells -------------------------------------------------
-    if (!__syncthreads_or(valid && mult > 1)) return;
+    if (!__syncthreads_or(valid && mult != 1)) return;
+    if (valid && mult == 0) {       // in no subcell (NaN / Inf coordinates): zero column, like the reference
+        for (int r = 0; r < P.nrows; ++r) out[(size_t)r * ostride + p] = 0.0;
+    }
     if (valid && mult > 1) {
         const double inv_mult = 1.0 / (double)mult;
         double* Tcol = T + tid;                             // one private column per thread (tid < PT <= ldT)

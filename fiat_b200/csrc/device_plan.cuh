@@ -82,6 +82,17 @@ __device__ __forceinline__ size_t fb_map_row(const DevRowMap& M, int r, double& 
     return (size_t)(M.dof_base + dof) * M.nc_out + M.comp_out[k];
 }
 
+// A point that lies in no subcell of a split complex (NaN / Inf coordinates make every l1 distance NaN): the
+// reference leaves the point's column of its zero-initialised tables untouched (FIAT/expansions.py:479-489).
+__device__ __forceinline__ void fb_zero_column(const DevRowMap& M, double* __restrict__ out, long long ostride,
+                                               long long p, int na, int nrows) {
+    for (int a = 0; a < na; ++a)
+        for (int r = 0; r < nrows; ++r) {
+            double sgn;
+            out[((size_t)a * M.total_rows + fb_map_row(M, r, sgn)) * ostride + p] = 0.0;
+        }
+}
+
 struct DevEntity {
     int dim, identity;
     double C[9];

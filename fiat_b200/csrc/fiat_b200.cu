@@ -8,6 +8,41 @@ thread_local std::string g_error;
 }
 std::atomic<long long> fb_launches{0};
 
+const FbTuning& fb_tuning() {
+    static const FbTuning t = [] {
+        auto geti = [](const char* name) {
+            const char* env = getenv(name);
+            return env ? atoi(env) : -1;
+        };
+        FbTuning v;
+        v.mma_pt = geti("FIATB200_MMA_PT");
+        v.mma_skip = geti("FIATB200_MMA_SKIP");
+        v.mma_threads = geti("FIATB200_MMA_THREADS");
+        v.tensor_bp = geti("FIATB200_TENSOR_BP");
+        v.eval_bp = geti("FIATB200_EVAL_BP");
+        v.eval_generic = geti("FIATB200_EVAL_GENERIC");
+        v.vals_tpc = geti("FIATB200_VALS_TPC");
+        v.vals_j = geti("FIATB200_VALS_J");
+        v.stage = geti("FIATB200_MMA_STAGE");
+        return v;
+    }();
+    return t;
+}
+
+int fb_raise_smem_limit(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> limit;     // (device, kernel) -> bytes opted in
+    int dev = 0;
+    FB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> guard(mu);
+    size_t& cur = limit[std::make_pair(dev, kernel)];
+    if (bytes > cur) {
+        FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return FIATB200_OK;
+}
+
 int fb_fail(int code, const std::string& msg) {
     g_error = msg;
     return code;
@@ -107,7 +142,8 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     // one CTA per SM: the widest tile whose expansion table fits in shared memory
     const size_t budget = (size_t)plan->max_smem_optin - 1024;
     int pt_max = 128;
-    if (const char* env = getenv("FIATB200_MMA_PT")) pt_max = std::max(8, atoi(env)) & ~7;   // tuning override
+    const FbTuning& tune = fb_tuning();
+    if (tune.mma_pt >= 0) pt_max = std::max(8, tune.mma_pt) & ~7;
     const int go = P.na >= 8 ? 1 : (P.na >= 5 ? 2 : (P.na >= 3 ? 4 : (P.na == 2 ? 8 : 16)));   // octets per contraction work item (kernels.cuh)
     int maxlev = 1;
     for (int l = 0; l < plan->tab.nlevels; ++l)
@@ -117,7 +153,7 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     for (int pass = 0; pass < 2; ++pass) {
         const size_t limit = pass == 0 ? (size_t)110 * 1024 : budget;
         const int pt_min = pass == 0 ? std::max(32, 8 * go) : 8 * go;
-        if (pass == 0 && getenv("FIATB200_MMA_PT")) continue;
+        if (pass == 0 && tune.mma_pt >= 0) continue;
         for (int pt = pt_max; pt >= pt_min; pt >>= 1) {
             int ld = P.na * pt;
             while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
@@ -129,7 +165,7 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
                 G->ldT = ld;
                 G->maxlev = maxlev;
                 G->skip = 0;
-                if (const char* env = getenv("FIATB200_MMA_SKIP")) G->skip = atoi(env);   // profiling only
+                if (tune.mma_skip >= 0) G->skip = tune.mma_skip;    // profiling only
                 *smem_out = bytes;
                 return true;
             }
@@ -148,7 +184,7 @@ int launch_mma_pw(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& 
     // tables small enough for two resident CTAs: run them with 256 threads each so that one CTA's
     // recurrence / tail overlaps the other's contraction
     if (smem <= 110 * 1024) threads = 256;
-    if (const char* env = getenv("FIATB200_MMA_THREADS")) threads = atoi(env) >= 512 ? 512 : 256;   // tuning override
+    if (fb_tuning().mma_threads >= 0) threads = fb_tuning().mma_threads >= 512 ? 512 : 256;
     k_mma<SD, ORDER, PW><<<grid, threads, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
     fb_launches++;
     FB_CUDA(cudaGetLastError());
@@ -258,7 +294,7 @@ int tabulate_tensor(const fiatb200_plan* plan, const double* pts, long long npts
                     long long ostride, const DevRowMap& M, cudaStream_t st) {
     const DevTensor& Q = plan->tensor;
     int bp = 64;            // measured: 64-thread blocks write the many-row tables ~4 % faster than 128
-    if (const char* env = getenv("FIATB200_TENSOR_BP")) bp = std::max(32, atoi(env)) & ~31;   // tuning override
+    if (fb_tuning().tensor_bp >= 0) bp = std::max(32, fb_tuning().tensor_bp) & ~31;
     while (bp > 32 && (size_t)Q.total_doubles * bp * sizeof(double) > 96 * 1024) bp >>= 1;
     const size_t smem = (size_t)Q.total_doubles * bp * sizeof(double);
     if (smem > (size_t)plan->max_smem_optin)
@@ -668,7 +704,7 @@ int fiatb200_evaluate_tensor(const fiatb200_plan* plan, const double* coef_dev, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // (measured: 128-point blocks 8.7 ms, 64-point blocks 9.2 ms per 2^22 points on the GLL Q10 hexahedron)
     int bp = 128;
-    if (const char* env = getenv("FIATB200_EVAL_BP")) bp = std::max(32, atoi(env)) & ~31;     // tuning override
+    if (fb_tuning().eval_bp >= 0) bp = std::max(32, fb_tuning().eval_bp) & ~31;
     while (bp > 32 && (size_t)Q.total_doubles * bp * sizeof(double) > 96 * 1024) bp >>= 1;
     const size_t smem = (size_t)Q.total_doubles * bp * sizeof(double);
     if (smem > (size_t)plan->max_smem_optin)
@@ -676,7 +712,7 @@ int fiatb200_evaluate_tensor(const fiatb200_plan* plan, const double* coef_dev, 
     const unsigned grid = (unsigned)((npts + bp - 1) / bp);
     int rc = FIATB200_OK;
     // three scalar line factors of moderate size (quadrilateral x interval = hexahedron): sum-factorised kernel
-    bool hex = Q.nleaf == 3 && Q.order <= 2 && !getenv("FIATB200_EVAL_GENERIC");
+    bool hex = Q.nleaf == 3 && Q.order <= 2 && fb_tuning().eval_generic < 0;
     for (int l = 0; l < Q.nleaf && hex; ++l)
         hex = Q.leaf[l].prog.sd == 1 && Q.leaf[l].ncomp == 1 && Q.leaf[l].ndof <= FB_EVAL_NMAX;
     if (hex) {
@@ -773,14 +809,20 @@ int host_pipeline(fiatb200_plan* owner, int64_t rows, const double* pts_host, in
         const int b = it & 1;
         cudaStream_t st = owner->host_stream[b];
         const int64_t n = std::min<int64_t>(chunk_pts, npts - done);
+        // (errors leave the loop but never the function: copies already queued into the caller's buffers must
+        // have drained before we return)
+        cudaError_t e = cudaSuccess;
         if (pts_ld > 0)
-            FB_CUDA(cudaMemcpyAsync(owner->host_pts[b], pts_host + done * pts_ld, sizeof(double) * n * pts_ld,
-                                    cudaMemcpyHostToDevice, st));
-        rc = run(owner->host_pts[b], n, owner->host_out[b], chunk_pts, st);
-        if (rc) break;
-        // rows of the chunk land at column offset `done` of the (rows x npts) host result
-        FB_CUDA(cudaMemcpy2DAsync(out_host + done, sizeof(double) * npts, owner->host_out[b], sizeof(double) * chunk_pts,
-                                  sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st));
+            e = cudaMemcpyAsync(owner->host_pts[b], pts_host + done * pts_ld, sizeof(double) * n * pts_ld,
+                                cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            rc = run(owner->host_pts[b], n, owner->host_out[b], chunk_pts, st);
+            if (rc) break;
+            // rows of the chunk land at column offset `done` of the (rows x npts) host result
+            e = cudaMemcpy2DAsync(out_host + done, sizeof(double) * npts, owner->host_out[b], sizeof(double) * chunk_pts,
+                                  sizeof(double) * n, rows, cudaMemcpyDeviceToHost, st);
+        }
+        if (e != cudaSuccess) rc = fb_fail(FIATB200_ERR_CUDA, std::string("host pipeline copy: ") + cudaGetErrorString(e));
     }
     for (int i = 0; i < 2; ++i) {
         cudaError_t e = cudaStreamSynchronize(owner->host_stream[i]);

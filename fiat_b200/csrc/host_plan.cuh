@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -23,6 +24,13 @@ extern std::atomic<long long> fb_launches;
         if (e_ != cudaSuccess)                                                              \
             return fb_fail(FIATB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+
+// Tuning overrides for experiments, read from the environment ONCE, the first time a launch
+// asks for them; -1 = not set.  Nothing on the per-launch path calls getenv.
+struct FbTuning {
+    int mma_pt, mma_skip, mma_threads, tensor_bp, eval_bp, eval_generic, vals_tpc, vals_j, stage;
+};
+const FbTuning& fb_tuning();
 
 enum PlanKind { PLAN_SIMPLEX = 1, PLAN_TENSOR = 2, PLAN_LATTICE = 3 };
 
@@ -46,11 +54,14 @@ struct fiatb200_plan {
     size_t host_pts_cap, host_out_cap;
 };
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is a per-kernel maximum: it is only ever
+// raised, under a lock, so that host threads launching the same kernel with different sizes cannot lower it
+// under each other.
+int fb_raise_smem_limit(const void* kernel, size_t bytes);
 template <typename K>
 int fb_set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024)
-        FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return FIATB200_OK;
+    if (bytes <= 48 * 1024) return FIATB200_OK;
+    return fb_raise_smem_limit(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 // launchers that live in their own translation units (compiled in parallel)

@@ -55,6 +55,10 @@ k_cellwise(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEnti
     double x[3];
     apply_entity<SD>(E, pts + p * ldp, x);
     unsigned mask = locate_cells<SD>(P.bary, P.ncells, P.unique, x);
+    if (mask == 0) {            // in no subcell: zero column, like the reference
+        fb_zero_column(M, out, ostride, p, na, P.nrows);
+        return;
+    }
     const double inv_mult = 1.0 / (double)__popc(mask);
     bool first = true;
     while (mask) {
@@ -359,6 +363,10 @@ __device__ __forceinline__ void leaf_table(const DevTensorLeaf& L, const double*
     apply_entity<SD>(L.ent, pt + L.point_offset, x);
     const int na = P.na;
     unsigned mask = locate_cells<SD>(P.bary, P.ncells, P.unique, x);
+    if (mask == 0) {            // in no subcell of a split factor: that factor's table is zero
+        for (int i = 0; i < na * P.nrows; ++i) table[(size_t)i * BP] = 0.0;
+        return;
+    }
     const double inv_mult = 1.0 / (double)__popc(mask);
     bool first = true;
     while (mask) {

@@ -78,6 +78,10 @@ k_small(const DevSimplex P, const __grid_constant__ SmallTab st, const DevEntity
     double x[3];
     apply_entity<SD>(E, pts + p * ldp, x);
     unsigned mask = locate_cells<SD>(st.bary, P.ncells, P.unique, x);
+    if (mask == 0) {            // in no subcell: zero column, like the reference
+        fb_zero_column(M, out, ostride, p, NA, P.nrows);
+        return;
+    }
     const double inv_mult = 1.0 / (double)__popc(mask);
     bool first = true;
     while (mask) {

@@ -173,6 +173,10 @@ k_vals(const DevSimplex P, const __grid_constant__ SmallTab st, const DevEntity 
         double x[3];
         apply_entity<SD>(E, pts + p * ldp, x);
         unsigned mask = NCP == 1 ? 1u : locate_cells<SD>(st.bary, P.ncells, P.unique, x);
+        if (mask == 0) {        // in no subcell: zero column, like the reference
+            fb_zero_column(M, out, ostride, p, P.na, P.nrows);
+            continue;
+        }
         const double inv_mult = 1.0 / (double)__popc(mask);
         int cell = NCP == 1 ? 0 : __ffs(mask) - 1;
         mask &= mask - 1;

@@ -22,7 +22,7 @@ int launch_vals_id(const fiatb200_plan* plan, const DevEntity& E, const double* 
     const int bp = 128;
     // a CTA stages the coefficient table once and then walks `tpc` consecutive point tiles
     int tpc = smem > 16 * 1024 ? 4 : (smem > 4 * 1024 ? 2 : 1);
-    if (const char* env = getenv("FIATB200_VALS_TPC")) tpc = std::max(1, atoi(env));   // tuning override
+    if (fb_tuning().vals_tpc >= 0) tpc = std::max(1, fb_tuning().vals_tpc);
     const long long per_cta = (long long)bp * tpc;
     const unsigned grid = (unsigned)((npts + per_cta - 1) / per_cta);
     k_vals<SD, N, NCP, J, IDENT><<<grid, bp, smem, st>>>(P, plan->small_tab, E, pts, npts, ldp, tpc, out, ostride, M);
@@ -37,7 +37,7 @@ int launch_vals_id(const fiatb200_plan* plan, const DevEntity& E, const double* 
 // and is kept unless its loads alone would take more than 70 % of that time (measured on B200:
 // PS6/PS12 order 2 run faster with J = 0, HCT / Arnold-Winther / BDM with J = 1).
 int vals_jet_order(const DevSimplex& P) {
-    if (const char* env = getenv("FIATB200_VALS_J")) return std::min(P.order, atoi(env) > 0 ? 1 : 0);   // tuning override
+    if (fb_tuning().vals_j >= 0) return std::min(P.order, fb_tuning().vals_j > 0 ? 1 : 0);
     if (P.order < 1) return 0;
     const int sd = P.sd, n = P.degree;
     double loads = 0.0;

@@ -275,6 +275,8 @@ def _describe_enriched(element):
     """EnrichedElement: child tables stacked along the dof axis (FIAT/enriched.py:88-113)."""
     vs = tuple(int(v) for v in element.value_shape())
     nc = _ncomp(vs)
+    if len(vs) > 1:
+        vs = (nc,)          # the reference's table is (ndofs, prod(value_shape), npts) (enriched.py:93-94)
     parts, off = [], 0
     for sub in element.elements():
         parts.append({"element": describe_element(sub), "dof_offset": off,

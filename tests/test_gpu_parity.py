@@ -386,3 +386,50 @@ def test_nodality_at_lattice_nodes(name, cuda_device):
     for flags, tol in ((0, 1e-13), (FORCE_GENERAL, 1e-10)):
         vals = tab.tabulate(0, nodes, flags=flags)[(0,) * sd]
         assert (vals - eye).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("name", ["hct_o2", "hct_o0", "ps12_o2", "ps12_o0", "ps6_o2", "p2_alfeld_tet_o2", "gn_tet_o2",
+                                  "walkington_tet_o2", "hct4_tri_o2"])
+def test_points_in_no_subcell_give_zero_columns(name, cuda_device):
+    """NaN / Inf coordinates make every l1 distance NaN, so the point is binned to no subcell and the reference
+    leaves its column of the zero-initialised tables untouched (FIAT/expansions.py:479-489).  Every kernel that
+    locates subcells must write zeros there (never stale memory), at the fixture's order and at order 0."""
+    from fiat_b200.api import Tabulator, FORCE_GENERAL, FORCE_THREAD_PER_POINT, NO_VALUE_TABLE, NO_MACRO_MERGED
+    case = load_case(name)
+    desc = case["desc"]
+    sd = int(desc["sd"])
+    pts = numpy.array(case["points"], dtype=float)[:40].copy()
+    bad = [1, 5, 17, 18, 33]
+    pts[1, 0] = numpy.nan
+    pts[5, sd - 1] = numpy.inf
+    pts[17, 0] = -numpy.inf
+    pts[18, :] = numpy.nan
+    pts[33, 1] = numpy.nan
+    tab = Tabulator(desc, cuda_device)
+    with numpy.errstate(all="ignore"):
+        want = fiat_oracle.tabulate(desc, case["order"], pts)
+    assert all(not v[..., bad].any() for v in want.values())
+    for flags in (0, FORCE_GENERAL, FORCE_GENERAL | NO_VALUE_TABLE, FORCE_THREAD_PER_POINT, NO_MACRO_MERGED):
+        out = torch.full((len(want), int(numpy.prod(next(iter(want.values())).shape[:-1])), len(pts)), 7.0,
+                         dtype=torch.float64, device=cuda_device)
+        tab.tabulate_into(out, case["order"], torch.as_tensor(pts, device=cuda_device), flags=flags)
+        got = {a: out[j].reshape(want[a].shape) for j, a in enumerate(want)}
+        _compare(desc, got, want)
+        assert int(tab.locate_subcells(pts, unique=False)[bad].abs().sum().item()) == 0
+
+
+def test_host_buffer_out_is_validated(cuda_device):
+    """tabulate_host(out=...) hands the raw pointer to the library: dtype, shape, contiguity and writeability
+    are checked first (a float32 / transposed / short buffer would be overrun)."""
+    from fiat_b200.api import Tabulator
+    case = load_case("p3_tri_o1")
+    tab = Tabulator(case["desc"], cuda_device)
+    pts = numpy.asarray(case["points"], dtype=float)[:32]
+    good = numpy.empty((3, 10, 32))
+    _compare(case["desc"], tab.tabulate_host(1, pts, out=good), {a: v[:, :32] for a, v in case["ref"].items()})
+    readonly = numpy.empty((3, 10, 32))
+    readonly.flags.writeable = False
+    for bad in (numpy.empty((3, 10, 32), dtype=numpy.float32), numpy.empty((3, 10, 31)), numpy.empty((32, 10, 3)).T,
+                numpy.empty((3, 10, 64))[:, :, ::2], readonly, [[0.0]]):
+        with pytest.raises(ValueError):
+            tab.tabulate_host(1, pts, out=bad)
