@@ -70,6 +70,7 @@ EXPORTS = [
     "fiatb200_version", "fiatb200_last_error", "fiatb200_simplex_plan_create", "fiatb200_tensor_plan_create",
     "fiatb200_lattice_plan_create", "fiatb200_plan_destroy", "fiatb200_plan_shape", "fiatb200_plan_kernel", "fiatb200_tabulate", "fiatb200_tabulate_mapped", "fiatb200_zero_rows", "fiatb200_locate_subcells",
     "fiatb200_tabulate_host", "fiatb200_tabulate_host_list", "fiatb200_evaluate_tensor", "fiatb200_launch_count",
+    "fiatb200_cluster_rows", "fiatb200_colour_members",
 ]
 
 
@@ -103,6 +104,9 @@ def load():
     lib.fiatb200_evaluate_tensor.argtypes = [p_void, p_void, c_i32, p_void, c_i64, c_i64, p_void, c_i64, p_void]
     lib.fiatb200_tabulate_host_list.argtypes = [ctypes.POINTER(LaunchStruct), c_i32, c_i32, c_i64, p_void, c_i32, p_void,
                                                 c_i64, c_i64, p_void, c_i64, c_u32]
+    p_u8 = ctypes.POINTER(ctypes.c_uint8)
+    lib.fiatb200_cluster_rows.argtypes = [p_u8, c_i32, c_i32, c_i32, c_i32, p_i32, c_i64, ctypes.c_uint64, p_i32]
+    lib.fiatb200_colour_members.argtypes = [p_u8, c_i32, c_i32, c_i32, p_i32, c_i64, ctypes.c_uint64, p_i32, p_i32]
     _lib = lib
     return lib
 
@@ -146,7 +150,7 @@ def simplex_struct(prog):
     s.line_tab, s.line_tab_len = f64(prog.line_tab), int(numpy.size(prog.line_tab))
     s.blk_cells = int(prog.blk_cells)
     s.nrb = len(prog.blk_ptr) // prog.blk_cells - 1 if prog.blk_cells > 1 else len(prog.blk_ptr) - 1
-    s.kpad, s.nblk = prog.kpad, len(prog.blk_kb)
+    s.kpad, s.nblk = prog.kpad, len(prog.blk_kb) // 4
     s.blk_ptr, s.blk_kb, s.blk_frag, s.rb_order = i32(prog.blk_ptr), i32(prog.blk_kb), f64(prog.blk_frag), i32(prog.rb_order)
     s.row_perm = i32(prog.row_perm if len(prog.row_perm) else numpy.arange(prog.nrows))
     s.cderiv, s.cderiv_len, s.ncp = f64(prog.cderiv), int(numpy.size(prog.cderiv)), int(prog.ncp)

@@ -10,8 +10,9 @@ deps_fiat_b200="fiat_b200.cu host_plan.cuh device_plan.cuh expansion.cuh kernels
 deps_small_launch="small_launch.cu host_plan.cuh device_plan.cuh expansion.cuh small.cuh ../../include/fiat_b200.h"
 deps_cells_launch="cells_launch.cu host_plan.cuh device_plan.cuh expansion.cuh cells.cuh ../../include/fiat_b200.h"
 deps_vals_launch="vals_launch.cu host_plan.cuh device_plan.cuh expansion.cuh small.cuh vals.cuh ../../include/fiat_b200.h"
+deps_cluster="cluster.cu ../../include/fiat_b200.h"
 pids=""
-for tu in fiat_b200 small_launch vals_launch cells_launch; do
+for tu in fiat_b200 small_launch vals_launch cells_launch cluster; do
     eval deps=\$deps_$tu
     stale=0
     [ -n "$FORCE" ] || [ -n "$*" ] || [ ! -f _obj/$tu.o ] && stale=1
@@ -22,4 +23,4 @@ for tu in fiat_b200 small_launch vals_launch cells_launch; do
     fi
 done
 for pid in $pids; do wait $pid; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libfiat_b200.so _obj/fiat_b200.o _obj/small_launch.o _obj/vals_launch.o _obj/cells_launch.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libfiat_b200.so _obj/fiat_b200.o _obj/small_launch.o _obj/vals_launch.o _obj/cells_launch.o _obj/cluster.o

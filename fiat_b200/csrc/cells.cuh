@@ -33,22 +33,23 @@ struct CellsGeom {
 // numbers are fetched two blocks ahead; the loop stays rolled (code size).
 template <int NOCT>
 __device__ __forceinline__ void cells_segment(const double* __restrict__ fp, const int* __restrict__ kp, int nq,
-                                              const double* __restrict__ Tchunk, size_t kb_stride,
+                                              const double* __restrict__ Tchunk, size_t ldT,
                                               const int* __restrict__ perm, double* __restrict__ srow) {
     double acc[NOCT][2];
 #pragma unroll
     for (int o = 0; o < NOCT; ++o) acc[o][0] = acc[o][1] = 0.0;
+    // kp points at this lane's member slot of the first block (slot t of block i at kp[4 i]): gather packing
     double a0 = __ldg(fp), a1 = nq > 1 ? __ldg(fp + 32) : 0.0;
-    int m0 = __ldg(kp), m1 = nq > 1 ? __ldg(kp + 1) : 0;
+    int m0 = __ldg(kp), m1 = nq > 1 ? __ldg(kp + 4) : 0;
 #pragma unroll 1
     for (int i = 0; i < nq; ++i) {
         const double a = a0;
-        const double* Tb = Tchunk + (m0 & 0xffff) * kb_stride;
+        const double* Tb = Tchunk + m0 * ldT;
         a0 = a1;
         m0 = m1;
         if (i + 2 < nq) {
             a1 = __ldg(fp + (size_t)(i + 2) * 32);
-            m1 = __ldg(kp + i + 2);
+            m1 = __ldg(kp + 4 * (i + 2));
         }
 #pragma unroll
         for (int o = 0; o < NOCT; ++o) dmma_8x8x4(acc[o][0], acc[o][1], a, Tb[o * 8]);
@@ -178,8 +179,7 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     const int g = lane >> 2, t = lane & 3;
     const int nrb = tab.nrb;
     const int nchunk = s_nchunk;
-    const double* Tlane = T + (size_t)t * ldT + g;
-    const size_t kb_stride = (size_t)4 * ldT;
+    const double* Tlane = T + g;                                     // + member slot * ldT, gathered per block
     double* stage = s_stage + (size_t)warp * 8 * SP;                 // 8 rows x PT points (+ 2 padding)
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0) && base + PT <= npts;
     for (;;) {
@@ -200,14 +200,14 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
             // one specialisation per number of octets: exactly noct DMMAs per block (an `if (o < noct)` in an unrolled
             // loop becomes predicated DMMAs that still occupy the tensor pipe) and no dispatch inside the block loop
             switch (noct) {
-                case 1: cells_segment<1>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
-                case 2: cells_segment<2>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
-                case 3: cells_segment<3>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
-                case 4: cells_segment<4>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
-                case 5: cells_segment<5>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
-                case 6: cells_segment<6>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
-                case 7: cells_segment<7>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
-                default: cells_segment<8>(fp, P.blk_kb + q0, q1 - q0, Tchunk, kb_stride, perm, srow); break;
+                case 1: cells_segment<1>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+                case 2: cells_segment<2>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+                case 3: cells_segment<3>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+                case 4: cells_segment<4>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+                case 5: cells_segment<5>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+                case 6: cells_segment<6>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+                case 7: cells_segment<7>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+                default: cells_segment<8>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
             }
         }
         __syncwarp();

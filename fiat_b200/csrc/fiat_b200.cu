@@ -455,7 +455,7 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     const int blk_cells = h->blk_cells > 1 ? h->blk_cells : 1;
     if (blk_cells > 1 && blk_cells != h->ncells) { delete plan; return fb_fail(FIATB200_ERR_ARG, "per-subcell block tables do not match the complex"); }
     const size_t o_blk_ptr = A.add(h->blk_ptr, sizeof(int32_t) * (size_t)blk_cells * (h->nrb + 1));
-    const size_t o_blk_kb = A.add(h->blk_kb, sizeof(int32_t) * h->nblk);
+    const size_t o_blk_kb = A.add(h->blk_kb, sizeof(int32_t) * 4 * (size_t)h->nblk);      // four member slots per block
     const size_t o_blk_frag = A.add(h->blk_frag, sizeof(double) * 32 * (size_t)h->nblk);
     const size_t o_rb_order = A.add(h->rb_order, sizeof(int32_t) * h->nrb);
     const bool has_cderiv = h->ncp > 0 && h->cderiv && h->cderiv_len > 0;

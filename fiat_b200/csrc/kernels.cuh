@@ -231,7 +231,9 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
 
     // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe (the C0 fix-ups
     // are folded into C).  Work item = (8-row block, GO point octets): one coefficient fragment feeds
-    // GO * NA DMMAs.  Fragments are fetched CH blocks ahead so that their L2 latency hides behind
+    // GO * NA DMMAs.  A block multiplies ANY four member slots (gather packing, plan.py: pack_blocks): the B
+    // fragment is read from the four matching rows of T, so a row block only pays for the members its rows
+    // use.  Fragments are fetched CH blocks ahead so that their L2 latency hides behind
     // the DMMAs of the current chunk; row-block tables come from the constant bank.
     constexpr int CH = 8;
     constexpr int GO = NA >= 8 ? 1 : (NA >= 5 ? 2 : (NA >= 3 ? 4 : (NA == 2 ? 8 : 16)));     // ~16 DMMAs per fragment
@@ -241,8 +243,8 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     const int nitems = (G.skip & 2) ? 0 : tab.nrb * ngrp;
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0);
     const size_t astride = (size_t)M.total_rows * ostride;      // distance between derivative tables
-    const double* Tlane = T + (size_t)t * G.ldT + g;
-    const size_t kb_stride = (size_t)4 * G.ldT;
+    const double* Tlane = T + g;                        // + member slot * ldT, gathered per block
+    const int ldT = G.ldT;
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&s_next, 1);
@@ -257,10 +259,11 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             for (int s = 0; s < NA; ++s) acc[o][s][0] = acc[o][s][1] = 0.0;
         const int q0 = tab.blk_ptr[rb], q1 = tab.blk_ptr[rb + 1];
         double a_cur[CH], a_nxt[CH];
+        // member slots of the CH blocks of a chunk: lane 4 j + t holds slot t of block j (one coalesced load)
         int kb_cur = 0, kb_nxt = 0;
 #pragma unroll
         for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
-        if (lane < CH && q0 + lane < q1) kb_cur = __ldg(P.blk_kb + q0 + lane);
+        if (4 * q0 + lane < 4 * q1) kb_cur = __ldg(P.blk_kb + 4 * q0 + lane);
         // octet o of the tile lives in point group o / (PW/8), at column offset (o % (PW/8)) * 8
         constexpr int OPG = PW / 8;                         // octets per point group
         const double* Titem = Tlane + (oct0 / OPG) * (PW * NA) + (oct0 % OPG) * 8;
@@ -269,14 +272,15 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
 #pragma unroll
                 for (int j = 0; j < CH; ++j)
                     a_nxt[j] = (q + CH + j < q1) ? __ldg(P.blk_frag + (size_t)(q + CH + j) * 32 + lane) : 0.0;
-                kb_nxt = (lane < CH && q + CH + lane < q1) ? __ldg(P.blk_kb + q + CH + lane) : 0;
+                kb_nxt = (4 * (q + CH) + lane < 4 * q1) ? __ldg(P.blk_kb + 4 * (q + CH) + lane) : 0;
             }
             const int nj = min(CH, q1 - q);
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
                 if (j < nj) {
-                    const int kb = __shfl_sync(0xffffffffu, kb_cur, j);
-                    const double* Tb = Titem + kb * kb_stride;
+                    // B fragment: lane (g, t) reads member slot blk_kb[4 (q + j) + t] at point g of every octet
+                    const int slot = __shfl_sync(0xffffffffu, kb_cur, 4 * j + t);
+                    const double* Tb = Titem + (size_t)slot * ldT;
                     double bfrag[GO * NA];
 #pragma unroll
                     for (int s = 0; s < GO * NA; ++s) {

@@ -219,9 +219,9 @@ class SimplexProgram:
     mul2: numpy.ndarray
     line_tab: numpy.ndarray     # expansion-specific 1-D tables (see _line_tables)
     line_n: int = 0
-    # block-sparse packing of ccell[0] (single-cell elements only)
+    # block-sparse gather packing of the fix-up-folded coefficient matrix (tile kernels)
     blk_ptr: numpy.ndarray = field(default_factory=lambda: numpy.zeros(1, numpy.int32))
-    blk_kb: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))
+    blk_kb: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))      # (nblk, 4) member slots, flat
     blk_frag: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0))
     rb_order: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))
     row_perm: numpy.ndarray = field(default_factory=lambda: numpy.zeros(0, numpy.int32))   # packed row -> table row
@@ -349,70 +349,115 @@ def _line_tables(desc, order):
     return dict(nslots=nn, geom=geom, line_tab=tab, line_n=nn)
 
 
-def _greedy_groups(support, group):
-    """Order the rows of a boolean (items x features) matrix so that each run of `group` consecutive
-    items has a small feature union: start from the widest remaining item, keep adding the item
-    that enlarges the union least (ties: largest overlap)."""
-    left = list(range(support.shape[0]))
-    sizes = support.sum(axis=1).tolist()
-    order = []
-    while left:
-        seed = max(left, key=sizes.__getitem__)
-        left.remove(seed)
-        grp, sup = [seed], support[seed].copy()
-        while len(grp) < group and left:
-            sub = support[left]
-            grow = (sub & ~sup).sum(axis=1)
-            share = (sub & sup).sum(axis=1)
-            r = left.pop(int(numpy.lexsort((-share, grow))[0]))
-            grp.append(r)
-            sup |= support[r]
-        order.extend(grp)
-    return numpy.array(order, dtype=numpy.int64)
+def _support(C, tol, nseg=1):
+    return numpy.ascontiguousarray(numpy.abs(C) > tol, dtype=numpy.uint8)
 
 
-def cluster_rows(C, drop_tol=0.0):
-    """Row order such that each group of 8 consecutive rows touches few 4-wide column blocks
-    (fewer stored 8x4 blocks = fewer DMMAs in the tile kernel)."""
-    nrows, K = C.shape
-    nkb = -(-K // 4)
-    z = numpy.zeros((nrows, nkb * 4), dtype=bool)
-    z[:, :K] = numpy.abs(C) > drop_tol
-    return _greedy_groups(z.reshape(nrows, nkb, 4).any(axis=2), 8)
+def cluster_rows(C, drop_tol=0.0, nseg=1, iters=None, seed=1):
+    """Row order such that each run of 8 consecutive rows touches few expansion members (per column segment):
+    the 8x4 blocks of the tile kernels gather any four members, so a row group costs ceil(|union| / 4) blocks.
+    Greedy seed + swap local search, both in the library (csrc/cluster.cu).  -> (order, number of blocks)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    S = _support(C, drop_tol)
+    nrows, ncols = S.shape
+    order = numpy.zeros(nrows, dtype=numpy.int32)
+    blocks = ctypes.c_int32()
+    if iters is None:
+        iters = CLUSTER_ITERS if nrows > 8 else 0
+    _lib.check(lib.fiatb200_cluster_rows(S.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), nrows, ncols, nseg, 1,
+                                         order.ctypes.data_as(_lib.p_i32), int(iters), seed, ctypes.byref(blocks)))
+    return order.astype(numpy.int64), int(blocks.value)
 
 
-def cluster_cols(C, drop_tol=0.0):
-    """Column order such that each group of 4 consecutive columns touches few 8-row blocks."""
-    nrows, K = C.shape
+def colour_members(C, order, drop_tol=0.0, nseg=1, seed=1):
+    """colour[member] in 0..3: the member's slot number mod 4.  The four rows of the expansion table that one block
+    reads are shared-memory bank-conflict free iff their slots differ mod 4; the colours spread the members each row
+    group uses evenly.  -> (colours, members left in conflict)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    S = _support(C, drop_tol)
+    nrows, ncols = S.shape
+    colour = numpy.zeros(ncols // nseg, dtype=numpy.int32)
+    conflicts = ctypes.c_int32()
+    order32 = numpy.ascontiguousarray(order, dtype=numpy.int32)
+    _lib.check(lib.fiatb200_colour_members(S.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), nrows, ncols, nseg,
+                                           order32.ctypes.data_as(_lib.p_i32), 200000, seed,
+                                           colour.ctypes.data_as(_lib.p_i32), ctypes.byref(conflicts)))
+    return colour, int(conflicts.value)
+
+
+def slots_from_colours(colour):
+    """Slot permutation realising the colours: perm[new slot] = member (old slot), new slot % 4 == colour."""
+    K = len(colour)
+    perm = numpy.empty(K, dtype=numpy.int64)
+    nxt = [c for c in range(4)]
+    for m in range(K):
+        c = int(colour[m])
+        perm[nxt[c]] = m
+        nxt[c] += 4
+    assert sorted(perm.tolist()) == list(range(K))
+    return perm
+
+
+CLUSTER_ITERS = 100000      # swap rounds of the row clustering (P8 tet order 2, 1650 x 165: 0.4 s, 2826 -> 2406 blocks)
+
+
+def pack_blocks(C, drop_tol=0.0, nseg=1, min_one=False):
+    """8x4 block-sparse *gather* packing of a (nrows, nseg * K) matrix in mma.m8n8k4 A-fragment order.
+
+    Rows are taken 8 at a time in the given order (the caller clusters them); within a row block and a column
+    segment the members with a non-zero column are dealt into ceil(n / 4) blocks of four, position t of a block
+    preferring a member whose slot is t mod 4 (then the kernel's gather of the four table rows is bank-conflict
+    free); leftover positions hold coefficient zero on slot t.  Lane l of a warp holds
+    C[8 rb + l // 4, blk_idx[q, l % 4]].
+    Returns (blk_ptr (nseg, nrb + 1), blk_idx (nblk, 4), frags (nblk * 32), rb_order, Kpad); blk_ptr is flat for
+    nseg == 1.  min_one: every (segment, row block) gets at least one (possibly all-zero) block."""
+    nrows, ncols = C.shape
+    K = ncols // nseg
     nrb = -(-nrows // 8)
-    z = numpy.zeros((nrb * 8, K), dtype=bool)
-    z[:nrows] = numpy.abs(C) > drop_tol
-    return _greedy_groups(z.reshape(nrb, 8, K).any(axis=1).T, 4)
-
-
-def pack_blocks(C, drop_tol=0.0):
-    """8x4 block-sparse packing of a (nrows, K) matrix in mma.m8n8k4 A-fragment order.
-
-    Lane l of a warp holds C[8*rb + l//4, 4*kb + l%4].  Returns (blk_ptr, blk_kb, frags, rb_order, Kpad);
-    rb_order lists row blocks by decreasing number of stored blocks (longest first scheduling).
-    """
-    nrows, K = C.shape
-    nrb, nkb = -(-nrows // 8), -(-K // 4)
-    Cp = numpy.zeros((nrb * 8, nkb * 4))
-    Cp[:nrows, :K] = C
-    tiles = Cp.reshape(nrb, 8, nkb, 4).transpose(0, 2, 1, 3)        # (rb, kb, 8, 4)
-    keep = numpy.abs(tiles).max(axis=(2, 3)) > drop_tol
-    blk_ptr = numpy.zeros(nrb + 1, dtype=numpy.int32)
-    blk_kb, frags = [], []
-    for rb in range(nrb):
-        kbs = numpy.nonzero(keep[rb])[0]
-        blk_kb.extend(kbs.tolist())
-        frags.extend(tiles[rb, kb].reshape(32) for kb in kbs)
-        blk_ptr[rb + 1] = len(blk_kb)
-    counts = numpy.diff(blk_ptr)
+    Cp = numpy.zeros((nrb * 8, ncols))
+    Cp[:nrows] = C
+    used = (numpy.abs(Cp) > drop_tol).reshape(nrb, 8, nseg, K).any(axis=1)          # (nrb, nseg, K)
+    ptrs, idx, frags = numpy.zeros((nseg, nrb + 1), dtype=numpy.int64), [], []
+    total = 0
+    for sg in range(nseg):
+        ptrs[sg, 0] = total
+        for rb in range(nrb):
+            members = numpy.flatnonzero(used[rb, sg])
+            nb = -(-len(members) // 4)
+            if min_one:
+                nb = max(nb, 1)
+            if nb:
+                blk = -numpy.ones((nb, 4), dtype=numpy.int64)
+                extra = []
+                for c in range(4):
+                    mine = members[members % 4 == c]
+                    blk[:min(nb, len(mine)), c] = mine[:nb]
+                    extra.extend(mine[nb:].tolist())
+                holes = numpy.argwhere(blk < 0)
+                for (bq, bt), m in zip(holes, extra):
+                    blk[bq, bt] = m
+                tile = Cp[rb * 8:rb * 8 + 8, sg * K:(sg + 1) * K]
+                for bq in range(nb):
+                    fr = numpy.zeros((8, 4))
+                    for t in range(4):
+                        if blk[bq, t] >= 0:
+                            fr[:, t] = tile[:, blk[bq, t]]
+                        else:
+                            blk[bq, t] = t if t < K else 0
+                    idx.append(blk[bq])
+                    frags.append(fr.reshape(32))
+                total += nb
+            ptrs[sg, rb + 1] = total
+    counts = numpy.diff(ptrs, axis=1).sum(axis=0)
     rb_order = numpy.argsort(-counts, kind="stable").astype(numpy.int32)
     frags = numpy.array(frags, dtype=float).reshape(-1) if frags else numpy.zeros(0)
-    return blk_ptr, numpy.array(blk_kb, dtype=numpy.int32), frags, rb_order, nkb * 4
+    blk_idx = numpy.array(idx, dtype=numpy.int32).reshape(-1, 4)
+    blk_ptr = ptrs.astype(numpy.int32)
+    return (blk_ptr[0] if nseg == 1 else blk_ptr), blk_idx, frags, rb_order, -(-K // 4) * 4
 
 
 def _member_degree(m, sd):
@@ -576,15 +621,14 @@ def alpha_split(desc, order, prog=None):
     def stored_blocks(mat):
         if mat.size == 0:
             return 0
-        tol = 1e-14 * max(numpy.abs(mat).max(), 1e-300)
-        return len(pack_blocks(mat[cluster_rows(mat, tol)], tol)[1])
+        return cluster_rows(mat, 1e-14 * max(numpy.abs(mat).max(), 1e-300), iters=0)[1]      # greedy estimate
 
     # stacked into one launch (merged_split) the split also saves the jets of the recurrence, which is worth a few
     # more blocks; as separate launches it must store clearly fewer
     mergeable = len(alphas) * ndofs * ncomp <= MAX_MERGED_ROWS
     split_blocks = sum(stored_blocks(m[0]) for m in mats)
     limit = float(os.environ.get("FIATB200_SPLIT_RATIO", 1.3)) if mergeable else 0.9       # env: tuning override
-    if split_blocks > limit * len(prog.blk_kb) * len(alphas):
+    if split_blocks > limit * stored_blocks(prog.ccell_morton[0]) * len(alphas):
         return None
     out = []
     for alpha, per_cell in zip(alphas, mats):
@@ -614,27 +658,25 @@ def compile_simplex(desc, order):
 
     if desc["expansion"] == "dubiner":
         t = _dubiner_tables(desc, order)
-        if ncells == 1 and nrows * nexp_total >= 1024:
-            # Large single-cell elements go to the tile kernel, whose cost is the number of stored
-            # 8x4 coefficient blocks: renumber the member slots (a free choice) so that groups of 4
-            # slots are used by few row blocks, if that stores fewer blocks.
-            def folded_matrix(tabs):
-                base = C[:, cnm[0][tabs["pos_of_slot"]]] * tabs["fold_by_slot"][None, :]
-                out = base.copy()
-                for (tgt, src), w in zip(tabs["fix_idx"], tabs["fix_w"]):
-                    out[:, src] -= w * base[:, tgt]
-                return out
-
-            def stored_blocks(mat):
-                tol = 1e-14 * numpy.abs(mat).max()
-                return len(pack_blocks(mat[cluster_rows(mat, tol)], tol)[1])
-
-            f0 = folded_matrix(t)
-            tol0 = 1e-14 * numpy.abs(f0).max()
-            cols = cluster_cols(f0[cluster_rows(f0, tol0)], tol0)
-            t_alt = _dubiner_tables(desc, order, slot_perm=cols)
-            if stored_blocks(folded_matrix(t_alt)) < stored_blocks(f0):
-                t = t_alt
+        tile_cells = ncells > 1 and bool(desc.get("raw_members"))       # split-cell tile kernel (cells.cuh)
+        if (ncells == 1 or tile_cells) and nrows * nexp_total >= 1024:
+            # Large elements go to the tile kernels, whose 8x4 blocks gather any four member slots; the four rows of
+            # the expansion table a block reads are bank-conflict free iff the slots differ mod 4.  Slot numbers are
+            # a free choice: pick each member's slot mod 4 (its colour) so that the members every row group uses
+            # spread evenly over the colours.  (Split cells: one column segment per subcell, common slots.)
+            wide = []
+            for c in range(ncells):
+                base = C[:, cnm[c][t["pos_of_slot"]]] * t["fold_by_slot"][None, :]
+                f0 = base.copy()
+                for (tgt, src), w in zip(t["fix_idx"], t["fix_w"]):
+                    f0[:, src] -= w * base[:, tgt]
+                wide.append(f0)
+            wide = numpy.concatenate(wide, axis=1)
+            tol0 = 1e-14 * max(numpy.abs(wide).max(), 1e-300)
+            packed_rows = cluster_rows(wide, tol0, nseg=ncells)[0]
+            colour, _ = colour_members(wide, packed_rows, tol0, nseg=ncells)
+            t = _dubiner_tables(desc, order, slot_perm=slots_from_colours(colour))
+            t["packed_rows"] = packed_rows          # row supports do not depend on the slot numbering
         fold = t["fold_by_slot"]
         line_tab, line_n = numpy.zeros(0), 0
     else:
@@ -688,50 +730,25 @@ def compile_simplex(desc, order):
         if cder is not None:
             prog.cderiv, prog.ncp = cder, ncp
         prog.slot_of = numpy.asarray(t["slot_of"], dtype=numpy.int64)
-    if ncells > 1 and desc.get("raw_members") and desc["expansion"] == "dubiner":
-        # split-cell tile kernel (cells.cuh): one block-sparse matrix per subcell, common row order
-        scale = numpy.abs(ccell_morton).max() if ccell_morton.size else 0.0
-        tol = 1e-14 * scale
-        rows_order = cluster_rows(numpy.concatenate(list(ccell_morton), axis=1), tol)
-        # the kernel streams a subcell's blocks row block by row block: every row block gets at least one
-        # (possibly zero) block, and the last block of a row block is flagged in bit 16 of its column-block number;
-        # blk_ptr holds one (nrb + 1)-entry row per subcell
-        ptrs, kbs, frags, total, counts = [], [], [], 0, None
+    if desc["expansion"] == "dubiner" and (ncells == 1 or desc.get("raw_members")):
+        # Tile kernels (kernels.cuh: k_mma, cells.cuh: k_mma_cells) have no fix-up phase: T' = X T  =>  C T' = (C X) T.
+        # Split cells: one block stream per subcell (blk_ptr holds one (nrb + 1)-entry row per subcell, every row
+        # block has at least one, possibly zero, block), common row order and slots.
+        folded = []
         for c in range(ncells):
-            bp, bk, bf, _, kpad = pack_blocks(ccell_morton[c][rows_order], tol)
-            kb2, fr2, ptr2 = [], [], [0]
-            for rb in range(len(bp) - 1):
-                ks = [int(k) for k in bk[bp[rb]:bp[rb + 1]]] or [0]
-                fr2.append(bf[32 * bp[rb]:32 * bp[rb + 1]] if bp[rb + 1] > bp[rb] else numpy.zeros(32))
-                ks[-1] |= 1 << 16
-                kb2.extend(ks)
-                ptr2.append(len(kb2))
-            ptrs.append(numpy.array(ptr2, dtype=numpy.int64) + total)
-            kbs.append(numpy.array(kb2, dtype=numpy.int32))
-            frags.append(numpy.concatenate(fr2))
-            total += len(kb2)
-            counts = numpy.diff(ptr2) if counts is None else counts + numpy.diff(ptr2)
-        prog.blk_ptr = numpy.concatenate(ptrs).astype(numpy.int32)
-        prog.blk_kb = numpy.concatenate(kbs)
-        prog.blk_frag = numpy.concatenate(frags)
-        prog.rb_order = numpy.argsort(-counts, kind="stable").astype(numpy.int32)
-        prog.row_perm = rows_order.astype(numpy.int32)
-        prog.kpad, prog.blk_cells = kpad, ncells
-    if ncells == 1:
-        # the tile kernel has no fix-up phase: T' = X T  =>  C T' = (C X) T
-        folded = ccell[0].copy()
-        for (tgt, src), w in zip(prog.fix_idx, prog.fix_w):
-            folded[:, src] -= w * ccell[0][:, tgt]
-        scale = numpy.abs(folded).max() if folded.size else 0.0
-        # row blocks of the packed matrix are clusters of rows with similar column support
-        order = cluster_rows(folded, 1e-14 * scale)
-        natural = pack_blocks(folded, 1e-14 * scale)
-        clustered = pack_blocks(folded[order], 1e-14 * scale)
-        if len(clustered[1]) < len(natural[1]):
-            packed, prog.row_perm = clustered, order.astype(numpy.int32)
-        else:
-            packed, prog.row_perm = natural, numpy.arange(nrows, dtype=numpy.int32)
-        (prog.blk_ptr, prog.blk_kb, prog.blk_frag, prog.rb_order, prog.kpad) = packed
+            f = ccell[c].copy()
+            for (tgt, src), w in zip(prog.fix_idx, prog.fix_w):
+                f[:, src] -= w * ccell[c][:, tgt]
+            folded.append(f)
+        wide = numpy.concatenate(folded, axis=1)
+        tol = 1e-14 * (numpy.abs(wide).max() if wide.size else 0.0)
+        # row blocks of the packed matrix are clusters of rows with similar member support
+        rows_order = t["packed_rows"] if "packed_rows" in t else cluster_rows(wide, tol, nseg=ncells)[0]
+        bp, bi, prog.blk_frag, prog.rb_order, prog.kpad = pack_blocks(wide[rows_order], tol, nseg=ncells, min_one=ncells > 1)
+        prog.blk_ptr = numpy.ascontiguousarray(bp.reshape(-1), dtype=numpy.int32)
+        prog.blk_kb = numpy.ascontiguousarray(bi.reshape(-1), dtype=numpy.int32)
+        prog.row_perm = numpy.asarray(rows_order, dtype=numpy.int32)
+        prog.blk_cells = ncells if ncells > 1 else 0
     return prog
 
 

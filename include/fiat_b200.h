@@ -71,13 +71,18 @@ typedef struct {
     const double* mul2;        /* na x 6 */
     const double* line_tab;    /* expansion 1/2 tables */
     int64_t line_tab_len;
-    /* 8x4 block-sparse packing of ccell[0] in mma.m8n8k4 fragment order (ncells == 1 only) */
+    /* 8x4 block-sparse "gather" packing of the (fix-up-folded) coefficient matrix in mma.m8n8k4 fragment order
+     * (ncells == 1, or one stream per subcell when blk_cells > 1).  Row block rb = packed rows 8 rb .. 8 rb + 7;
+     * its blocks are blk_ptr[rb] .. blk_ptr[rb + 1] - 1.  Block q multiplies the four member slots
+     * blk_kb[4 q + t], t = 0..3 (ANY four slots: the kernel gathers the matching rows of the expansion table from
+     * shared memory; slots that differ mod 4 are bank-conflict free), and blk_frag[32 q + 4 g + t] is the
+     * coefficient of packed row 8 rb + g on member slot blk_kb[4 q + t]. */
     int32_t nrb, kpad, nblk;
     const int32_t* blk_ptr;    /* nrb + 1 */
-    const int32_t* blk_kb;     /* nblk */
+    const int32_t* blk_kb;     /* 4 x nblk member slots */
     const double* blk_frag;    /* nblk x 32 */
     const int32_t* rb_order;   /* nrb, longest row block first */
-    const int32_t* row_perm;   /* nrows: packed row i holds table row row_perm[i] (rows are clustered by column
+    const int32_t* row_perm;   /* nrows: packed row i holds table row row_perm[i] (rows are clustered by member
                                   support so that fewer blocks are stored) */
     /* Derivative-folded coefficients for the value-table kernel (optional, ncp == 0: absent).  D^alpha of an
      * expansion member of degree k lies in the span of the members of degree <= k - |alpha| (the fact behind
@@ -89,8 +94,8 @@ typedef struct {
     int32_t ncp;               /* subcell stride: ncells padded to 1, 4 or 16 */
     /* Split-cell tile kernel (order-0 derived elements of fiat_b200.plan.macro_merged): blk_cells == ncells > 1
      * means blk_ptr holds one (nrb + 1)-entry row per subcell (offsets into blk_kb / blk_frag; every row block has
-     * at least one, possibly zero, block), blk_kb[q] = column block | (last block of its row block) << 16, and all
-     * subcells share rb_order and row_perm; 0: single matrix as described above. */
+     * at least one, possibly zero, block), and all subcells share rb_order, row_perm and the member slots; 0: single
+     * matrix as described above. */
     int32_t blk_cells;
 } fiatb200_simplex_program;
 
@@ -216,6 +221,23 @@ typedef struct {
 int fiatb200_tabulate_host_list(const fiatb200_launch* launches, int32_t nlaunch, int32_t nalpha, int64_t total_rows,
                                 const int32_t* zero_rows_dev, int32_t nzero_rows, const double* pts_host,
                                 int64_t npts, int64_t pts_ld, double* out_host, int64_t chunk_pts, uint32_t flags);
+
+/* Plan-compilation helpers (host only; no device is touched).  They optimise the two free choices of the gather
+ * packing above for a boolean support matrix `support` (nrows x ncols, row-major, ncols = nseg segments of equal
+ * width: one segment per subcell, the same members in each):
+ *   fiatb200_cluster_rows    order[] (a permutation of the rows; with greedy_init != 0 it is built here, otherwise it
+ *                            is the starting point) such that every run of 8 rows has a small union of members, by
+ *                            `iters` rounds of best-swap local search between two random groups; *blocks_out =
+ *                            sum over groups and segments of ceil(union / 4) = number of 8x4 blocks.
+ *   fiatb200_colour_members  colour_out[member] in 0..3 = the member's slot number mod 4 (exactly as many members per
+ *                            colour as there are slots of that residue), chosen so that the members each group
+ *                            uses spread evenly over the colours; *conflicts_out = members that cannot be placed
+ *                            in a block of four distinct colours.
+ * They replace nothing in the reference (numpy.dot is dense, FIAT/polynomial_set.py:71). */
+int fiatb200_cluster_rows(const uint8_t* support, int32_t nrows, int32_t ncols, int32_t nseg, int32_t greedy_init,
+                          int32_t* order, int64_t iters, uint64_t seed, int32_t* blocks_out);
+int fiatb200_colour_members(const uint8_t* support, int32_t nrows, int32_t ncols, int32_t nseg, const int32_t* order,
+                            int64_t iters, uint64_t seed, int32_t* colour_out, int32_t* conflicts_out);
 
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t fiatb200_launch_count(void);

@@ -97,14 +97,19 @@ def run_value_table(prog, pts, near):
     return out
 
 
-def blocks_to_dense(prog):
-    """Rebuild the dense folded coefficient matrix from the 8x4 block packing."""
-    nrb = len(prog.blk_ptr) - 1
+def blocks_to_dense(prog, cell=0):
+    """Rebuild the dense folded coefficient matrix (table rows x member slots) of one subcell from the 8x4 gather
+    packing: block q holds the coefficients of 8 packed rows on the four member slots blk_kb[4 q .. 4 q + 3]."""
+    ncells = max(prog.blk_cells, 1)
+    nrb = len(prog.blk_ptr) // ncells - 1
+    ptr = prog.blk_ptr[cell * (nrb + 1):(cell + 1) * (nrb + 1)]
+    idx = numpy.asarray(prog.blk_kb).reshape(-1, 4)
     C = numpy.zeros((nrb * 8, prog.kpad))
     for rb in range(nrb):
-        for q in range(prog.blk_ptr[rb], prog.blk_ptr[rb + 1]):
-            kb = prog.blk_kb[q]
-            C[rb * 8:rb * 8 + 8, kb * 4:kb * 4 + 4] = prog.blk_frag[q * 32:(q + 1) * 32].reshape(8, 4)
+        for q in range(ptr[rb], ptr[rb + 1]):
+            frag = prog.blk_frag[q * 32:(q + 1) * 32].reshape(8, 4)
+            for t in range(4):
+                C[rb * 8:rb * 8 + 8, idx[q, t]] += frag[:, t]
     out = numpy.zeros((prog.nrows, prog.nslots))
     out[prog.row_perm] = C[:prog.nrows, :prog.nslots]          # packed row i is table row row_perm[i]
     return out

@@ -111,23 +111,16 @@ def test_macro_merged_reproduces_reference(name):
     for j, alpha in enumerate(alphas):
         ref = case["ref"][alpha].reshape(-1, len(pts))
         assert abs(out[j * nrows:(j + 1) * nrows] - ref).max() <= tolerance(desc, alpha) * max(abs(ref).max(), 1e-300), alpha
-    # block stream of every subcell: one (nrb + 1) pointer row per subcell, >= 1 block per row block, last-block flags
+    # block stream of every subcell: one (nrb + 1) pointer row per subcell, >= 1 block per row block
     nrb = len(prog.blk_ptr) // prog.ncells - 1
     assert len(prog.blk_ptr) == prog.ncells * (nrb + 1) and nrb == -(-prog.nrows // 8)
+    assert len(prog.blk_kb) == 4 * prog.blk_ptr[-1] and len(prog.blk_frag) == 32 * prog.blk_ptr[-1]
+    assert prog.blk_kb.min() >= 0 and prog.blk_kb.max() < prog.kpad
     for c in range(prog.ncells):
         ptr = prog.blk_ptr[c * (nrb + 1):(c + 1) * (nrb + 1)]
         assert (numpy.diff(ptr) >= 1).all()
-        dense = numpy.zeros((nrb * 8, prog.kpad))
-        for rb in range(nrb):
-            flags = prog.blk_kb[ptr[rb]:ptr[rb + 1]] >> 16
-            assert flags[-1] == 1 and not flags[:-1].any()
-            for q in range(ptr[rb], ptr[rb + 1]):
-                kb = prog.blk_kb[q] & 0xffff
-                dense[rb * 8:rb * 8 + 8, kb * 4:kb * 4 + 4] += prog.blk_frag[q * 32:(q + 1) * 32].reshape(8, 4)
-        full = numpy.zeros((nrb * 8, prog.kpad))
-        full[:prog.nrows, :prog.nslots] = prog.ccell_morton[c][prog.row_perm]
-        # dropped blocks hold nothing above 1e-14 of the largest coefficient (round-off of the folded matrices)
-        assert abs(dense - full).max() <= 1e-14 * abs(prog.ccell_morton).max()
+        # dropped entries hold nothing above 1e-14 of the largest coefficient (round-off of the folded matrices)
+        assert abs(emu.blocks_to_dense(prog, c) - prog.ccell[c]).max() <= 1e-14 * abs(prog.ccell).max()
 
 
 def test_mis_order_matches_reference_keys():
@@ -150,6 +143,11 @@ def test_block_packing_roundtrip(name):
     # dropped blocks hold nothing but Vandermonde round-off
     assert abs(dense - full).max() <= 1e-14 * abs(full).max()
     assert prog.kpad % 4 == 0 and len(prog.rb_order) == len(prog.blk_ptr) - 1
+    idx = prog.blk_kb.reshape(-1, 4)
+    assert len(idx) == prog.blk_ptr[-1] and idx.min() >= 0 and idx.max() < prog.kpad
+    # the gather of a block is bank-conflict free when its four slots differ mod 4: true for nearly all blocks
+    conflict_free = (numpy.sort(idx % 4, axis=1) == numpy.arange(4)).all(axis=1).mean()
+    assert conflict_free >= 0.9, conflict_free
 
 
 def test_tensor_flattening_hex():
