@@ -66,6 +66,79 @@ def adversarial_triangle_points(complex_):
     return numpy.array(pts)
 
 
+def _ulp_steps(x, k):
+    """x moved by k representable numbers (k may be negative), coordinate-wise."""
+    x = numpy.array(x, dtype=float)
+    for _ in range(abs(k)):
+        x = numpy.nextafter(x, numpy.inf if k > 0 else -numpy.inf)
+    return x
+
+
+OFFSETS = (1e-13, 1e-11, 1e-9, 3e-13, 5e-12)        # across a facet; the binning tolerance is 1e-12 (never ON it:
+ULPS = (1, 2, 8)                                    # there the reference's own BLAS rounding decides)
+
+
+def adversarial_points(complex_, rng, per_facet=4, n_random=0):
+    """Adversarial point set for split-cell location in any dimension (FIAT/expansions.py:771-811): every subcell
+    vertex, the barycentre of every edge / face / subcell, and for every interior facet its barycentre and
+    `per_facet` random points on it, each also moved by +-{1,2,8} ulp in every coordinate and by
+    +-{1e-13, 3e-13, 5e-12, 1e-11, 1e-9} along the facet normal; points near the facet's own boundary (where three
+    or more subcells meet); a ring of exterior points and points just outside every parent facet; uniform points."""
+    sd = complex_.get_spatial_dimension()
+    top = complex_.get_topology()
+    verts = numpy.array(complex_.get_vertices(), dtype=float)
+    pts = [v for v in verts]
+    for dim in range(1, sd + 1):
+        for ent in top[dim].values():
+            pts.append(verts[list(ent)].mean(axis=0))
+    centre = verts[:sd + 1].mean(axis=0)
+
+    def with_offsets(x, nrm):
+        out = [x]
+        for k in ULPS:
+            out += [_ulp_steps(x, k), _ulp_steps(x, -k)]
+        for eps in OFFSETS:
+            out += [x + eps * nrm, x - eps * nrm]
+        return out
+
+    def normal_of(fv):
+        # unit normal of the facet spanned by the sd vertices fv (rows)
+        edges = fv[1:] - fv[0]
+        _, _, vh = numpy.linalg.svd(edges)
+        return vh[-1]
+
+    for f in complex_.get_interior_facets(sd - 1):
+        fv = verts[list(top[sd - 1][f])]
+        nrm = normal_of(fv)
+        lams = [numpy.full(sd, 1.0 / sd)]
+        lams += list(rng.dirichlet(numpy.ones(sd), size=per_facet))
+        # near a vertex / an edge of the facet: several subcells meet there
+        e = numpy.zeros(sd)
+        e[0] = 1.0
+        lams += [(1 - 1e-9) * e + 1e-9 / sd, (1 - 1e-13) * e + 1e-13 / sd]
+        for lam in lams:
+            pts += with_offsets(lam @ fv, nrm)
+    # exterior: a ring / sphere around the cell and points just outside every facet of the parent
+    dirs = rng.standard_normal((12 * sd, sd))
+    dirs /= numpy.linalg.norm(dirs, axis=1, keepdims=True)
+    for r in (0.9, 2.5):
+        pts += list(centre + r * dirs)
+    parent = complex_.get_parent() or complex_
+    ptop = parent.get_topology()
+    pverts = numpy.array(parent.get_vertices(), dtype=float)
+    for ent in ptop[sd - 1].values():
+        fv = pverts[list(ent)]
+        nrm = normal_of(fv)
+        if numpy.dot(nrm, fv.mean(axis=0) - centre) < 0:
+            nrm = -nrm
+        for lam in [numpy.full(sd, 1.0 / sd)] + list(rng.dirichlet(numpy.ones(sd), size=2)):
+            x = lam @ fv
+            pts += [x + eps * nrm for eps in (1e-14, 1e-13, 1e-11, 1e-9, 1e-3, -1e-14)]
+    if n_random:
+        pts += list(simplex_points(rng, n_random, sd) @ (pverts[1:sd + 1] - pverts[0]) + pverts[0])
+    return numpy.array(pts)
+
+
 class CiarletElement:
     """Holder that presents a bare PolynomialSet through the element interface
     (used to pin expansion variants that no shipped element family exposes directly)."""
@@ -97,10 +170,14 @@ def membership(complex_, pts, unique):
 ONLY = None        # set by `--only name1,name2`: write just these cases (the rng stream is still consumed in order)
 
 
-def write_case(name, element, order, pts, entity=None, with_cells=False):
+def write_case(name, element, order, pts, entity=None, with_cells=False, table_stride=1):
+    """table_stride > 1: the reference tables are stored for pts[::table_stride] only (large adversarial sets);
+    the subcell membership matrices always cover all points (`mask_points`)."""
     if ONLY is not None and name not in ONLY:
         return
     desc = describe_element(element)
+    all_pts = numpy.asarray(pts, dtype=float)
+    pts = all_pts[::table_stride]
     ref = element.tabulate(order, pts, entity)
     case = {
         "name": name,
@@ -113,8 +190,13 @@ def write_case(name, element, order, pts, entity=None, with_cells=False):
     }
     if with_cells:
         complex_ = element.get_nodal_basis().get_expansion_set().ref_el
-        case["near_unique"] = membership(complex_, numpy.asarray(pts), True)
-        case["near_all"] = membership(complex_, numpy.asarray(pts), False)
+        mpts = all_pts
+        if entity is not None:      # binning sees the points on the cell (FIAT/finite_element.py:190-196)
+            mpts = element.get_reference_element().get_entity_transform(*entity)(all_pts)
+        case["near_unique"] = membership(complex_, mpts, True)
+        case["near_all"] = membership(complex_, mpts, False)
+        if table_stride > 1 or entity is not None:
+            case["mask_points"] = numpy.asarray(mpts, dtype=float)
     path = os.path.join(OUT, f"case_{name}.npz")
     description.save(path, case)
     print(f"{name:32s} {os.path.getsize(path) / 1024:8.1f} KiB  keys={len(ref)}  shape={next(iter(ref.values())).shape}")
@@ -270,11 +352,56 @@ def main():
     for nm, el, order, pts, ent in wrappers:
         write_case(nm, el, order, pts, entity=ent)
 
+    # ---- round 2: appended with their own generator so that every earlier file still reproduces bit for bit ----
+    rng2 = numpy.random.default_rng(20261019)
+    # (a) 3-D split complexes with an adversarial generator: Alfeld (4 subcells), Worsey-Farin (12), Powell-Sabin (24)
+    for nm, el, order in (("p2_alfeld_tet_adv", FIAT.Lagrange(T3, 2, variant="alfeld"), 2),
+                          ("p2_wf_tet_adv", FIAT.Lagrange(T3, 2, variant="worsey-farin"), 2),
+                          ("ch_wf_tet_adv", FIAT.ChristiansenHu(T3, 1), 1),
+                          ("alfeld_sorokina_tet_adv", FIAT.AlfeldSorokina(T3, 2), 2),
+                          ("p1_ps_tet_adv", FIAT.Lagrange(T3, 1, variant="powell-sabin"), 1),
+                          ("gn_tet_adv", FIAT.GuzmanNeilanFirstKindH1(T3, 1), 2),
+                          ("walkington_tet_adv", FIAT.Walkington(T3), 2)):
+        complex_ = el.get_nodal_basis().get_expansion_set().ref_el
+        pts = adversarial_points(complex_, rng2, per_facet=3, n_random=200)
+        stride = max(1, len(pts) // 160)
+        write_case(f"{nm}_o{order}", el, order, pts, with_cells=True, table_stride=stride)
+        write_case(f"{nm}_o0", el, 0, pts, with_cells=True, table_stride=stride)
+    # (b) >= 10^4 adversarial points in 2-D for the BASELINE macro elements
+    for nm, el in (("hct", FIAT.HsiehCloughTocher(T2)), ("ps6", FIAT.QuadraticPowellSabin6(T2)),
+                   ("ps12", FIAT.QuadraticPowellSabin12(T2))):
+        complex_ = el.get_nodal_basis().get_expansion_set().ref_el
+        nfac = len(complex_.get_interior_facets(1))
+        pts = adversarial_points(complex_, rng2, per_facet=-(-9000 // (17 * nfac)), n_random=1500)
+        assert len(pts) >= 10000, len(pts)
+        write_case(f"{nm}_adv10k_o2", el, 2, pts, with_cells=True, table_stride=16)
+        write_case(f"{nm}_adv10k_o0", el, 0, pts, with_cells=True, table_stride=16)
+    # (c) macro elements on a facet entity (points of a parent edge, incl. the split points of Powell-Sabin)
+    edge_pts = numpy.concatenate([rng2.random((21, 1)), [[0.0], [1.0], [0.5], [0.5 + 1e-13], [0.5 - 1e-11], [0.25], [1.0 / 3.0]]])
+    write_case("hct_edge2_o2", FIAT.HsiehCloughTocher(T2), 2, edge_pts, entity=(1, 2), with_cells=True)
+    write_case("ps12_edge0_o2", FIAT.QuadraticPowellSabin12(T2), 2, edge_pts, entity=(1, 0), with_cells=True)
+    write_case("ps6_edge1_o0", FIAT.QuadraticPowellSabin6(T2), 0, edge_pts, entity=(1, 1), with_cells=True)
+    face_pts = numpy.concatenate([simplex_points(rng2, 17, 2), [[1.0 / 3.0, 1.0 / 3.0], [0.5, 0.5], [0.0, 0.0], [0.25, 0.25]]])
+    write_case("p2_wf_tet_face1_o2", FIAT.Lagrange(T3, 2, variant="worsey-farin"), 2, face_pts, entity=(2, 1), with_cells=True)
+    # (d) the highest degrees the reference's own tests construct (test_gauss_lobatto_legendre.py:111-138,
+    # test_hct.py:79-82 go further on quadrature only)
+    write_case("p12_tri_o2", FIAT.Lagrange(T2, 12), 2, simplex_points(rng2, 14, 2))
+    write_case("p12_spectral_tri_o2", FIAT.Lagrange(T2, 12, variant="spectral"), 2, simplex_points(rng2, 14, 2))
+    write_case("p10_spectral_tet_o2", FIAT.Lagrange(T3, 10, variant="spectral"), 2, simplex_points(rng2, 10, 3))
+    write_case("p8_spectral_tet_o2", FIAT.Lagrange(T3, 8, variant="spectral"), 2, simplex_points(rng2, 14, 3))
+    write_case("gll16_line_o3", FIAT.GaussLobattoLegendre(T1, 16), 3,
+               numpy.concatenate([rng2.random((20, 1)), [[0.0], [1.0], [0.5]]]))
+    for deg in (5, 6):
+        el = FIAT.HsiehCloughTocher(T2, deg)
+        complex_ = el.get_nodal_basis().get_expansion_set().ref_el
+        pts = numpy.concatenate([simplex_points(rng2, 24, 2), adversarial_triangle_points(complex_)[:40]])
+        write_case(f"hct{deg}_tri_o2", el, 2, pts, with_cells=True)
+
     # element descriptions alone, for bench.py and full-size GPU tests
     for nm, el in () if ONLY is not None else (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),
                    ("hct", FIAT.HsiehCloughTocher(T2)), ("ps6", FIAT.QuadraticPowellSabin6(T2)),
                    ("ps12", FIAT.QuadraticPowellSabin12(T2)), ("gll_q10_hex", hexa),
-                   ("p3_tri", FIAT.Lagrange(T2, 3))):
+                   ("p3_tri", FIAT.Lagrange(T2, 3)), ("p8_spectral_tet", FIAT.Lagrange(T3, 8, variant="spectral"))):
         path = os.path.join(OUT, f"desc_{nm}.npz")
         description.save(path, describe_element(el))
         print(f"desc {nm:27s} {os.path.getsize(path) / 1024:8.1f} KiB")
