@@ -23,4 +23,6 @@ for tu in fiat_b200 small_launch vals_launch cells_launch cluster; do
     fi
 done
 for pid in $pids; do wait $pid; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libfiat_b200.so _obj/fiat_b200.o _obj/small_launch.o _obj/vals_launch.o _obj/cells_launch.o _obj/cluster.o
+# (linked under a temporary name and renamed: a snapshot taken meanwhile never sees a half-written library)
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o _obj/libfiat_b200.so.tmp _obj/fiat_b200.o _obj/small_launch.o _obj/vals_launch.o _obj/cells_launch.o _obj/cluster.o
+mv -f _obj/libfiat_b200.so.tmp libfiat_b200.so

@@ -40,15 +40,8 @@ def load_desc(name):
 
 def tolerance(desc, alpha):
     """north_star: 1e-12 * max|ref| per derivative component; 1e-10 for order >= 2 at degree >= 8."""
-    def degree(d):
-        if d["kind"] == "simplex":
-            return int(d["degree"])
-        if d["kind"] == "flattened":
-            return degree(d["element"])
-        if d["kind"] == "composite":
-            return max(degree(p["element"]) for p in d["parts"])
-        return max(degree(d["A"]), degree(d["B"]))
-    return 1e-10 if (sum(alpha) >= 2 and degree(desc) >= 8) else 1e-12
+    from oracle.tolerance import tolerance as tol
+    return tol(desc, alpha)
 
 
 @pytest.fixture(scope="session")
