@@ -70,7 +70,7 @@ EXPORTS = [
     "fiatb200_version", "fiatb200_last_error", "fiatb200_simplex_plan_create", "fiatb200_tensor_plan_create",
     "fiatb200_lattice_plan_create", "fiatb200_plan_destroy", "fiatb200_plan_shape", "fiatb200_plan_kernel", "fiatb200_tabulate", "fiatb200_tabulate_mapped", "fiatb200_zero_rows", "fiatb200_locate_subcells",
     "fiatb200_tabulate_host", "fiatb200_tabulate_host_list", "fiatb200_evaluate_tensor", "fiatb200_launch_count",
-    "fiatb200_cluster_rows", "fiatb200_colour_members",
+    "fiatb200_cluster_rows", "fiatb200_colour_members", "fiatb200_evaluate_simplex", "fiatb200_evaluate_host",
 ]
 
 
@@ -104,6 +104,10 @@ def load():
     lib.fiatb200_evaluate_tensor.argtypes = [p_void, p_void, c_i32, p_void, c_i64, c_i64, p_void, c_i64, p_void]
     lib.fiatb200_tabulate_host_list.argtypes = [ctypes.POINTER(LaunchStruct), c_i32, c_i32, c_i64, p_void, c_i32, p_void,
                                                 c_i64, c_i64, p_void, c_i64, c_u32]
+    lib.fiatb200_evaluate_simplex.argtypes = [p_void, c_i32, c_i32, p_void, c_i32, ctypes.POINTER(EntityMapStruct), p_void,
+                                              c_i64, c_i64, p_void, c_i64, p_void]
+    lib.fiatb200_evaluate_host.argtypes = [p_void, c_i32, c_i32, p_void, c_i32, ctypes.POINTER(EntityMapStruct), p_void,
+                                           c_i64, c_i64, p_void, c_i64]
     p_u8 = ctypes.POINTER(ctypes.c_uint8)
     lib.fiatb200_cluster_rows.argtypes = [p_u8, c_i32, c_i32, c_i32, c_i32, p_i32, c_i64, ctypes.c_uint64, p_i32]
     lib.fiatb200_colour_members.argtypes = [p_u8, c_i32, c_i32, c_i32, p_i32, c_i64, ctypes.c_uint64, p_i32, p_i32]

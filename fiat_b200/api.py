@@ -453,45 +453,169 @@ class Tabulator:
         at the points, without ever writing the (ndofs, npts) tables (point evaluation /
         interpolation).  Returns {alpha: tensor (nfunc, *value_shape, npts)}.
 
-        Because tabulation is linear in the coefficient tensor (FIAT/polynomial_set.py:71), this is the
-        tabulation of a derived element whose coefficient tensor is coefficients . coeffs; it runs
-        through the same kernels.  Scalar tensor-product elements take a kernel of their own that nests the sum over
-        the factors (`_evaluate_tensor`)."""
-        if self.kind in ("tensor", "flattened") and (self.kind == "tensor" or self.desc["element"]["kind"] == "tensor"):
-            return self._evaluate_tensor(coefficients, order, points, entity)
-        if self.kind != "simplex":
-            raise UnsupportedElement("evaluate() is available for Ciarlet elements on simplices and scalar "
-                                     "tensor-product elements")
-        u = numpy.atleast_2d(numpy.asarray(coefficients, dtype=numpy.float64))
-        coeffs = numpy.asarray(self.desc["coeffs"], dtype=numpy.float64)         # (ndofs, ncomp, nexp)
-        if u.shape[1] != coeffs.shape[0]:
-            raise ValueError(f"expected {coeffs.shape[0]} coefficients per function, got {u.shape[1]}")
-        derived = dict(self.desc)
-        derived["coeffs"] = numpy.einsum("fd,dck->fck", u, coeffs)
-        derived.pop("nodes", None)                                               # no longer a nodal basis
-        return Tabulator(derived, self.device).tabulate(order, points, entity)
+        Tabulation is linear in the coefficient tensor (FIAT/polynomial_set.py:71): the functions' tables are the
+        tables of the weights coefficients . C, which the library forms on the device in the same call
+        (`fiatb200_evaluate_simplex`), so a new coefficient vector needs no re-planning.  Scalar tensor-product
+        elements nest the sum over the factors (`fiatb200_evaluate_tensor`); wrapper elements (enriched, mixed,
+        H(div)/H(curl) on tensor products) add up their parts' evaluations with the parts' dof slices, component
+        placement and signs (FIAT/enriched.py:88-113, mixed.py:61-92, hdivcurl.py)."""
+        out, alphas, shape = self._evaluate_device(coefficients, order, points, entity)
+        return {a: out[j].reshape(shape) for j, a in enumerate(alphas)}
 
-    def _evaluate_tensor(self, coefficients, order, points, entity):
-        """evaluate() on scalar tensor-product elements: nested partial sums over the factors in one kernel
-        (`fiatb200_evaluate_tensor`); the prod(n_l)-row table is never formed."""
-        if planmod.value_shape_of(self.desc):
-            raise UnsupportedElement("fused evaluation covers scalar tensor-product elements")
-        p, nrows, pdim = self._tensor_plan(self.desc, order, entity)
-        u = numpy.atleast_2d(numpy.asarray(coefficients, dtype=numpy.float64))
-        if u.shape[1] != nrows:
-            raise ValueError(f"expected {nrows} coefficients per function, got {u.shape[1]}")
-        pts = self._points(points, pdim)
-        npts = pts.shape[0]
+    def _coefficients(self, coefficients, ndofs):
+        if isinstance(coefficients, torch.Tensor):
+            u = coefficients.to(device=self.device, dtype=torch.float64)
+            u = u.reshape(1, -1) if u.ndim == 1 else u
+        else:
+            u = torch.as_tensor(numpy.ascontiguousarray(numpy.atleast_2d(numpy.asarray(coefficients, dtype=numpy.float64))),
+                                device=self.device)
+        if u.ndim != 2 or u.shape[1] != ndofs:
+            raise ValueError(f"expected {ndofs} coefficients per function, got {tuple(u.shape)}")
+        return u.contiguous()
+
+    def _eval_plan(self, desc, order):
+        """Plan of the stacked derived element (plan.stacked_derived) -> (plan, nstack, ndofs, ncomp), or None."""
+        key = ("eval", id(desc), order)
+        with self._lock:
+            if key in self._plans:
+                return self._plans[key]
+        out = None
+        if desc["kind"] == "simplex" and desc["expansion"] == "dubiner":
+            _, prog = self._simplex_plan(desc, order)
+            stacked = planmod.stacked_derived(desc, order, prog)
+            if stacked is not None:
+                p = self._simplex_plan(stacked, 0)[0]
+                out = (p, prog.na, prog.ndofs, prog.nrows // max(prog.ndofs, 1), stacked)
+        with self._lock:
+            self._plans[key] = out
+        return out
+
+    def _evaluate_device(self, coefficients, order, points, entity):
+        """-> (tensor (nalpha, nfunc * ncomp, npts), alphas, (nfunc, *value_shape, npts))"""
+        if order < 0:
+            raise ValueError("order must be non-negative")
         alphas = self.alphas(order)
-        coef = torch.as_tensor(numpy.ascontiguousarray(u), device=self.device)
-        out = torch.empty((len(alphas), u.shape[0], npts), dtype=torch.float64, device=self.device)
+        vs = planmod.value_shape_of(self.desc)
+        nc_out = int(numpy.prod(vs)) if vs else 1
+        ndofs = planmod.num_dofs_of(self.desc)
+        u = self._coefficients(coefficients, ndofs)
+        nfunc = u.shape[0]
+        parts = planmod.resolve_parts(self.desc, entity)
+        single = len(parts) == 1 and parts[0].dof_base == 0 and parts[0].comp_out == list(range(nc_out)) \
+            and all(sg == 1.0 for sg in parts[0].sign)
+        total = None
+        for part in parts:
+            nd = planmod.num_dofs_of(part.desc)
+            up = u if single else u[:, part.dof_base:part.dof_base + nd].contiguous()
+            if part.desc["kind"] == "simplex":
+                got = self._evaluate_simplex_part(part.desc, up, order, points, part.entity)
+            else:
+                got = self._evaluate_tensor_part(part.desc, up, order, points, part.entity)
+            if single:
+                total = got
+                break
+            # got: (nalpha, nfunc * nc_in, npts) -> components comp_out of the wrapper's value, with signs
+            npts = got.shape[-1]
+            if total is None:
+                total = torch.zeros((len(alphas), nfunc, nc_out, npts), dtype=torch.float64, device=self.device)
+            g = got.reshape(len(alphas), nfunc, len(part.comp_out), npts)
+            for k, (c, sg) in enumerate(zip(part.comp_out, part.sign)):
+                total[:, :, c, :] += sg * g[:, :, k, :]
+        npts = total.shape[-1]
+        return total.reshape(len(alphas), nfunc * nc_out, npts), alphas, (nfunc,) + vs + (npts,)
+
+    def _evaluate_simplex_part(self, desc, u, order, points, entity):
+        sd = int(desc["sd"])
+        dim, tr = _resolve_simplex_entity(desc, entity)
+        ent = _lib.entity_struct(sd, tr)
+        pts = self._points(points, dim)
+        npts = pts.shape[0]
+        nfunc = u.shape[0]
+        ep = self._eval_plan(desc, order)
+        if ep is None:
+            # sets without derivative matrices (1-D Legendre / Lagrange lines, degree 0, very high degrees): tabulate
+            # the derived element whose coefficient tensor is u . coeffs (planned per coefficient set)
+            coeffs = numpy.asarray(desc["coeffs"], dtype=numpy.float64)
+            derived = dict(desc)
+            derived["coeffs"] = numpy.einsum("fd,dck->fck", u.cpu().numpy(), coeffs)
+            derived.pop("nodes", None)
+            tab = Tabulator(derived, self.device).tabulate(order, points, entity)
+            return torch.stack([v.reshape(nfunc * coeffs.shape[1], npts) for v in tab.values()])
+        p, nstack, ndofs, ncomp, _ = ep
+        out = torch.empty((nstack, nfunc * ncomp, npts), dtype=torch.float64, device=self.device)
         if npts:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.fiatb200_evaluate_tensor(p.handle, coef.data_ptr(), u.shape[0], pts.data_ptr(), npts,
+                _lib.check(self.lib.fiatb200_evaluate_simplex(
+                    p.handle, nstack, ndofs, u.data_ptr(), nfunc, ctypes.byref(ent), pts.data_ptr(), npts,
+                    pts.stride(0) if pts.shape[1] else 0, out.data_ptr(), npts, stream))
+        return out
+
+    def _evaluate_tensor_part(self, desc, u, order, points, entity):
+        if planmod.value_shape_of(desc):
+            # one vector-valued factor (FIAT/tensor_product.py:293-335): contract the table (no nested-sum kernel yet)
+            tab = get_tabulator(desc, self.device).tabulate(order, points, entity)
+            return torch.stack([torch.einsum("fd,dcp->fcp", u, v.reshape(v.shape[0], -1, v.shape[-1])).reshape(
+                u.shape[0] * (v.numel() // (v.shape[0] * v.shape[-1])), v.shape[-1]) for v in tab.values()])
+        p, nrows, pdim = self._tensor_plan(desc, order, entity)
+        pts = self._points(points, pdim)
+        npts = pts.shape[0]
+        out = torch.empty((len(self.alphas(order)), u.shape[0], npts), dtype=torch.float64, device=self.device)
+        if npts:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fiatb200_evaluate_tensor(p.handle, u.data_ptr(), u.shape[0], pts.data_ptr(), npts,
                                                               pts.stride(0) if pts.shape[1] else 0, out.data_ptr(), npts,
                                                               stream))
-        return {a: out[j] for j, a in enumerate(alphas)}
+        return out
+
+    def evaluate_host(self, coefficients, order, points, entity=None, out=None, chunk_pts=1 << 17):
+        """evaluate() with host (numpy) buffers: points in, {alpha: ndarray (nfunc, *value_shape, npts)} out, chunked and
+        double-buffered inside the library (`fiatb200_evaluate_host`).  Per point 8 * dim bytes go to the device and
+        8 * nalpha * nfunc * ncomp bytes come back -- not the tables.  Plain Ciarlet elements and scalar tensor-product
+        elements take the pipelined path; wrapper elements go through evaluate() and one copy."""
+        alphas = self.alphas(order)
+        vs = planmod.value_shape_of(self.desc)
+        nc = int(numpy.prod(vs)) if vs else 1
+        ndofs = planmod.num_dofs_of(self.desc)
+        u = numpy.ascontiguousarray(numpy.atleast_2d(numpy.asarray(coefficients, dtype=numpy.float64)))
+        if u.shape[1] != ndofs:
+            raise ValueError(f"expected {ndofs} coefficients per function, got {u.shape}")
+        nfunc = u.shape[0]
+        parts = planmod.resolve_parts(self.desc, entity)
+        plain = len(parts) == 1 and parts[0].dof_base == 0 and parts[0].comp_out == list(range(nc)) \
+            and all(sg == 1.0 for sg in parts[0].sign)
+        handle = ent = None
+        if plain and parts[0].desc["kind"] == "simplex":
+            ep = self._eval_plan(parts[0].desc, order)
+            if ep is not None:
+                handle, nstack = ep[0].handle, ep[1]
+                pdim, tr = _resolve_simplex_entity(parts[0].desc, parts[0].entity)
+                ent = _lib.entity_struct(int(parts[0].desc["sd"]), tr)
+        elif plain and not vs:
+            p, nrows, pdim = self._tensor_plan(parts[0].desc, order, parts[0].entity)
+            handle, nstack = p.handle, len(alphas)
+        if handle is None:
+            dev, _, shape = self._evaluate_device(u, order, points, entity)
+            res = dev.cpu().numpy()
+            if out is not None:
+                out[...] = res.reshape(out.shape)
+                res = out
+            return {a: res[j].reshape(shape) for j, a in enumerate(alphas)}
+        pts = numpy.ascontiguousarray(numpy.asarray(points, dtype=numpy.float64)).reshape(-1, pdim)
+        npts = pts.shape[0]
+        if out is None:
+            out = numpy.empty((len(alphas), nfunc * nc, npts))
+        elif not (isinstance(out, numpy.ndarray) and out.dtype == numpy.float64 and out.flags.c_contiguous
+                  and out.flags.writeable and out.size == len(alphas) * nfunc * nc * npts):
+            raise ValueError(f"out must be a writeable C-contiguous float64 ndarray with {len(alphas) * nfunc * nc * npts} entries")
+        if npts:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fiatb200_evaluate_host(
+                    handle, nstack, ndofs, u.ctypes.data, nfunc, ctypes.byref(ent) if ent is not None else None,
+                    pts.ctypes.data, npts, pdim, out.ctypes.data, chunk_pts))
+        flat = out.reshape(len(alphas), nfunc * nc, npts)
+        return {a: flat[j].reshape((nfunc,) + vs + (npts,)) for j, a in enumerate(alphas)}
 
     def locate_subcells(self, points, unique, entity=None):
         """Bitmask (uint32 as int64 tensor) of the subcells each point is binned to."""

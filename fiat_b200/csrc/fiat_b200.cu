@@ -99,9 +99,8 @@ DevRowMap make_row_map(const fiatb200_row_map* m, int ncomp, int nrows) {
 
 // ---- thread-per-point launch -----------------------------------------------------------------
 template <int SD, int ORDER>
-int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
-                    double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    const DevSimplex& P = plan->simplex;
+int launch_cellwise(const fiatb200_plan* plan, const DevSimplex& P, const DevEntity& E, const double* pts, long long npts,
+                    long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
     const size_t per_point = (size_t)P.nslots * P.na * sizeof(double);
     // widest block whose private expansion columns fit; very large elements end up with narrow blocks
     int bp = 128;
@@ -124,27 +123,26 @@ int launch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double*
 }
 
 template <int SD>
-int dispatch_cellwise(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts,
+int dispatch_cellwise(const fiatb200_plan* plan, const DevSimplex& P, const DevEntity& E, const double* pts, long long npts,
                       long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    switch (plan->simplex.order) {
-        case 0: return launch_cellwise<SD, 0>(plan, E, pts, npts, ldp, out, ostride, M, st);
-        case 1: return launch_cellwise<SD, 1>(plan, E, pts, npts, ldp, out, ostride, M, st);
-        case 2: return launch_cellwise<SD, 2>(plan, E, pts, npts, ldp, out, ostride, M, st);
-        case 3: return launch_cellwise<SD, 3>(plan, E, pts, npts, ldp, out, ostride, M, st);
-        default: return launch_cellwise<SD, -1>(plan, E, pts, npts, ldp, out, ostride, M, st);
+    switch (P.order) {
+        case 0: return launch_cellwise<SD, 0>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
+        case 1: return launch_cellwise<SD, 1>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
+        case 2: return launch_cellwise<SD, 2>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
+        case 3: return launch_cellwise<SD, 3>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
+        default: return launch_cellwise<SD, -1>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
 // ---- tile / DMMA launch ------------------------------------------------------------------------
-bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
-    const DevSimplex& P = plan->simplex;
-    if (P.ncells != 1 || P.expansion != 0 || P.order > 3 || P.nblk == 0 || plan->tab.nrb == 0) return false;
+bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGeom* G, size_t* smem_out) {
+    if (P.ncells != 1 || P.expansion != 0 || P.order > 3 || P.nblk == 0 || nrb == 0) return false;
     // one CTA per SM: the widest tile whose expansion table fits in shared memory
     const size_t budget = (size_t)plan->max_smem_optin - 1024;
     int pt_max = 128;
     const FbTuning& tune = fb_tuning();
     if (tune.mma_pt >= 0) pt_max = std::max(8, tune.mma_pt) & ~7;
-    const int go = P.na >= 8 ? 1 : (P.na >= 5 ? 2 : (P.na >= 3 ? 4 : (P.na == 2 ? 8 : 16)));   // octets per contraction work item (kernels.cuh)
+    const int go = fb_mma_go(P.na);     // octets per contraction work item (kernels.cuh)
     int maxlev = 1;
     for (int l = 0; l < plan->tab.nlevels; ++l)
         maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
@@ -152,8 +150,11 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     // launch_mma); otherwise the widest tile that fits one CTA per SM
     for (int pass = 0; pass < 2; ++pass) {
         const size_t limit = pass == 0 ? (size_t)110 * 1024 : budget;
-        const int pt_min = pass == 0 ? std::max(32, 8 * go) : 8 * go;
-        if (pass == 0 && tune.mma_pt >= 0) continue;
+        // (value-only tables, na == 1: 64-point tiles with half-width work items are allowed so that the large
+        // derived elements -- P8 tet: 168 members -- still get two resident CTAs whose phases overlap)
+        const int pt_half = P.na == 1 ? 4 * go : 8 * go;
+        const int pt_min = pass == 0 ? std::max(32, pt_half) : (tune.mma_pt >= 0 ? pt_half : 8 * go);
+        if (pass == 0 && tune.mma_pt >= 0) continue;     // an explicit tile width is taken as is
         for (int pt = pt_max; pt >= pt_min; pt >>= 1) {
             int ld = P.na * pt;
             while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
@@ -174,10 +175,10 @@ bool mma_geometry(const fiatb200_plan* plan, MmaGeom* G, size_t* smem_out) {
     return false;
 }
 
-template <int SD, int ORDER, int PW>
-int launch_mma_pw(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
+template <int SD, int ORDER, int PW, int GOSHIFT>
+int launch_mma_pw(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                   long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    int rc = fb_set_smem(k_mma<SD, ORDER, PW>, smem);
+    int rc = fb_set_smem(k_mma<SD, ORDER, PW, GOSHIFT>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
     int threads = FB_MMA_THREADS;
@@ -185,27 +186,29 @@ int launch_mma_pw(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& 
     // recurrence / tail overlaps the other's contraction
     if (smem <= 110 * 1024) threads = 256;
     if (fb_tuning().mma_threads >= 0) threads = fb_tuning().mma_threads >= 512 ? 512 : 256;
-    k_mma<SD, ORDER, PW><<<grid, threads, smem, st>>>(plan->simplex, plan->tab, E, G, pts, npts, ldp, out, ostride, M);
+    k_mma<SD, ORDER, PW, GOSHIFT><<<grid, threads, smem, st>>>(P, tab, E, G, pts, npts, ldp, out, ostride, M);
     fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
 }
 
 template <int SD, int ORDER>
-int launch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
+int launch_mma(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-    return launch_mma_pw<SD, ORDER, 8>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    if (ORDER == 0 && G.PT < 8 * fb_mma_go(1))          // 64-point tile of a value-only table
+        return launch_mma_pw<SD, 0, 16, 1>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16, 0>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    return launch_mma_pw<SD, ORDER, 8, 0>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
 }
 
 template <int SD>
-int dispatch_mma(const fiatb200_plan* plan, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
+int dispatch_mma(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                  long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    switch (plan->simplex.order) {
-        case 0: return launch_mma<SD, 0>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-        case 1: return launch_mma<SD, 1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-        case 2: return launch_mma<SD, 2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-        default: return launch_mma<SD, 3>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    switch (P.order) {
+        case 0: return launch_mma<SD, 0>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+        case 1: return launch_mma<SD, 1>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+        case 2: return launch_mma<SD, 2>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+        default: return launch_mma<SD, 3>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
@@ -219,7 +222,7 @@ enum KernelChoice { K_CELLWISE = 1, K_MMA = 2, K_SMALL = 3, K_VALS = 4, K_LATTIC
 //              of a warp sit in different subcells) against 0.5 cycles per FP64 instruction.
 int choose_simplex_kernel(const fiatb200_plan* plan, uint32_t flags, MmaGeom* G, size_t* smem) {
     const DevSimplex& P = plan->simplex;
-    bool use_mma = mma_geometry(plan, G, smem);
+    bool use_mma = mma_geometry(plan, P, plan->tab.nrb, G, smem);
     if (flags & 1u) use_mma = false;
     if ((flags & 2u) && !use_mma) return 0;
     if (flags & 2u) return K_MMA;
@@ -277,16 +280,16 @@ int tabulate_simplex(const fiatb200_plan* plan, const fiatb200_entity_map* entit
         case K_SMALL: return fb_dispatch_small(plan, E, pts, npts, ldp, out, ostride, M, st);
         case K_MMA:
             switch (P.sd) {
-                case 1: return dispatch_mma<1>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-                case 2: return dispatch_mma<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-                default: return dispatch_mma<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+                case 1: return dispatch_mma<1>(P, plan->tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+                case 2: return dispatch_mma<2>(P, plan->tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+                default: return dispatch_mma<3>(P, plan->tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
             }
         default: break;
     }
     switch (P.sd) {
-        case 1: return dispatch_cellwise<1>(plan, E, pts, npts, ldp, out, ostride, M, st);
-        case 2: return dispatch_cellwise<2>(plan, E, pts, npts, ldp, out, ostride, M, st);
-        default: return dispatch_cellwise<3>(plan, E, pts, npts, ldp, out, ostride, M, st);
+        case 1: return dispatch_cellwise<1>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
+        case 2: return dispatch_cellwise<2>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
+        default: return dispatch_cellwise<3>(plan, P, E, pts, npts, ldp, out, ostride, M, st);
     }
 }
 
@@ -747,6 +750,78 @@ int fiatb200_evaluate_tensor(const fiatb200_plan* plan, const double* coef_dev, 
     return FIATB200_OK;
 }
 
+int fiatb200_evaluate_simplex(const fiatb200_plan* plan, int32_t nstack, int32_t ndofs, const double* coef_dev,
+                              int32_t nfunc, const fiatb200_entity_map* entity, const double* pts_dev, int64_t npts,
+                              int64_t pts_ld, double* out_dev, int64_t out_row_stride, void* stream) {
+    if (!plan || plan->kind != PLAN_SIMPLEX) return fb_fail(FIATB200_ERR_ARG, "a simplex plan is required");
+    const DevSimplex& P0 = plan->simplex;
+    const int ncomp = P0.ncomp;
+    if (P0.order != 0 || nstack < 1 || ndofs < 1 || nfunc < 1 || (int64_t)nstack * ndofs * ncomp != P0.nrows)
+        return fb_fail(FIATB200_ERR_ARG, "evaluate needs the order-0 stacked derived plan: nrows == nstack * ndofs * ncomp");
+    if (npts < 0 || out_row_stride < npts) return fb_fail(FIATB200_ERR_ARG, "bad point count / row stride");
+    if (npts == 0) return FIATB200_OK;
+    if (!coef_dev || !out_dev || (!pts_dev && pts_ld != 0)) return fb_fail(FIATB200_ERR_ARG, "null device pointer");
+    const int64_t reval = (int64_t)nstack * nfunc * ncomp;
+    if (reval > 8 * FB_MAX_RB) return fb_fail(FIATB200_ERR_UNSUPPORTED, "too many functions for one evaluation launch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevEntity E = make_entity(entity, P0.sd);
+    if (E.dim < 0 || E.dim > 3) return fb_fail(FIATB200_ERR_ARG, "entity dimension out of range");
+
+    // stream-ordered workspace: W, and for the tile kernel its fragments and member slots
+    const int nrb = (int)((reval + 7) / 8), nkb = (P0.nslots + 3) / 4;
+    const size_t w_bytes = sizeof(double) * (size_t)P0.ncells * reval * P0.nslots;
+    const size_t f_bytes = sizeof(double) * 32 * (size_t)nrb * nkb, i_bytes = sizeof(int) * 4 * (size_t)nrb * nkb;
+    const size_t w_off = 0, f_off = (w_bytes + 255) & ~size_t(255), i_off = (f_off + f_bytes + 255) & ~size_t(255);
+    unsigned char* ws = nullptr;
+    FB_CUDA(cudaMallocAsync(&ws, i_off + i_bytes + 256, st));
+    double* W = reinterpret_cast<double*>(ws + w_off);
+    double* frag = reinterpret_cast<double*>(ws + f_off);
+    int* slots = reinterpret_cast<int*>(ws + i_off);
+    {
+        const long long total = (long long)P0.ncells * reval * P0.nslots;
+        k_eval_weights<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(P0.ccell, P0.ncells, nstack, ndofs, ncomp, P0.nslots,
+                                                                        coef_dev, nfunc, W);
+        fb_launches++;
+    }
+    DevSimplex P = P0;
+    P.nrows = (int)reval;
+    P.ccell = W;
+    P.ccell_morton = W;
+    P.ncp = 0;
+    P.cderiv_len = 0;
+    P.blk_cells = 0;
+    DevRowMap M = make_row_map(nullptr, ncomp, (int)reval);
+    int rc = FIATB200_OK;
+    MmaGeom G;
+    size_t smem = 0;
+    P.nrb = nrb; P.kpad = nkb * 4; P.nblk = nrb * nkb;
+    P.blk_frag = frag; P.blk_kb = slots;
+    if (P.sd >= 2 && P.degree >= 1 && mma_geometry(plan, P, nrb, &G, &smem)) {
+        // single-cell Dubiner sets: level-parallel value recurrence + dense DMMA contraction with the weights
+        k_eval_fragments<<<(unsigned)(nrb * nkb), 32, 0, st>>>(W, (int)reval, P.nslots, nkb, frag, slots);
+        fb_launches++;
+        RecTab tab = plan->tab;
+        tab.nrb = nrb;
+        for (int rb = 0; rb < nrb; ++rb) { tab.rb_order[rb] = (short)rb; tab.blk_ptr[rb] = rb * nkb; }
+        tab.blk_ptr[nrb] = nrb * nkb;
+        for (int i = 0; i < nrb * 8; ++i) tab.row_perm[i] = (short)(i < reval ? i : -1);
+        switch (P.sd) {
+            case 2: rc = dispatch_mma<2>(P, tab, E, G, smem, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, st); break;
+            default: rc = dispatch_mma<3>(P, tab, E, G, smem, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, st); break;
+        }
+    } else {
+        // split cells, 1-D sets: thread per point with the per-subcell weights
+        switch (P.sd) {
+            case 1: rc = dispatch_cellwise<1>(plan, P, E, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, st); break;
+            case 2: rc = dispatch_cellwise<2>(plan, P, E, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, st); break;
+            default: rc = dispatch_cellwise<3>(plan, P, E, pts_dev, npts, pts_ld, out_dev, out_row_stride, M, st); break;
+        }
+    }
+    cudaError_t e = cudaFreeAsync(ws, st);
+    if (rc == FIATB200_OK && e != cudaSuccess) rc = fb_fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
 int fiatb200_zero_rows(double* out_dev, int64_t out_row_stride, int64_t npts, int64_t total_rows, int32_t nalpha,
                        const int32_t* rows_dev, int32_t nrows, void* stream) {
     if (npts == 0 || nrows == 0) return FIATB200_OK;
@@ -879,6 +954,35 @@ int fiatb200_tabulate_host_list(const fiatb200_launch* launches, int32_t nlaunch
                              }
                              return rc;
                          });
+}
+
+int fiatb200_evaluate_host(const fiatb200_plan* cplan, int32_t nstack, int32_t ndofs, const double* coef_host,
+                           int32_t nfunc, const fiatb200_entity_map* entity, const double* pts_host, int64_t npts,
+                           int64_t pts_ld, double* out_host, int64_t chunk_pts) {
+    if (!cplan || (cplan->kind != PLAN_SIMPLEX && cplan->kind != PLAN_TENSOR))
+        return fb_fail(FIATB200_ERR_ARG, "a simplex or tensor-product plan is required");
+    if (npts == 0) return FIATB200_OK;
+    if (!coef_host || (!pts_host && pts_ld != 0) || !out_host || chunk_pts <= 0 || nfunc < 1 || ndofs < 1 || nstack < 1)
+        return fb_fail(FIATB200_ERR_ARG, "bad host buffers / sizes");
+    fiatb200_plan* plan = const_cast<fiatb200_plan*>(cplan);
+    const bool tensor = plan->kind == PLAN_TENSOR;
+    const int ncomp = tensor ? 1 : plan->simplex.ncomp;
+    if (tensor && (nstack != plan->tensor.nalpha || ndofs != plan->tensor.nrows))
+        return fb_fail(FIATB200_ERR_ARG, "nstack / ndofs do not match the tensor-product plan");
+    double* coef_dev = nullptr;
+    FB_CUDA(cudaMalloc(&coef_dev, sizeof(double) * (size_t)nfunc * ndofs));
+    cudaError_t e = cudaMemcpy(coef_dev, coef_host, sizeof(double) * (size_t)nfunc * ndofs, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? FIATB200_OK : fb_fail(FIATB200_ERR_CUDA, cudaGetErrorString(e));
+    if (rc == FIATB200_OK)
+        rc = host_pipeline(plan, (int64_t)nstack * nfunc * ncomp, pts_host, npts, pts_ld, out_host, chunk_pts,
+                           [&](const double* dpts, int64_t n, double* dout, int64_t stride, cudaStream_t st) {
+                               if (tensor)
+                                   return fiatb200_evaluate_tensor(plan, coef_dev, nfunc, dpts, n, pts_ld, dout, stride, st);
+                               return fiatb200_evaluate_simplex(plan, nstack, ndofs, coef_dev, nfunc, entity, dpts, n, pts_ld,
+                                                                dout, stride, st);
+                           });
+    cudaFree(coef_dev);
+    return rc;
 }
 
 }  // extern "C"

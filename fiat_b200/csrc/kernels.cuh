@@ -152,7 +152,12 @@ struct MmaGeom {
 // T layout: T[slot][point group][alpha][PW points], PW = 16 (8 for the narrowest tile): 16 consecutive
 // points are contiguous so that the recurrence's per-point accesses of a half warp hit 32 distinct
 // banks, and every octet of a group is still 8 contiguous columns for the DMMA fragments.
-template <int SD, int ORDER, int PW>
+// octets per contraction work item: ~16 DMMAs per coefficient fragment
+__host__ __device__ constexpr int fb_mma_go(int na) {
+    return na >= 8 ? 1 : (na >= 5 ? 2 : (na >= 3 ? 4 : (na == 2 ? 8 : 16)));
+}
+
+template <int SD, int ORDER, int PW, int GOSHIFT>
 __global__ void __launch_bounds__(FB_MMA_THREADS, 1)
 k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const MmaGeom G,
       const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride,
@@ -236,7 +241,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     // use.  Fragments are fetched CH blocks ahead so that their L2 latency hides behind
     // the DMMAs of the current chunk; row-block tables come from the constant bank.
     constexpr int CH = 8;
-    constexpr int GO = NA >= 8 ? 1 : (NA >= 5 ? 2 : (NA >= 3 ? 4 : (NA == 2 ? 8 : 16)));     // ~16 DMMAs per fragment
+    constexpr int GO = fb_mma_go(NA) >> GOSHIFT;        // GOSHIFT = 1: half-width items for 64-point tiles (two CTAs per SM)
     const int lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int ngrp = PT / (8 * GO);
@@ -629,6 +634,39 @@ k_hex_eval(const DevTensor Q, const double* __restrict__ coef, int nfunc, const 
                     ++al;
                 }
     }
+}
+
+// Weights of a fused point evaluation u_f = sum_i coef[f][i] phi_i: tabulation is linear in the coefficient tensor
+// (FIAT/polynomial_set.py:71), so the functions' derivative tables are the tables of W = coef . C,
+//   W[cell][(j * nfunc + f) * ncomp + c][k] = sum_i coef[f][i] * C[cell][(j * ndofs + i) * ncomp + c][k],
+// for the stacked derived element C (rows: table j, dof i, component c; fiat_b200/plan.py: stacked_derived).  Formed
+// on the device per call, so new coefficients need no re-planning.
+__global__ void k_eval_weights(const double* __restrict__ C, int ncells, int nstack, int ndofs, int ncomp, int nslots,
+                               const double* __restrict__ coef, int nfunc, double* __restrict__ W) {
+    const int reval = nstack * nfunc * ncomp;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)ncells * reval * nslots) return;
+    const int k = (int)(idx % nslots);
+    const int er = (int)((idx / nslots) % reval);
+    const int cell = (int)(idx / ((long long)nslots * reval));
+    const int c = er % ncomp, f = (er / ncomp) % nfunc, j = er / (ncomp * nfunc);
+    const double* Cc = C + ((size_t)cell * nstack * ndofs * ncomp + (size_t)j * ndofs * ncomp + c) * nslots + k;
+    const double* u = coef + (size_t)f * ndofs;
+    double s = 0.0;
+    for (int i = 0; i < ndofs; ++i) s = fma(__ldg(u + i), __ldg(Cc + (size_t)i * ncomp * nslots), s);
+    W[idx] = s;
+}
+
+// The same weights (single-cell plans) as the A fragments of a dense grid of 8x4 blocks for the tile kernel:
+// block (rb, kb) multiplies member slots 4 kb .. 4 kb + 3 (slots >= nslots are zero rows of the expansion table).
+__global__ void k_eval_fragments(const double* __restrict__ W, int reval, int nslots, int nkb, double* __restrict__ frag,
+                                 int* __restrict__ slots) {
+    const int q = blockIdx.x;                   // block rb * nkb + kb
+    const int lane = threadIdx.x;
+    const int rb = q / nkb, kb = q % nkb;
+    const int row = rb * 8 + (lane >> 2), slot = kb * 4 + (lane & 3);
+    frag[(size_t)q * 32 + lane] = (row < reval && slot < nslots) ? W[(size_t)row * nslots + slot] : 0.0;
+    if (lane < 4) slots[(size_t)q * 4 + lane] = kb * 4 + lane;
 }
 
 // zero-fill rows that no part of a wrapper element writes (all derivative tables)

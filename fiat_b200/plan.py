@@ -26,7 +26,7 @@ from dataclasses import dataclass, field
 import numpy
 
 __all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf", "lattice_rowmap",
-           "alpha_split", "merged_split", "macro_merged",
+           "alpha_split", "merged_split", "macro_merged", "stacked_derived",
            "resolve_parts", "Part", "value_shape_of", "num_dofs_of"]
 
 EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
@@ -659,7 +659,7 @@ def compile_simplex(desc, order):
     if desc["expansion"] == "dubiner":
         t = _dubiner_tables(desc, order)
         tile_cells = ncells > 1 and bool(desc.get("raw_members"))       # split-cell tile kernel (cells.cuh)
-        if (ncells == 1 or tile_cells) and nrows * nexp_total >= 1024:
+        if (ncells == 1 or tile_cells) and nrows * nexp_total >= 1024 and not desc.get("dense_only"):
             # Large elements go to the tile kernels, whose 8x4 blocks gather any four member slots; the four rows of
             # the expansion table a block reads are bank-conflict free iff the slots differ mod 4.  Slot numbers are
             # a free choice: pick each member's slot mod 4 (its colour) so that the members every row group uses
@@ -726,11 +726,11 @@ def compile_simplex(desc, order):
         fix_idx=t["fix_idx"], fix_w=t["fix_w"],
         fix_grp=fix_grp, ccell=ccell, low1=low1, mul1=mul1, low2=low2, mul2=mul2, line_tab=line_tab, line_n=line_n)
     if desc["expansion"] == "dubiner":
-        cder, ncp = derivative_coefficients(desc, t, ccell_morton, order)
+        cder, ncp = (None, 0) if desc.get("dense_only") else derivative_coefficients(desc, t, ccell_morton, order)
         if cder is not None:
             prog.cderiv, prog.ncp = cder, ncp
         prog.slot_of = numpy.asarray(t["slot_of"], dtype=numpy.int64)
-    if desc["expansion"] == "dubiner" and (ncells == 1 or desc.get("raw_members")):
+    if desc["expansion"] == "dubiner" and (ncells == 1 or desc.get("raw_members")) and not desc.get("dense_only"):
         # Tile kernels (kernels.cuh: k_mma, cells.cuh: k_mma_cells) have no fix-up phase: T' = X T  =>  C T' = (C X) T.
         # Split cells: one block stream per subcell (blk_ptr holds one (nrb + 1)-entry row per subcell, every row
         # block has at least one, possibly zero, block), common row order and slots.
@@ -816,6 +816,41 @@ def merged_split(desc, order, split):
     out = dict(top)
     out["coeffs"] = stacked
     return out
+
+
+def stacked_derived(desc, order, prog=None):
+    """Order-0 element whose rows are ALL derivative tables of `desc` up to `order`, one after the other
+    (row = (table j, dof i, component c)), with dense per-subcell coefficient matrices on the un-normalised
+    recurrence members: the operand of the fused point evaluation (api.Tabulator.evaluate), whose weights
+    coefficients . C are formed on the device.  Works for single-cell and split-cell Dubiner sets of any size (no
+    block packing is built: "dense_only").  None when the derivative matrices cannot be trusted (very high degree)
+    or the set is not a Dubiner set."""
+    if desc.get("kind") != "simplex" or desc.get("expansion") != "dubiner" or desc.get("raw_members"):
+        return None
+    sd, n, ncells = int(desc["sd"]), int(desc["degree"]), int(desc["ncells"])
+    if n < 1:
+        return None
+    coeffs = numpy.asarray(desc["coeffs"])
+    ndofs, ncomp = coeffs.shape[0], coeffs.shape[1]
+    alphas = alpha_list(sd, order)
+    if prog is None:
+        prog = compile_simplex(desc, order)
+    mats = alpha_matrices(desc, _dubiner_tables(desc, order), prog.ccell_morton, order)
+    if mats is None:
+        return None
+    nmem = prog.nslots
+    nrows = ndofs * ncomp
+    stacked = numpy.zeros((len(alphas) * nrows, ncells * nmem))
+    for j, per_cell in enumerate(mats):
+        for c in range(ncells):
+            m = per_cell[c]
+            stacked[j * nrows:(j + 1) * nrows, c * nmem:c * nmem + m.shape[1]] = m
+    d = {key: val for key, val in desc.items() if key not in ("nodes", "coeffs", "cell_node_map", "c0")}
+    d.update(c0=False, raw_members=True, dense_only=True, unique=int(bool(desc["c0"]) and order == 0),
+             coeffs=numpy.ascontiguousarray(stacked.reshape(len(alphas) * ndofs, ncomp, ncells * nmem)),
+             cell_node_map=(numpy.arange(nmem, dtype=numpy.int64)[None, :]
+                            + nmem * numpy.arange(ncells, dtype=numpy.int64)[:, None]))
+    return d
 
 
 def macro_merged(desc, order, prog=None):

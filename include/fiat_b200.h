@@ -182,6 +182,17 @@ int fiatb200_tabulate_mapped(const fiatb200_plan* plan, const fiatb200_entity_ma
 int fiatb200_evaluate_tensor(const fiatb200_plan* plan, const double* coef_dev, int32_t nfunc, const double* pts_dev,
                              int64_t npts, int64_t pts_ld, double* out_dev, int64_t out_row_stride, void* stream);
 
+/* The same fused consumer for Ciarlet elements on (possibly split) simplices.  `plan` is the order-0 simplex plan of
+ * the element's *stacked derived element* (fiat_b200/plan.py: stacked_derived), whose rows are
+ * (derivative table j of nstack, dof i of ndofs, component c): D^alpha_j phi_i[c].  Then
+ *   out[((j * nfunc + f) * ncomp + c) * out_row_stride + point] = sum_i coef[f * ndofs + i] * D^alpha_j phi_i[c](point)
+ * = coef . CiarletElement.tabulate(order, points)[alpha_j] (FIAT/finite_element.py:181-197, polynomial_set.py:68-72)
+ * without writing the (ndofs x npts) tables.  The weights coef . C are formed on the device in the same call, so a
+ * new coefficient vector costs no re-planning.  coef_dev: nfunc x ndofs, row-major, on the device. */
+int fiatb200_evaluate_simplex(const fiatb200_plan* plan, int32_t nstack, int32_t ndofs, const double* coef_dev,
+                              int32_t nfunc, const fiatb200_entity_map* entity, const double* pts_dev, int64_t npts,
+                              int64_t pts_ld, double* out_dev, int64_t out_row_stride, void* stream);
+
 /* Zero-fill the listed rows (device array of nrows row numbers) of every derivative table: the
  * entries of a wrapper element's table that none of its parts writes. */
 int fiatb200_zero_rows(double* out_dev, int64_t out_row_stride, int64_t npts, int64_t total_rows, int32_t nalpha,
@@ -238,6 +249,15 @@ int fiatb200_cluster_rows(const uint8_t* support, int32_t nrows, int32_t ncols, 
                           int32_t* order, int64_t iters, uint64_t seed, int32_t* blocks_out);
 int fiatb200_colour_members(const uint8_t* support, int32_t nrows, int32_t ncols, int32_t nseg, const int32_t* order,
                             int64_t iters, uint64_t seed, int32_t* colour_out, int32_t* conflicts_out);
+
+/* fiatb200_evaluate_simplex / fiatb200_evaluate_tensor with HOST buffers: coefficients and points are staged to the
+ * device, the points are evaluated in chunks and the (nstack * nfunc * ncomp) x npts result is copied back, copies and
+ * kernels overlapped on the plan's two internal streams.  Per point this moves 8 * dim bytes in and
+ * 8 * nstack * nfunc * ncomp bytes out instead of the 8 * nstack * ndofs * ncomp bytes of the tables.  For
+ * tensor-product plans nstack / ndofs must be the plan's number of derivative tables / rows.  Synchronous. */
+int fiatb200_evaluate_host(const fiatb200_plan* plan, int32_t nstack, int32_t ndofs, const double* coef_host,
+                           int32_t nfunc, const fiatb200_entity_map* entity, const double* pts_host, int64_t npts,
+                           int64_t pts_ld, double* out_host, int64_t chunk_pts);
 
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t fiatb200_launch_count(void);

@@ -339,23 +339,69 @@ def test_nodality_of_tensor_product_dof_order(cuda_device):
     assert (vals - eye).abs().max().item() <= 1e-12
 
 
-@pytest.mark.parametrize("name", ["p8_tet_o2", "hct_o2", "n2curl4_tet_o1", "p2_tri_facet1_o1"])
+def _check_evaluation(desc, got, u, ref_tables):
+    ndofs = u.shape[1]
+    for alpha, ref in ref_tables.items():
+        want = numpy.tensordot(u, ref, axes=(1, 0))
+        g = got[alpha]
+        g = g.cpu().numpy() if isinstance(g, torch.Tensor) else g
+        assert g.shape == want.shape, (alpha, g.shape, want.shape)
+        bound = (abs(u)[:, :, None] * abs(ref.reshape(ndofs, -1))[None]).sum(axis=1).max()
+        assert abs(g - want).max() <= tolerance(desc, alpha) * max(bound, 1e-300), alpha
+
+
+@pytest.mark.parametrize("name", ["p8_tet_o2", "hct_o2", "hct_o0", "ps12_o2", "n2curl4_tet_o1", "p2_tri_facet1_o1", "gn_tet_o2",
+                                  "walkington_tet_o2", "p2_wf_tet_adv_o2", "hct_edge2_o2", "regge2_tet_o1", "p6_tri_o4",
+                                  "p4_line_o2", "gll7_line_o3", "legendre5_line_o3", "dp0_tet_o1", "p10_spectral_tet_o2",
+                                  # wrapper elements: parts' dof slices, component placement and signs
+                                  "mini_tri_o2", "taylor_hood_tri_o1", "rt1_dg0_mixed_tri_o1", "rtcf1_quad_o1", "rtce2_quad_o2",
+                                  "nce1_hex_o1", "rt2xp1_prism_vector_o1", "dp1xp2_prism_hdiv_o2", "n2curl3_p3_mixed_tet_o1",
+                                  # scalar tensor products
+                                  "gll_q3_hex_face4_o2", "q2_quad_o2", "p2xp1_prism_o1"])
 def test_fused_point_evaluation(name, cuda_device):
-    """evaluate(): sum_i c[f, i] D^alpha phi_i without materialising the tables, against
-    coefficients . reference table."""
+    """evaluate(): sum_i c[f, i] D^alpha phi_i without materialising the tables, against coefficients . reference
+    table (incl. the fixtures' points on interior facets); a second coefficient set reuses every plan (the weights
+    are formed on the device), coefficients may already live on the device, and the host-buffer form agrees."""
+    from fiat_b200 import plan as planmod
     from fiat_b200.api import Tabulator
     case = load_case(name)
     desc = case["desc"]
     rng = numpy.random.default_rng(3)
-    ndofs = desc["coeffs"].shape[0]
+    ndofs = planmod.num_dofs_of(desc)
+    tab = Tabulator(desc, cuda_device)
     u = rng.standard_normal((3, ndofs))
-    got = Tabulator(desc, cuda_device).evaluate(u, case["order"], case["points"], case["entity"])
-    for alpha, ref in case["ref"].items():
-        want = numpy.tensordot(u, ref, axes=(1, 0))
-        g = got[alpha].cpu().numpy()
-        assert g.shape == want.shape
-        bound = (abs(u)[:, :, None] * abs(ref.reshape(ndofs, -1))[None]).sum(axis=1).max()
-        assert abs(g - want).max() <= tolerance(desc, alpha) * max(bound, 1e-300)
+    _check_evaluation(desc, tab.evaluate(u, case["order"], case["points"], case["entity"]), u, case["ref"])
+    plans = len(tab._plans)
+    u2 = rng.standard_normal((5, ndofs))
+    _check_evaluation(desc, tab.evaluate(torch.as_tensor(u2, device=cuda_device), case["order"], case["points"], case["entity"]),
+                      u2, case["ref"])
+    if desc["kind"] == "simplex" and desc["expansion"] == "dubiner" and int(desc["degree"]) >= 1:
+        assert len(tab._plans) == plans          # new coefficients: no new plan
+    u1 = rng.standard_normal(ndofs)              # a single function as a 1-D vector
+    _check_evaluation(desc, tab.evaluate(u1, case["order"], case["points"], case["entity"]), u1[None, :], case["ref"])
+    host = tab.evaluate_host(u, case["order"], case["points"], case["entity"], chunk_pts=8)
+    assert all(isinstance(v, numpy.ndarray) for v in host.values())
+    _check_evaluation(desc, host, u, case["ref"])
+
+
+def test_fused_point_evaluation_at_scale(cuda_device):
+    """2^16 bench points of P8 (tile kernel with device-built weight fragments) and HCT (thread per point with
+    per-subcell weights) against coefficients . tabulate()."""
+    import bench
+    from fiat_b200.api import Tabulator
+    for workload in ("p8_tet_o2", "hct_o2", "n2curl4_tet_o1"):
+        dname, order, kind, _ = bench.WORKLOADS[workload]
+        desc = bench.load_desc(dname)
+        tab = Tabulator(desc, cuda_device)
+        pts = bench.device_points(kind, 1 << 16, 99, cuda_device)
+        u = torch.as_tensor(numpy.random.default_rng(5).standard_normal((2, desc["coeffs"].shape[0])), device=cuda_device)
+        got = tab.evaluate(u, order, pts)
+        full = tab.tabulate(order, pts)
+        for alpha, table in full.items():
+            want = torch.einsum("fd,d...->f...", u, table)
+            bound = torch.einsum("fd,d...->f...", u.abs(), table.abs()).max().item()
+            assert got[alpha].shape == want.shape
+            assert (got[alpha] - want).abs().max().item() <= tolerance(desc, alpha) * max(bound, 1e-300), (workload, alpha)
 
 
 @pytest.mark.parametrize("name", ["gll_q10_hex_o1", "q2_quad_edge2_o1", "p2xp1_prism_o1"])
@@ -399,7 +445,8 @@ def test_points_in_no_subcell_give_zero_columns(name, cuda_device):
     case = load_case(name)
     desc = case["desc"]
     sd = int(desc["sd"])
-    pts = numpy.array(case["points"], dtype=float)[:40].copy()
+    pts0 = numpy.asarray(case["points"], dtype=float)
+    pts = pts0[numpy.arange(40) % len(pts0)].copy()
     bad = [1, 5, 17, 18, 33]
     pts[1, 0] = numpy.nan
     pts[5, sd - 1] = numpy.inf

@@ -185,3 +185,28 @@ def test_every_golden_description_compiles(name):
     ref0 = next(iter(case["ref"].values()))
     assert ref0.shape[0] == ndofs and ref0.shape[1:-1] == planmod.value_shape_of(case["desc"])
     assert all(0 <= p.dof_base < ndofs for p in parts)
+
+
+@pytest.mark.parametrize("name", ["p8_tet_o2", "n2curl4_tet_o1", "hct_o2", "ps12_o0", "gn_tet_o2", "p2_tri_facet1_o1",
+                                  "p2_wf_tet_adv_o2", "regge2_tet_o1"])
+def test_stacked_derived_reproduces_reference(name):
+    """The operand of the fused point evaluation (plan.stacked_derived): an order-0 element whose rows are all the
+    derivative tables of the element, with dense per-subcell matrices; its order-0 tabulation with the reference's
+    binning is the stack of the reference's tables, and u . (that) are the derivatives of u = sum_i u_i phi_i."""
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    stacked = planmod.stacked_derived(desc, order)
+    assert stacked is not None and stacked["dense_only"]
+    prog = planmod.compile_simplex(stacked, 0)
+    assert len(prog.blk_kb) == 0 and prog.ncp == 0          # no packing, no value table: only the dense matrices
+    pts = numpy.asarray(case["points"], dtype=float)
+    tr = fiat_oracle.resolve_entity(desc, case["entity"])
+    if tr is not None:
+        pts = pts.reshape(len(pts), tr[0].shape[0]) @ tr[0] + tr[1]
+    near = fiat_oracle.locate_cells(desc, pts, unique=bool(prog.unique))
+    out = emu.run_simplex(prog, pts, near)[0]
+    alphas = planmod.alpha_list(int(desc["sd"]), order)
+    nrows = out.shape[0] // len(alphas)
+    for j, alpha in enumerate(alphas):
+        ref = case["ref"][alpha].reshape(-1, len(pts))
+        assert abs(out[j * nrows:(j + 1) * nrows] - ref).max() <= tolerance(desc, alpha) * max(abs(ref).max(), 1e-300), alpha
