@@ -7,4 +7,7 @@ def __getattr__(name):
     if name in ("tabulate", "tabulate_into", "tabulate_host", "locate_subcells", "Tabulator", "get_tabulator"):
         from . import api as _t
         return getattr(_t, name)
+    if name in ("tabulate_sharded", "gather_shards", "shard_range"):
+        from . import shard as _s
+        return getattr(_s, name)
     raise AttributeError(name)

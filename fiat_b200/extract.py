@@ -25,7 +25,7 @@ import sys
 
 import numpy
 
-__all__ = ["describe_element", "UnsupportedElement"]
+__all__ = ["describe_element", "describe_expansion_set", "UnsupportedElement"]
 
 
 class UnsupportedElement(NotImplementedError):
@@ -102,12 +102,34 @@ def _rescaled_barycentric_map(ref_module, verts, sd):
 def _describe_ciarlet(element):
     poly_set = element.get_nodal_basis()
     es = poly_set.get_expansion_set()
+    n = int(poly_set.get_embedded_degree())
+    coeffs = numpy.array(poly_set.get_coeffs(), dtype=float)
+    desc = _describe_expansion(es, n, coeffs, element.get_reference_element())
+    # Plain point-evaluation dual sets (Lagrange-type elements): keep the nodes.  The plan compiler
+    # uses them to recognise the nodal basis of the principal lattice, which has a closed product
+    # form (fiat_b200/plan.py: lattice_rowmap).
+    sd = int(desc["sd"])
+    nodes = _point_evaluation_nodes(element, sd)
+    if nodes is not None and len(desc["value_shape"]) == 0:
+        desc["nodes"] = nodes
+    return desc
+
+
+def describe_expansion_set(es, n):
+    """Description of the expansion set itself up to degree n: the "element" whose coefficient tensor is the
+    identity, i.e. what ExpansionSet.tabulate / tabulate_derivatives / tabulate_jet return
+    (FIAT/expansions.py:601-637, = ExpansionSet._tabulate, :449-490)."""
+    nexp = int(es.get_num_members(n))
+    ref_el = es.ref_el.get_parent() or es.ref_el
+    return _describe_expansion(es, int(n), numpy.eye(nexp).reshape(nexp, nexp), ref_el)
+
+
+def _describe_expansion(es, n, coeffs, cell):
     es_names = _mro_names(es)
     complex_ = es.ref_el
     sd = complex_.get_spatial_dimension()
     if sd == 0 or "PointExpansionSet" in es_names:
         raise UnsupportedElement("elements on a point are not tabulated on the device")
-    n = int(poly_set.get_embedded_degree())
     top = complex_.get_topology()
     cells = sorted(top[sd])
     ncells = len(cells)
@@ -127,7 +149,6 @@ def _describe_ciarlet(element):
     if continuity not in (None, "C0"):
         raise UnsupportedElement(f"unsupported expansion continuity {continuity!r}")
 
-    coeffs = numpy.array(poly_set.get_coeffs(), dtype=float)
     value_shape = tuple(int(s) for s in coeffs.shape[1:-1])
     nexp_total = int(es.get_num_members(n))
     if coeffs.shape[-1] != nexp_total:
@@ -191,16 +212,9 @@ def _describe_ciarlet(element):
         bary_A[ncells], bary_b[ncells] = _rescaled_barycentric_map(ref_module, pverts, sd)
         desc["bary_A"], desc["bary_b"] = bary_A, bary_b
 
-    keys, Cs, offs = _entity_transforms(element.get_reference_element())
+    keys, Cs, offs = _entity_transforms(cell)
     desc["ent_keys"], desc["ent_C"], desc["ent_off"] = keys, Cs, offs
-
-    # Plain point-evaluation dual sets (Lagrange-type elements): keep the nodes.  The plan compiler
-    # uses them to recognise the nodal basis of the principal lattice, which has a closed product
-    # form (fiat_b200/plan.py: lattice_rowmap).
     desc["vertices"] = numpy.array(complex_.get_vertices(), dtype=float).reshape(-1, sd)
-    nodes = _point_evaluation_nodes(element, sd)
-    if nodes is not None and value_shape == ():
-        desc["nodes"] = nodes
     return desc
 
 

@@ -1,0 +1,142 @@
+"""Device versions of the reference's setup-path tabulations of an expansion set:
+
+    ExpansionSet.tabulate / tabulate_derivatives / tabulate_jet   FIAT/expansions.py:601-637
+    ExpansionSet.tabulate_jumps                                    FIAT/expansions.py:532-575
+    ExpansionSet.get_dmats                                         FIAT/expansions.py:577-599
+
+All of them are `ExpansionSet._tabulate` (:449-490) or `_tabulate_on_cell` (:411-447) of the set itself, i.e. the
+tabulation of the "element" whose coefficient tensor is the identity (extract.describe_expansion_set), followed by
+re-packing of the tables; they run through the same plans and kernels as `FiniteElement.tabulate`.  The reference uses
+them while it CONSTRUCTS elements (macro.py, polynomial_set.py), where results feed linear solves whose output must
+stay bit-compatible with numpy for the coefficients to be identical -- so these are offered beside the reference
+(parity to the tabulation tolerance), not wired into element construction.  `DualSet.to_riesz`
+(FIAT/dual_set.py:86-206) is not covered.
+"""
+import numpy
+import torch
+
+from . import plan as planmod
+from .api import Tabulator
+from .extract import describe_expansion_set
+
+__all__ = ["ExpansionTabulator"]
+
+
+class ExpansionTabulator:
+    """Device tabulation of one reference-constructed ExpansionSet up to degree n."""
+
+    def __init__(self, expansion_set, n, device=None):
+        self.es = expansion_set
+        self.n = int(n)
+        self.desc = describe_expansion_set(expansion_set, n)
+        self.sd = int(self.desc["sd"])
+        self.tab = Tabulator(self.desc, device)
+        self.device = self.tab.device
+        self._cells = {}
+
+    # -- ExpansionSet.tabulate(n, pts): (num_members, npts) -------------------------------------------------------
+    def tabulate(self, pts):
+        if len(pts) == 0:
+            return torch.zeros((0,), dtype=torch.float64, device=self.device)     # numpy.array([]) in the reference
+        return self.tab.tabulate(0, pts)[(0,) * self.sd]
+
+    # -- ExpansionSet.tabulate_derivatives(n, pts) ----------------------------------------------------------------
+    def tabulate_derivatives(self, pts, nested=False):
+        """(v, [dv_0, ..., dv_{sd-1}]) as device tensors (num_members, npts); nested=True re-packs them into the
+        reference's list structure data[i][j] = (v[i, j], [dv_k[i, j] for k])."""
+        vals = self.tab.tabulate(1, pts)
+        v = vals[(0,) * self.sd]
+        dv = [vals[a] for a in planmod.multi_indices(self.sd, 1)]
+        if not nested:
+            return v, dv
+        vh, dvh = v.cpu().numpy(), [d.cpu().numpy() for d in dv]
+        return [[(vh[i, j], [d[i, j] for d in dvh]) for j in range(vh.shape[1])] for i in range(vh.shape[0])]
+
+    # -- ExpansionSet.tabulate_jet(n, pts, order) -----------------------------------------------------------------
+    def tabulate_jet(self, pts, order=1):
+        """[v0, v1, ..., v_order] with v_r of shape (num_members, npts) + (sd,) * r:
+        v_r[i, j, k1, ..., kr] = d^r phi_i / dx_k1 ... dx_kr (pts[j])."""
+        vals = self.tab.tabulate(order, pts)
+        sd = self.sd
+        v0 = vals[(0,) * sd]
+        data = [v0]
+        for r in range(1, order + 1):
+            vr = torch.empty((sd,) * r + tuple(v0.shape), dtype=v0.dtype, device=v0.device)
+            for index in numpy.ndindex(*((sd,) * r)):
+                vr[index] = vals[tuple(index.count(k) for k in range(sd))]
+            data.append(vr.permute((r, r + 1) + tuple(range(r))))
+        return data
+
+    # -- ExpansionSet.get_dmats(degree, cell) -----------------------------------------------------------------------
+    def _cell_tabulator(self, cell):
+        """_tabulate_on_cell(..., cell=cell): the single-cell set of one subcell (its affine map, scale, members)."""
+        if cell not in self._cells:
+            d = self.desc
+            nmem = numpy.asarray(d["cell_node_map"]).shape[1]
+            single = {k: v for k, v in d.items() if k not in ("bary_A", "bary_b", "nodes")}
+            single.update(ncells=1, cell_A=d["cell_A"][cell:cell + 1], cell_b=d["cell_b"][cell:cell + 1],
+                          cell_scale=d["cell_scale"][cell:cell + 1], nexp_total=nmem,
+                          cell_node_map=numpy.arange(nmem, dtype=numpy.int64)[None, :],
+                          coeffs=numpy.eye(nmem).reshape(nmem, 1, nmem))
+            for key in ("ll_nodes", "ll_wts", "ll_dmat"):
+                if key in d:
+                    single[key] = d[key][cell:cell + 1]
+            self._cells[cell] = Tabulator(single, self.device)
+        return self._cells[cell]
+
+    def get_dmats(self, lattice_points, cell=0):
+        """dmat[k, j, i] with d/dx_k phi_j = sum_i dmat[k, j, i] phi_i, from the tabulation at `lattice_points`
+        (the reference takes make_lattice(verts, degree, variant="gl")); the solve runs on the device."""
+        sd = self.sd
+        if self.n == 0:
+            return torch.zeros((sd, 1, 1), dtype=torch.float64, device=self.device)
+        v = self._cell_tabulator(cell).tabulate(1, lattice_points)
+        rhs = torch.stack([v[a].T for a in planmod.multi_indices(sd, 1)])
+        return torch.linalg.solve(v[(0,) * sd].T.unsqueeze(0).expand(sd, -1, -1), rhs)
+
+    # -- ExpansionSet.tabulate_jumps(n, points, order) --------------------------------------------------------------
+    def tabulate_jumps(self, points, order=0):
+        """{r: tensor (num_members, len(mis(sd, r)) * num_jumps)}: jumps of the order-r derivatives across the
+        interior facets of the complex at the points lying on them.  Point-to-subcell assignment: the device binning
+        (bit-exact with compute_cell_point_map, unique=False)."""
+        es, sd = self.es, self.sd
+        complex_ = es.ref_el
+        pts = numpy.ascontiguousarray(numpy.asarray(points, dtype=numpy.float64)).reshape(-1, sd)
+        num_members = int(es.get_num_members(self.n))
+        cell_node_map = es.get_cell_node_map(self.n)
+        if int(self.desc["ncells"]) > 1:
+            mask = self.tab.locate_subcells(pts, unique=False).cpu().numpy().astype(numpy.int64)
+        else:
+            mask = numpy.ones(len(pts), dtype=numpy.int64)
+        ncells = int(self.desc["ncells"])
+        cell_point_map = {c: numpy.flatnonzero((mask >> c) & 1) for c in range(ncells)}
+        cell_point_map = {c: ip for c, ip in cell_point_map.items() if len(ip)}
+        num_jumps, facet_point_map = 0, {}
+        for facet in complex_.get_interior_facets(sd - 1):
+            try:
+                cells = complex_.connectivity[(sd - 1, sd)][facet]
+                ipts = list(set.intersection(*(set(cell_point_map[c].tolist()) for c in cells)))
+                if ipts != ():
+                    facet_point_map[facet] = ipts
+                    num_jumps += len(ipts)
+            except KeyError:
+                pass
+        dpts = torch.as_tensor(pts, device=self.device)
+        derivs = {c: self._cell_tabulator(c).tabulate(order, dpts) for c in cell_point_map}
+        jumps = {}
+        for r in range(order + 1):
+            cur = 0
+            alphas = planmod.multi_indices(sd, r)
+            jr = torch.zeros((num_members, len(alphas) * num_jumps), dtype=torch.float64, device=self.device)
+            for facet, ipts in facet_point_map.items():
+                c0, c1 = complex_.connectivity[(sd - 1, sd)][facet]
+                cols = torch.as_tensor(ipts, device=self.device, dtype=torch.long)
+                for alpha in alphas:
+                    rows1 = torch.as_tensor(numpy.asarray(cell_node_map[c1]), device=self.device, dtype=torch.long)
+                    rows0 = torch.as_tensor(numpy.asarray(cell_node_map[c0]), device=self.device, dtype=torch.long)
+                    block = slice(cur, cur + len(ipts))
+                    jr[rows1, block] += derivs[c1][alpha][:, cols]
+                    jr[rows0, block] -= derivs[c0][alpha][:, cols]
+                    cur += len(ipts)
+            jumps[r] = jr
+        return jumps

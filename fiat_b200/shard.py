@@ -8,7 +8,7 @@ timings); the functions below are backend-agnostic so the host logic is tested w
 """
 import torch.distributed as dist
 
-__all__ = ["shard_range", "tabulate_shard", "max_over_ranks"]
+__all__ = ["shard_range", "tabulate_shard", "max_over_ranks", "tabulate_sharded", "gather_shards"]
 
 
 def shard_range(npts, rank, world):
@@ -42,3 +42,40 @@ def max_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def tabulate_sharded(element, order, points, entity=None, devices=None):
+    """ONE point array over several GPUs of this process ("API returns per-device dicts").
+
+    `points` (host array or tensor, (npts, dim)) is split into contiguous shards with `shard_range`; shard g is
+    copied to device g and tabulated there with that device's own plan.  Every launch is asynchronous, so the
+    devices work concurrently; nothing is gathered.  Returns [(device, start, stop, {alpha: tensor on that device
+    (ndofs, *value_shape, stop - start)})], one entry per device in shard order."""
+    import numpy
+    import torch
+    from .api import get_tabulator
+    if devices is None:
+        devices = [torch.device("cuda", i) for i in range(torch.cuda.device_count())]
+    devices = [torch.device(d) for d in devices]
+    if not devices:
+        raise RuntimeError("tabulate_sharded needs at least one CUDA device (there is no CPU fallback)")
+    if not isinstance(points, torch.Tensor):
+        points = torch.as_tensor(numpy.ascontiguousarray(numpy.asarray(points, dtype=numpy.float64)))
+    npts = points.shape[0]
+    out = []
+    for g, dev in enumerate(devices):
+        start, stop = shard_range(npts, g, len(devices))
+        shard = points[start:stop].to(device=dev, dtype=torch.float64, non_blocking=True)
+        with torch.cuda.device(dev):
+            out.append((dev, start, stop, get_tabulator(element, dev).tabulate(order, shard, entity)))
+    return out
+
+
+def gather_shards(shards, device=None):
+    """Concatenate the per-device blocks of `tabulate_sharded` along the point axis on one device (peer copies over
+    NVLink when the devices are peers).  For checks and small problems only: at BASELINE sizes the logically global
+    array does not fit on one GPU."""
+    import torch
+    device = torch.device(device) if device is not None else shards[0][0]
+    keys = list(shards[0][3].keys())
+    return {a: torch.cat([tab[a].to(device) for _, _, _, tab in shards], dim=-1) for a in keys}

@@ -149,3 +149,28 @@ def test_live_reference_masks_on_fresh_adversarial_points(cuda_device):
                 want[ipts] |= 1 << c
             mask = tab.locate_subcells(pts, unique).cpu().numpy().astype(numpy.int64)
             assert numpy.array_equal(mask, want), (type(element).__name__, unique, ncells)
+
+
+@pytest.mark.parametrize("workload", ["p8_tet_o2", "hct_o2", "gll_q10_hex_o1"])
+def test_one_point_array_sharded_over_the_devices(workload, cuda_device):
+    """SURVEY 8e on hardware: ONE point array split contiguously over all visible GPUs of this process
+    (fiat_b200.tabulate_sharded), every shard tabulated on its own device with its own plan; the gathered blocks equal
+    the single-device tables bit for bit and the shard boundaries follow shard_range.  Runs with the devices the box
+    has (one device: a single shard)."""
+    import bench
+    import fiat_b200
+    dname, order, kind, _ = bench.WORKLOADS[workload]
+    desc = bench.load_desc(dname)
+    ndev = torch.cuda.device_count()
+    npts = 4099 if workload != "gll_q10_hex_o1" else 1031          # not divisible by the device count
+    pts = bench.host_points(kind, npts, 31)
+    shards = fiat_b200.tabulate_sharded(desc, order, pts)
+    assert len(shards) == ndev
+    assert [(s, e) for _, s, e, _ in shards] == [fiat_b200.shard_range(npts, g, ndev) for g in range(ndev)]
+    for g, (dev, s, e, tab) in enumerate(shards):
+        assert dev.index == g and all(v.device == dev and v.shape[-1] == e - s for v in tab.values())
+    whole = fiat_b200.api.get_tabulator(desc, cuda_device).tabulate(order, pts)
+    gathered = fiat_b200.gather_shards(shards, cuda_device)
+    assert list(gathered) == list(whole)
+    for a in whole:
+        assert torch.equal(gathered[a], whole[a])

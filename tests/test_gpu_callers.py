@@ -1,0 +1,152 @@
+"""Callers either side of the hot path: the FInAT caller's re-shaped tables (rank 2) and the
+reference's setup-path tabulations of an expansion set (rank 4), device results against the reference."""
+import numpy
+import pytest
+import torch
+
+from conftest import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference():
+    from oracle.make_ref import import_reference
+    FIAT = import_reference()
+    if FIAT is None:
+        pytest.skip("oracle/_ref has not been materialised")
+    return FIAT
+
+
+@pytest.mark.parametrize("name,order", [("p3_tri_o1", 5), ("p1_tri_o2", 2), ("n2curl4_tet_o1", 1), ("dg3_tri_o1", 4),
+                                        ("p4_line_o2", 5), ("bdm2_tet_o1", 3)])
+def test_basis_evaluation_shapes_and_contracts(name, order, cuda_device):
+    """finat/fiat_elements.py:60-123 restated with numpy on the oracle's tables: point axis dropped for |alpha| ==
+    degree on a simplex (cell-wise constant), zero table above the degree, index + value + point shape below."""
+    from fiat_b200.finat_adapter import basis_evaluation
+    from oracle import fiat_oracle
+    case = load_case(name)
+    desc = case["desc"]
+    pts = numpy.asarray(case["points"], dtype=float)[:12]
+    want = fiat_oracle.tabulate(desc, order, pts)
+    degree = int(desc["degree"])
+    got = basis_evaluation(desc, order, pts, device=cuda_device, point_shape=(3, 4))
+    assert list(got) == list(want)
+    for alpha, table in want.items():
+        g = got[alpha].cpu().numpy()
+        if sum(alpha) == degree:
+            assert numpy.allclose(table, table[..., 0, None], atol=1e-9 * max(abs(table).max(), 1.0))
+            expect = table[..., 0]
+        elif sum(alpha) > degree:
+            assert not table.any()
+            expect = numpy.zeros(table.shape[:-1])
+        else:
+            expect = table.reshape(table.shape[:-1] + (3, 4))
+        assert g.shape == expect.shape, (alpha, g.shape, expect.shape)
+        assert abs(g - expect).max() <= 1e-11 * max(abs(expect).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", ["gll_q10_hex_o1", "q2_quad_o2", "p2xp1_prism_o1", "rt2xp1_prism_vector_o1"])
+def test_factor_evaluations_merge_to_the_reference_table(name, cuda_device):
+    """finat/tensor_product.py:98-144: factors stay unmultiplied; their numeric product is the reference's table
+    with the factors' basis indices flattened dof-major."""
+    from fiat_b200.finat_adapter import factor_evaluations, merge_evaluations
+    case = load_case(name)
+    factors = factor_evaluations(case["desc"], case["order"], case["points"], case["entity"], device=cuda_device)
+    merged = merge_evaluations(factors, case["order"])
+    assert [tuple(k) for k in merged] == [tuple(k) for k in case["ref"]]
+    nbasis = len(factors)
+    for alpha, ref in case["ref"].items():
+        m = merged[alpha]
+        flat = m.reshape((-1,) + tuple(m.shape[nbasis:])).cpu().numpy()
+        assert flat.shape == ref.shape
+        assert abs(flat - ref).max() <= 1e-12 * max(abs(ref).max(), 1e-300)
+
+
+def _sets(FIAT):
+    from FIAT import expansions, macro
+    from FIAT.reference_element import ufc_simplex, UFCInterval
+    T1, T2, T3 = UFCInterval(), ufc_simplex(2), ufc_simplex(3)
+    return [
+        ("tri_none", expansions.ExpansionSet(T2), 5),
+        ("tet_bubble_c0", expansions.ExpansionSet(T3, variant="bubble"), 4),
+        ("line_legendre", expansions.ExpansionSet(T1), 6),
+        ("alfeld_tri_c0", expansions.ExpansionSet(macro.AlfeldSplit(T2), variant="bubble"), 3),
+        ("ps12_dg", expansions.ExpansionSet(macro.PowellSabin12Split(T2)), 2),
+        ("alfeld_tet_c0", expansions.ExpansionSet(macro.AlfeldSplit(T3), variant="bubble"), 3),
+    ]
+
+
+def _points(es, rng, n=60):
+    sd = es.ref_el.get_spatial_dimension()
+    if sd == 1:
+        return rng.random((n, 1))
+    u = numpy.sort(rng.random((n, sd)), axis=1)
+    return numpy.diff(numpy.concatenate([numpy.zeros((n, 1)), u], axis=1), axis=1)
+
+
+def test_expansion_set_tabulations_match_the_reference(cuda_device):
+    """ExpansionSet.tabulate / tabulate_derivatives / tabulate_jet (FIAT/expansions.py:601-637) on the device."""
+    from fiat_b200.setup_path import ExpansionTabulator
+    FIAT = _reference()
+    rng = numpy.random.default_rng(21)
+    for label, es, n in _sets(FIAT):
+        pts = _points(es, rng)
+        dev = ExpansionTabulator(es, n, cuda_device)
+        v = es.tabulate(n, pts)
+        assert abs(dev.tabulate(pts).cpu().numpy() - v).max() <= 1e-12 * abs(v).max(), label
+        assert dev.tabulate(pts[:0]).numel() == 0
+        nested = es.tabulate_derivatives(n, pts)
+        got = dev.tabulate_derivatives(pts, nested=True)
+        scale = max(abs(numpy.array([[d for _, d in row] for row in nested])).max(), 1.0)
+        for i in range(len(nested)):
+            for j in range(len(nested[0])):
+                assert abs(got[i][j][0] - nested[i][j][0]) <= 1e-12 * scale
+                assert numpy.allclose(got[i][j][1], nested[i][j][1], rtol=0, atol=1e-12 * scale)
+        for order in (1, 2):
+            want = es.tabulate_jet(n, pts, order=order)
+            jet = dev.tabulate_jet(pts, order=order)
+            assert len(jet) == len(want)
+            for w, g in zip(want, jet):
+                assert tuple(g.shape) == w.shape, label
+                assert abs(g.cpu().numpy() - w).max() <= 1e-12 * max(abs(w).max(), 1e-300), label
+
+
+def test_expansion_set_jumps_match_the_reference(cuda_device):
+    """ExpansionSet.tabulate_jumps (FIAT/expansions.py:532-575): derivative jumps across interior facets at points on
+    them (the reference's C^k macro constructions integrate these), device binning and per-subcell tabulation."""
+    from fiat_b200.setup_path import ExpansionTabulator
+    FIAT = _reference()
+    rng = numpy.random.default_rng(22)
+    for label, es, n in _sets(FIAT):
+        complex_ = es.ref_el
+        if not complex_.is_macrocell():
+            continue
+        sd = complex_.get_spatial_dimension()
+        top = complex_.get_topology()
+        verts = numpy.array(complex_.get_vertices())
+        pts = []
+        for f in complex_.get_interior_facets(sd - 1):
+            fv = verts[list(top[sd - 1][f])]
+            pts += list(rng.dirichlet(numpy.ones(sd), size=5) @ fv)
+        pts = numpy.array(pts + list(_points(es, rng, 7)))
+        want = es.tabulate_jumps(n, pts, order=2)
+        got = ExpansionTabulator(es, n, cuda_device).tabulate_jumps(pts, order=2)
+        assert sorted(got) == sorted(want)
+        for r in want:
+            assert tuple(got[r].shape) == want[r].shape, (label, r)
+            assert abs(got[r].cpu().numpy() - want[r]).max() <= 1e-11 * max(abs(want[r]).max(), 1.0), (label, r)
+
+
+def test_dmats_match_the_reference(cuda_device):
+    """ExpansionSet.get_dmats (FIAT/expansions.py:577-599) from the device tabulation at the same lattice."""
+    from fiat_b200.setup_path import ExpansionTabulator
+    FIAT = _reference()
+    from FIAT import reference_element
+    for label, es, n in _sets(FIAT)[:3]:
+        D = es.ref_el.get_dimension()
+        verts = es.ref_el.get_vertices_of_subcomplex(es.ref_el.get_topology()[D][0])
+        lattice = numpy.array(reference_element.make_lattice(verts, n, variant="gl"))
+        want = es.get_dmats(n)
+        got = ExpansionTabulator(es, n, cuda_device).get_dmats(lattice).cpu().numpy()
+        assert got.shape == want.shape
+        assert abs(got - want).max() <= 1e-9 * max(abs(want).max(), 1.0), label
