@@ -352,6 +352,7 @@ def run_leg(workload, device, sampler, batch=None, flags=0, steps=10, parity_pts
     vpp, sd = values_per_point(desc, order)
     batch = batch or default_batch(workload, vpp)
     na = len(planmod.alpha_list(sd, order))
+    time.sleep(1.0)          # every leg starts from an idle GPU, like the headline (power / clocks settle)
     t0 = time.perf_counter()
     tab = Tabulator(desc, device)
     pts = device_points(kind, batch, 4242, device)
@@ -435,6 +436,7 @@ def main():
     ap.add_argument("--e2e-points", type=int, default=1 << 16)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-points", type=int, default=100000)
+    ap.add_argument("--eval-functions", type=int, default=1, help="functions evaluated by the e2e_evaluate leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity leg")
     ap.add_argument("--no-legs", action="store_true", help="skip other_workloads / latency legs")
     args = ap.parse_args()
@@ -526,13 +528,14 @@ def main():
     # ---- fused consumer end to end: host points in, nfunc x npts function values / derivatives out ----
     e2e_eval = None
     if hasattr(tab, "evaluate_host"):
-        nfunc = 4
-        ndofs = vpp // na
+        nfunc = args.eval_functions
+        ndofs = planmod.num_dofs_of(desc)
         coef = numpy.random.default_rng(17).standard_normal((nfunc, ndofs))
         neval = min(1 << 20, tile)
         epts = torch.empty((neval, sd), dtype=torch.float64, pin_memory=True)
         epts.copy_(tiles[0][0][:neval].cpu())
-        eout = torch.empty((na, nfunc, neval), dtype=torch.float64, pin_memory=True)
+        ncomp = vpp // (na * ndofs)
+        eout = torch.empty((na, nfunc * ncomp, neval), dtype=torch.float64, pin_memory=True)
         for _ in range(2):
             tab.evaluate_host(coef, order, epts.numpy(), out=eout.numpy())
         barrier()
@@ -546,7 +549,7 @@ def main():
             secs = float(t.item())
         e2e_eval = {"value": world * neval / secs, "unit": "points/s", "functions": nfunc, "points_per_step": neval,
                     "tabulated_values_equivalent_per_s": world * neval * vpp / secs,
-                    "h2d_bytes_per_step": int(neval * sd * 8 + coef.size * 8), "d2h_bytes_per_step": int(na * nfunc * neval * 8),
+                    "h2d_bytes_per_step": int(neval * sd * 8 + coef.size * 8), "d2h_bytes_per_step": int(na * nfunc * ncomp * neval * 8),
                     "what": "Tabulator.evaluate_host: u_f = sum_i c[f,i] D^alpha phi_i at host points, host result; "
                             "the (ndofs x npts) tables are never written"}
 

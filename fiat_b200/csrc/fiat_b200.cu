@@ -153,7 +153,9 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
         // (value-only tables, na == 1: 64-point tiles with half-width work items are allowed so that the large
         // derived elements -- P8 tet: 168 members -- still get two resident CTAs whose phases overlap)
         const int pt_half = P.na == 1 ? 4 * go : 8 * go;
-        const int pt_min = pass == 0 ? std::max(32, pt_half) : (tune.mma_pt >= 0 ? pt_half : 8 * go);
+        // (measured on P8 tet order 2, 168 members: 64-point tiles with two CTAs per SM 6.16 ms, one 128-point CTA
+        // 5.82 ms -- half-width items double the per-DMMA overhead -- so half-width tiles are taken on request only)
+        const int pt_min = pass == 0 ? std::max(32, 8 * go) : (tune.mma_pt >= 0 ? pt_half : 8 * go);
         if (pass == 0 && tune.mma_pt >= 0) continue;     // an explicit tile width is taken as is
         for (int pt = pt_max; pt >= pt_min; pt >>= 1) {
             int ld = P.na * pt;

@@ -141,7 +141,7 @@ struct MmaGeom {
     int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)
     int logPT;     // log2(PT)
     int maxlev;    // most recurrence steps in one wavefront level
-    int skip;      // profiling only: bit 0 skips the recurrence, bit 1 the contraction
+    int skip;      // profiling only: bit 0 skips the recurrence, bit 1 the contraction, bit 2 the B-fragment loads, bit 3 the stores
 };
 #define FB_MMA_THREADS 512
 
@@ -291,7 +291,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                     for (int s = 0; s < GO * NA; ++s) {
                         // column block of (octet s / NA past oct0, alpha s % NA); GO is a multiple of OPG or 1
                         const int o = s / NA, a = s % NA;
-                        bfrag[s] = Tb[(o / OPG) * (PW * NA) + (o % OPG) * 8 + a * PW];
+                        bfrag[s] = (G.skip & 4) ? a_cur[j] : Tb[(o / OPG) * (PW * NA) + (o % OPG) * 8 + a * PW];   // bit 2: profiling, no B loads
                     }
 #pragma unroll
                     for (int s = 0; s < GO * NA; ++s)
@@ -306,6 +306,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         const long long p0 = base + oct0 * 8 + 2 * t;
         // warp-uniform: a full 8-row x GO-octet tile with aligned rows and no placement map
         const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows;
+        if (G.skip & 8) continue;                           // profiling only: no stores
         if (full_tile) {
             // trade fragments between lane groups g and g^4 so that one store instruction covers
             // 4 rows x 128 contiguous bytes (two octets) instead of 8 rows x 64 bytes
