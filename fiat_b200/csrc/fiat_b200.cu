@@ -137,7 +137,6 @@ int dispatch_cellwise(const fiatb200_plan* plan, const DevSimplex& P, const DevE
 // ---- tile / DMMA launch ------------------------------------------------------------------------
 bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGeom* G, size_t* smem_out) {
     if (P.ncells != 1 || P.expansion != 0 || P.order > 3 || P.nblk == 0 || nrb == 0) return false;
-    // one CTA per SM: the widest tile whose expansion table fits in shared memory
     const size_t budget = (size_t)plan->max_smem_optin - 1024;
     int pt_max = 128;
     const FbTuning& tune = fb_tuning();
@@ -146,27 +145,39 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
     int maxlev = 1;
     for (int l = 0; l < plan->tab.nlevels; ++l)
         maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
-    // first choice: a tile of >= 32 points small enough for two resident CTAs (256 threads each, see
-    // launch_mma); otherwise the widest tile that fits one CTA per SM
+    // first choice: a tile of >= 32 points small enough for two resident CTAs of 256 threads (one CTA's recurrence /
+    // tail overlaps the other's contraction); otherwise the widest tile that fits one CTA of 512 threads per SM.
+    // Value-only tables (na == 1) stage their stores for bulk copies when shared memory allows: whole 128-point rows
+    // (sto = 16 octets) or 32-point pieces (sto = 4); the staging rows alias the phase-1 scratch.
     for (int pass = 0; pass < 2; ++pass) {
         const size_t limit = pass == 0 ? (size_t)110 * 1024 : budget;
-        // (value-only tables, na == 1: 64-point tiles with half-width work items are allowed so that the large
-        // derived elements -- P8 tet: 168 members -- still get two resident CTAs whose phases overlap)
-        const int pt_half = P.na == 1 ? 4 * go : 8 * go;
-        // (measured on P8 tet order 2, 168 members: 64-point tiles with two CTAs per SM 6.16 ms, one 128-point CTA
-        // 5.82 ms -- half-width items double the per-DMMA overhead -- so half-width tiles are taken on request only)
-        const int pt_min = pass == 0 ? std::max(32, 8 * go) : (tune.mma_pt >= 0 ? pt_half : 8 * go);
-        if (pass == 0 && tune.mma_pt >= 0) continue;     // an explicit tile width is taken as is
+        const int pt_min = pass == 0 ? std::max(32, 8 * go) : 8 * go;
+        if (pass == 0 && (tune.mma_pt >= 0 || tune.mma_threads >= 512)) continue;
+        if (pass == 1 && tune.mma_threads >= 0 && tune.mma_threads < 512 && tune.mma_pt < 0) { /* forced 256: still allowed here */ }
+        const int threads = pass == 0 ? 256 : (tune.mma_threads >= 0 && tune.mma_threads < 512 ? 256 : 512);
         for (int pt = pt_max; pt >= pt_min; pt >>= 1) {
             int ld = P.na * pt;
             while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
-            const size_t bytes = ((size_t)P.kpad * ld + 6 * pt) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
+            const size_t table = (size_t)P.kpad * ld * sizeof(double);
+            const size_t scratch = (size_t)6 * pt * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
+            int sto = 0;
+            if (P.na == 1 && pt == 8 * go && tune.stage != 0) {
+                for (int cand : {16, 4}) {
+                    if (tune.stage > 0 && cand != tune.stage) continue;
+                    const size_t stage = (size_t)(threads / 32) * 8 * (8 * cand + 8) * sizeof(double);
+                    if (table + std::max(scratch, stage) <= limit) { sto = cand; break; }
+                }
+            }
+            const size_t stage = sto ? (size_t)(threads / 32) * 8 * (8 * sto + 8) * sizeof(double) : 0;
+            const size_t bytes = table + std::max(scratch, stage);
             if (bytes <= limit) {
                 G->PT = pt;
                 G->logPT = 0;
                 while ((1 << G->logPT) < pt) ++G->logPT;
                 G->ldT = ld;
                 G->maxlev = maxlev;
+                G->sto = sto;
+                G->threads = threads;
                 G->skip = 0;
                 if (tune.mma_skip >= 0) G->skip = tune.mma_skip;    // profiling only
                 *smem_out = bytes;
@@ -177,18 +188,13 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
     return false;
 }
 
-template <int SD, int ORDER, int PW, int GOSHIFT>
+template <int SD, int ORDER, int PW, int STO>
 int launch_mma_pw(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                   long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    int rc = fb_set_smem(k_mma<SD, ORDER, PW, GOSHIFT>, smem);
+    int rc = fb_set_smem(k_mma<SD, ORDER, PW, STO>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
-    int threads = FB_MMA_THREADS;
-    // tables small enough for two resident CTAs: run them with 256 threads each so that one CTA's
-    // recurrence / tail overlaps the other's contraction
-    if (smem <= 110 * 1024) threads = 256;
-    if (fb_tuning().mma_threads >= 0) threads = fb_tuning().mma_threads >= 512 ? 512 : 256;
-    k_mma<SD, ORDER, PW, GOSHIFT><<<grid, threads, smem, st>>>(P, tab, E, G, pts, npts, ldp, out, ostride, M);
+    k_mma<SD, ORDER, PW, STO><<<grid, G.threads, smem, st>>>(P, tab, E, G, pts, npts, ldp, out, ostride, M);
     fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -197,8 +203,8 @@ int launch_mma_pw(const DevSimplex& P, const RecTab& tab, const DevEntity& E, co
 template <int SD, int ORDER>
 int launch_mma(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    if (ORDER == 0 && G.PT < 8 * fb_mma_go(1))          // 64-point tile of a value-only table
-        return launch_mma_pw<SD, 0, 16, 1>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    if (ORDER == 0 && G.sto == 16) return launch_mma_pw<SD, 0, 16, 16>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    if (ORDER == 0 && G.sto == 4) return launch_mma_pw<SD, 0, 16, 4>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
     if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16, 0>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
     return launch_mma_pw<SD, ORDER, 8, 0>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
 }

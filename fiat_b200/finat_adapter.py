@@ -63,7 +63,7 @@ def basis_evaluation(element, order, points, entity=None, degree=None, point_sha
                     raise AssertionError("tabulation of the top derivative is not cell-wise constant")
             result[alpha] = table[..., 0] if npts else table.new_zeros(index_shape + vs)
         elif derivative > degree:
-            if check and npts and float(table.abs().max()) != 0.0:
+            if check and npts and float(table.abs().max()) > 1e-8:        # numpy.allclose(table, 0.0), as the reference asserts
                 raise AssertionError("tabulation above the degree is not zero")
             result[alpha] = table.new_zeros(index_shape + vs)
         else:
