@@ -24,6 +24,7 @@ const FbTuning& fb_tuning() {
         v.vals_tpc = geti("FIATB200_VALS_TPC");
         v.vals_j = geti("FIATB200_VALS_J");
         v.stage = geti("FIATB200_MMA_STAGE");
+        v.mma_wl = geti("FIATB200_MMA_WARPLOCAL");
         return v;
     }();
     return t;
@@ -147,8 +148,6 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
         maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
     // first choice: a tile of >= 32 points small enough for two resident CTAs of 256 threads (one CTA's recurrence /
     // tail overlaps the other's contraction); otherwise the widest tile that fits one CTA of 512 threads per SM.
-    // Value-only tables (na == 1) stage their stores for bulk copies when shared memory allows: whole 128-point rows
-    // (sto = 16 octets) or 32-point pieces (sto = 4); the staging rows alias the phase-1 scratch.
     for (int pass = 0; pass < 2; ++pass) {
         const size_t limit = pass == 0 ? (size_t)110 * 1024 : budget;
         const int pt_min = pass == 0 ? std::max(32, 8 * go) : 8 * go;
@@ -159,24 +158,20 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
             int ld = P.na * pt;
             while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
             const size_t table = (size_t)P.kpad * ld * sizeof(double);
-            const size_t scratch = (size_t)6 * pt * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
-            int sto = 0;
-            if (P.na == 1 && pt == 8 * go && tune.stage != 0) {
-                for (int cand : {16, 4}) {
-                    if (tune.stage > 0 && cand != tune.stage) continue;
-                    const size_t stage = (size_t)(threads / 32) * 8 * (8 * cand + 8) * sizeof(double);
-                    if (table + std::max(scratch, stage) <= limit) { sto = cand; break; }
-                }
-            }
-            const size_t stage = sto ? (size_t)(threads / 32) * 8 * (8 * sto + 8) * sizeof(double) : 0;
-            const size_t bytes = table + std::max(scratch, stage);
+            // warp-local recurrence (kernels.cuh) when the tile splits into 8 / 16 / 32 points per warp: its scratch
+            // is the full list of step records; otherwise recurrence factors + two levels of records
+            const int ppw_c = pt / (threads / 32);
+            const bool warp_local = tune.mma_wl != 0 && pt % (threads / 32) == 0 && (ppw_c == 8 || ppw_c == 16 || ppw_c == 32);
+            const size_t scratch = warp_local ? (size_t)plan->tab.nsteps * sizeof(StepRec)
+                                              : (size_t)6 * pt * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
+            const size_t bytes = table + scratch;
             if (bytes <= limit) {
                 G->PT = pt;
                 G->logPT = 0;
                 while ((1 << G->logPT) < pt) ++G->logPT;
                 G->ldT = ld;
                 G->maxlev = maxlev;
-                G->sto = sto;
+                G->ppw = warp_local ? ppw_c : 0;
                 G->threads = threads;
                 G->skip = 0;
                 if (tune.mma_skip >= 0) G->skip = tune.mma_skip;    // profiling only
@@ -188,13 +183,13 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
     return false;
 }
 
-template <int SD, int ORDER, int PW, int STO>
+template <int SD, int ORDER, int PW>
 int launch_mma_pw(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                   long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    int rc = fb_set_smem(k_mma<SD, ORDER, PW, STO>, smem);
+    int rc = fb_set_smem(k_mma<SD, ORDER, PW>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
-    k_mma<SD, ORDER, PW, STO><<<grid, G.threads, smem, st>>>(P, tab, E, G, pts, npts, ldp, out, ostride, M);
+    k_mma<SD, ORDER, PW><<<grid, G.threads, smem, st>>>(P, tab, E, G, pts, npts, ldp, out, ostride, M);
     fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -203,10 +198,8 @@ int launch_mma_pw(const DevSimplex& P, const RecTab& tab, const DevEntity& E, co
 template <int SD, int ORDER>
 int launch_mma(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    if (ORDER == 0 && G.sto == 16) return launch_mma_pw<SD, 0, 16, 16>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-    if (ORDER == 0 && G.sto == 4) return launch_mma_pw<SD, 0, 16, 4>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-    if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16, 0>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-    return launch_mma_pw<SD, ORDER, 8, 0>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    return launch_mma_pw<SD, ORDER, 8>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
 }
 
 template <int SD>

@@ -136,25 +136,12 @@ k_locate(const DevSimplex P, const DevEntity E, const double* __restrict__ pts, 
 // ---------------------------------------------------------------------------------------------
 // tile kernel with FP64 tensor-pipe contraction
 // ---------------------------------------------------------------------------------------------
-// Bulk asynchronous copy shared -> global (SASS UBLKCP): the finished piece of a table row leaves the SM as ONE
-// contiguous transfer issued by one lane; the warp goes straight back to the tensor pipe.
-__device__ __forceinline__ void fb_bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                 :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-// the staging buffer may be overwritten once the copies of the previous group have READ it
-__device__ __forceinline__ void fb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void fb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-// generic-proxy writes to shared memory -> visible to the async proxy that reads them
-__device__ __forceinline__ void fb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 struct MmaGeom {
     int PT;        // points per tile (multiple of 8)
     int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)
     int logPT;     // log2(PT)
     int maxlev;    // most recurrence steps in one wavefront level
-    int sto;       // octets per staged bulk store (0: direct stores; 4 or 16), see k_mma
+    int ppw;       // > 0: warp-local recurrence, points per warp (8, 16 or 32; tile = warps x ppw); 0: CTA-wide levels
     int threads;   // CTA size: 512 (one CTA per SM) or 256 (two)
     int skip;      // profiling only: bit 0 skips the recurrence, bit 1 the contraction, bit 3 the stores
 };
@@ -172,11 +159,7 @@ __host__ __device__ constexpr int fb_mma_go(int na) {
     return na >= 8 ? 1 : (na >= 5 ? 2 : (na >= 3 ? 4 : (na == 2 ? 8 : 16)));
 }
 
-// STO > 0 (value-only tables): finished 8-row x (8 STO)-point pieces are staged in shared memory and leave as bulk
-// asynchronous row copies (one lane issues them), so the stores overlap the next work item's DMMAs instead of
-// occupying the warp with 16 store + 96 shuffle / select instructions per item.  Measured before (2^20 points):
-// Nedelec 2nd kind deg 4 order 1 2.53 ms with, 1.80 ms without its stores (HBM floor 1.62 ms); P8 tet order 2 6.30 / 5.50.
-template <int SD, int ORDER, int PW, int STO>
+template <int SD, int ORDER, int PW>
 __global__ void __launch_bounds__(FB_MMA_THREADS, 1)
 k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const MmaGeom G,
       const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride,
@@ -192,8 +175,52 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     const int PT = G.PT;
     const long long base = (long long)blockIdx.x * PT;
 
-    // phase 0: points of the tile -> recurrence factors; member 0; zero padding rows
     if (tid == 0) s_next = 0;
+    if (G.ppw > 0) {
+        // phases 0 + 1, warp-local: a warp owns ppw consecutive points of the tile (tile = warps x ppw points) and runs
+        // the whole recurrence for them, level by level, with warp-level synchronisation only: lane = (step slot,
+        // point), the lane's recurrence factors stay in registers, all step records sit in shared memory.  The
+        // low wavefront levels have fewer (step, point) items than the CTA has threads, so the CTA-wide variant
+        // below pays one block barrier and one latency-bound round per level with most warps idle; here all warps
+        // run their own chains concurrently (P8 tet, 128-point tile: ~19k -> ~6k cycles per tile).
+        StepRec* s_all = reinterpret_cast<StepRec*>(s_fa);
+        for (int i = tid; i < tab.nsteps * 4; i += NT)
+            reinterpret_cast<double*>(s_all)[i] = reinterpret_cast<const double*>(tab.steps)[i];
+        for (int i = tid; i < (P.kpad - P.nslots) * G.ldT; i += NT) T[(size_t)P.nslots * G.ldT + i] = 0.0;
+        const int ppw = G.ppw, lane1 = tid & 31;
+        const int pl = (tid >> 5) * ppw + (lane1 & (ppw - 1));
+        long long p = base + pl;
+        if (p >= npts) p = npts - 1;                    // tail lanes repeat the last point, never stored
+        double x[3], xr[3] = {0.0, 0.0, 0.0};
+        apply_entity<SD>(E, pts + p * ldp, x);
+#pragma unroll
+        for (int i = 0; i < SD; ++i) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int d = 0; d < SD; ++d) sacc = fma(x[d], tab.geom0[i * SD + d], sacc);
+            xr[i] = sacc + tab.geom0[9 + i];
+        }
+        double fa[3], fb[3];
+        recurrence_factors<SD>(xr, fa, fb);
+        double* Tcol = T + (pl / PW) * (PW * NA) + (pl % PW);
+        if (lane1 < ppw) {
+            double* t0 = Tcol + (size_t)tab.start_slot * G.ldT;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) t0[a * PW] = (a == 0) ? tab.geom0[12] : 0.0;
+        }
+        __syncthreads();                                // step records staged
+        const int slot0 = lane1 / ppw, nslot = 32 / ppw;
+        for (int lev = 0; lev < ((G.skip & 1) ? 0 : tab.nlevels); ++lev) {
+            const int l0 = tab.level_ptr[lev], nst = tab.level_ptr[lev + 1] - l0;
+            for (int sl = slot0; sl < nst; sl += nslot) {
+                const StepRec r = s_all[l0 + sl];
+                run_step<SD, ORDER>(P, r, tab.geom0, fa, fb, Tcol, G.ldT, PW, NA);
+            }
+            __syncwarp();
+        }
+        __syncthreads();                                // every warp's columns are complete
+    } else {
+    // phase 0: points of the tile -> recurrence factors; member 0; zero padding rows
     if (tid < PT) {
         long long p = base + tid;
         if (p >= npts) p = npts - 1;                    // tail lanes repeat the last point, never stored
@@ -253,6 +280,8 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         __syncthreads();
     }
 
+    }
+
     // phase 2: out[row, col] = sum_k C[row, k] T[k, col] on the FP64 tensor pipe (the C0 fix-ups
     // are folded into C).  Work item = (8-row block, GO point octets): one coefficient fragment feeds
     // GO * NA DMMAs.  A block multiplies ANY four member slots (gather packing, plan.py: pack_blocks): the B
@@ -269,11 +298,22 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     const size_t astride = (size_t)M.total_rows * ostride;      // distance between derivative tables
     const double* Tlane = T + g;                        // + member slot * ldT, gathered per block
     const int ldT = G.ldT;
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(&s_next, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= nitems) break;
+    // Work items are handed out dynamically (longest row blocks first).  The NEXT item and its first coefficient
+    // fragments are fetched before the current item's stores are issued, so that the L2 latency of the fragments and
+    // the shared-memory atomic overlap the store epilogue instead of delaying the next item's first DMMA.
+    double a_cur[CH], a_nxt[CH];
+    int kb_cur = 0, kb_nxt = 0;
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&s_next, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item < nitems) {
+        const int rb0 = tab.rb_order[item / ngrp];
+        const int q0 = tab.blk_ptr[rb0], q1 = tab.blk_ptr[rb0 + 1];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
+        if (4 * q0 + lane < 4 * q1) kb_cur = __ldg(P.blk_kb + 4 * q0 + lane);
+    }
+    while (item < nitems) {
         const int rb = tab.rb_order[item / ngrp];
         const int oct0 = (item % ngrp) * GO;
         double acc[GO][NA][2];
@@ -282,12 +322,6 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
 #pragma unroll
             for (int s = 0; s < NA; ++s) acc[o][s][0] = acc[o][s][1] = 0.0;
         const int q0 = tab.blk_ptr[rb], q1 = tab.blk_ptr[rb + 1];
-        double a_cur[CH], a_nxt[CH];
-        // member slots of the CH blocks of a chunk: lane 4 j + t holds slot t of block j (one coalesced load)
-        int kb_cur = 0, kb_nxt = 0;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
-        if (4 * q0 + lane < 4 * q1) kb_cur = __ldg(P.blk_kb + 4 * q0 + lane);
         // octet o of the tile lives in point group o / (PW/8), at column offset (o % (PW/8)) * 8
         constexpr int OPG = PW / 8;                         // octets per point group
         const double* Titem = Tlane + (oct0 / OPG) * (PW * NA) + (oct0 % OPG) * 8;
@@ -321,39 +355,24 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
             for (int j = 0; j < CH; ++j) a_cur[j] = a_nxt[j];
             kb_cur = kb_nxt;
         }
+        // next item and its first fragments (a_nxt / kb_nxt are free after the last chunk)
+        int next = 0;
+        if (lane == 0) next = atomicAdd(&s_next, 1);
+        next = __shfl_sync(0xffffffffu, next, 0);
+        kb_nxt = 0;
+        if (next < nitems) {
+            const int rbn = tab.rb_order[next / ngrp];
+            const int n0 = tab.blk_ptr[rbn], n1 = tab.blk_ptr[rbn + 1];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) a_nxt[j] = (n0 + j < n1) ? __ldg(P.blk_frag + (size_t)(n0 + j) * 32 + lane) : 0.0;
+            if (4 * n0 + lane < 4 * n1) kb_nxt = __ldg(P.blk_kb + 4 * n0 + lane);
+        }
+        item = next;
         const int row = tab.row_perm[rb * 8 + g];           // table row of this lane's packed row (-1: padding)
         const long long p0 = base + oct0 * 8 + 2 * t;
         // warp-uniform: a full 8-row x GO-octet tile with aligned rows and no placement map
         const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows;
-        if (G.skip & 8) continue;                           // profiling only: no stores
-        if (STO > 0 && NA == 1 && vec_ok && M.identity && base + PT <= npts) {
-            // staging rows of 8 STO doubles + 8 doubles of padding: the two rows a quarter warp writes with one
-            // 16-byte store per lane fall into different halves of the 128-byte bank set (row stride = 64 mod 128)
-            constexpr int RS = 8 * STO + 8;
-            double* stage = s_fa + (size_t)(tid >> 5) * 8 * RS;         // aliases the recurrence factors (phase 1 only)
-#pragma unroll
-            for (int c0 = 0; c0 < GO; c0 += STO) {
-                if (lane == 0) fb_bulk_wait_read();
-                __syncwarp();
-#pragma unroll
-                for (int o = 0; o < STO; ++o)
-                    if (c0 + o < GO)
-                        *reinterpret_cast<double2*>(stage + g * RS + o * 8 + 2 * t) =
-                            make_double2(acc[(c0 + o) % GO][0][0], acc[(c0 + o) % GO][0][1]);
-                fb_fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    double* dst = out + base + (oct0 + c0) * 8;
-#pragma unroll 1
-                    for (int r = 0; r < 8; ++r) {
-                        const int orow = tab.row_perm[rb * 8 + r];
-                        if (orow >= 0) fb_bulk_store(dst + (size_t)orow * ostride, stage + r * RS, 64u * (STO < GO ? STO : GO));
-                    }
-                    fb_bulk_commit();
-                }
-            }
-            continue;
-        }
+        if (!(G.skip & 8)) {                                // (bit 3: profiling only, no stores)
         if (full_tile) {
             // trade fragments between lane groups g and g^4 so that one store instruction covers
             // 4 rows x 128 contiguous bytes (two octets) instead of 8 rows x 64 bytes
@@ -406,8 +425,11 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                 }
             }
         }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) a_cur[j] = a_nxt[j];
+        kb_cur = kb_nxt;
     }
-    if (STO > 0 && lane == 0) fb_bulk_wait_all();       // the staging rows must outlive the copies that read them
 }
 
 // ---------------------------------------------------------------------------------------------
