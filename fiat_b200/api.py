@@ -17,6 +17,7 @@ are cached per element and order.  There is no CPU fallback: unsupported element
 """
 import collections
 import ctypes
+import functools
 import threading
 import weakref
 
@@ -26,7 +27,7 @@ import torch
 from . import _lib, plan as planmod
 from .extract import describe_element, UnsupportedElement
 
-__all__ = ["tabulate", "tabulate_into", "tabulate_host", "locate_subcells", "Tabulator", "get_tabulator"]
+__all__ = ["tabulate", "tabulate_into", "tabulate_host", "locate_subcells", "Tabulator", "get_tabulator", "TraceError"]
 
 FORCE_THREAD_PER_POINT = 1
 FORCE_DMMA = 2
@@ -57,12 +58,42 @@ def _resolve_simplex_entity(desc, entity):
     return dim, (C, off)
 
 
+class TraceError(Exception):
+    """Tabulating a trace element on the interior of a cell, or its gradient (FIAT/hdiv_trace.py:25-31)."""
+
+    def __init__(self, msg):
+        super().__init__(msg)
+        self.msg = msg
+
+
+def _barycentric(points, vertices):
+    """FIAT/hdiv_trace.py:338-352."""
+    T = (numpy.asarray(vertices[:-1]) - vertices[-1]).T
+    bary = numpy.einsum("ij,kj->ki", numpy.linalg.inv(T), points - vertices[-1])
+    return numpy.concatenate([bary, (1 - bary.sum(axis=1))[:, None]], axis=1)
+
+
+def _extract_facets(coordinates, tolerance=1e-10):
+    """FIAT/hdiv_trace.py:306-335: every point must lie on exactly one facet; facet i excludes vertex i, except on the
+    interval, where point i is facet i."""
+    facet_to_pts = collections.defaultdict(list)
+    for ipt, c in enumerate(coordinates):
+        on_facet = [i for i, lam in enumerate(c) if abs(lam) < tolerance]
+        if len(on_facet) != 1:
+            return {}, False
+        facet_to_pts[on_facet[0]].append(ipt)
+    if coordinates.shape[1] == 2:
+        facet_to_pts[0], facet_to_pts[1] = facet_to_pts[1], facet_to_pts[0]
+    return facet_to_pts, True
+
+
 class _Plan:
     """Owns one device plan handle."""
 
     def __init__(self, handle, keep):
         self.handle = handle
         self.keep = keep
+        self.force_flags = 0        # library flags every launch of this plan carries (set by the self-check)
 
     def __del__(self):
         try:
@@ -125,7 +156,13 @@ class Tabulator:
                     int(desc["sd"]), int(desc["degree"]), order, keep[0].ctypes.data_as(_lib.p_i32), len(rowmap),
                     ctypes.byref(handle)))
             cand = _Plan(handle, keep)
-            if self._lattice_agrees(desc, order, cand):
+            # the product-form kernel only depends on (sd, degree, order): once it has reproduced the general kernel
+            # on this device the verdict is kept for the process, and later elements skip the general plan
+            vkey = (str(self.device), int(desc["sd"]), int(desc["degree"]), order)
+            verdict = _LATTICE_VERDICT.get(vkey)
+            if verdict is None:
+                verdict = _LATTICE_VERDICT[vkey] = self._lattice_agrees(desc, order, cand)
+            if verdict:
                 plan = cand
         with self._lock:
             self._plans[key] = plan
@@ -147,6 +184,62 @@ class Tabulator:
         scale = a.abs().amax(dim=(1, 2)).clamp_min(1e-300)
         err = (a - b).abs().amax(dim=(1, 2)) / scale
         return bool((err <= 1e-13).all().item())
+
+    def _self_check_flags(self, desc, order):
+        """On-device self-check of every path that replaces the derivative jets by host-folded derivative matrices
+        (value-table kernel, per-alpha / stacked derived elements, split-cell tile kernel): on first use the default
+        path and the thread-per-point jet kernel (FIAT/expansions.py:66-137 carried through the recurrence, no
+        derived matrix) tabulate 96 points of the cell; if any table differs by more than SELF_CHECK_TOL of its
+        largest entry the derived paths are switched off for this element and order.  -> flags to OR in."""
+        key = ("selfcheck", id(desc), order)
+        with self._lock:
+            if key in self._plans:
+                return self._plans[key]
+        verdict = 0
+        if desc["kind"] == "simplex" and desc["expansion"] == "dubiner" and int(desc["degree"]) >= 1 and order >= 0 \
+                and not desc.get("raw_members"):
+            sd = int(desc["sd"])
+            main, prog = self._simplex_plan(desc, order)
+            derived = [self.lib.fiatb200_plan_kernel(main.handle, 0) == 4]
+            derived.append(self._alpha_split_plans(desc, order, 0) is not None)
+            derived.append(self._macro_merged_plan(desc, order, 0) is not None)
+            if any(derived):
+                gen = torch.Generator(device="cpu")
+                gen.manual_seed(20261019)
+                lam = torch.rand((96, sd + 1), generator=gen, dtype=torch.float64) + 0.02
+                lam = lam / lam.sum(dim=1, keepdim=True)
+                verts = torch.as_tensor(numpy.asarray(desc["vertices"], dtype=numpy.float64)[:sd + 1])
+                pts = (lam @ verts).to(self.device).contiguous()
+                ent = _lib.entity_struct(sd, None)
+                ref = torch.empty((prog.na, prog.nrows, 96), dtype=torch.float64, device=self.device)
+                self._launch(main, ent, pts, ref, 96, FORCE_THREAD_PER_POINT)
+                got = torch.empty_like(ref)
+                self._run(self._default_launches(desc, order, ent), None, pts, got, 96, 96, 0)
+                scale = ref.abs().amax(dim=(1, 2)).clamp_min(1e-300)
+                err = (got - ref).abs().amax(dim=(1, 2)) / scale
+                if not bool((err <= SELF_CHECK_TOL).all().item()):
+                    verdict = NO_VALUE_TABLE | NO_ALPHA_SPLIT | NO_MACRO_MERGED
+                    main.force_flags = NO_VALUE_TABLE
+        with self._lock:
+            self._plans[key] = verdict
+        return verdict
+
+    def _default_launches(self, desc, order, ent):
+        """Launch list of the default (derived) path of one plain simplex element, as _resolve builds it."""
+        p, _ = self._simplex_plan(desc, order)
+        split = self._alpha_split_plans(desc, order, 0)
+        macro = self._macro_merged_plan(desc, order, 0)
+        if macro is not None:
+            p = macro
+        if split is None:
+            return [(p, ent, None, 0)]
+        if split[-1][0] == "merged":
+            return [(split[-1][1], ent, None, 0)]
+        out = []
+        for j, sub, _ in split:
+            if sub is not None:
+                out.append((sub, ent, None, j))
+        return out
 
     def _alpha_split_plans(self, desc, order, flags):
         """Per-alpha derived order-0 plans (plan.alpha_split) when the element would otherwise run on the DMMA
@@ -201,7 +294,7 @@ class Tabulator:
     def kernel_names(self, order, entity=None, flags=0):
         """Names of the kernels the launches of `tabulate(order, ...)` run on (diagnostics)."""
         launches = self._resolve(order, entity, flags)[0]
-        return [KERNEL_NAMES.get(self.lib.fiatb200_plan_kernel(p.handle, flags & 11), "?") if p is not None else "zero"
+        return [KERNEL_NAMES.get(self.lib.fiatb200_plan_kernel(p.handle, (flags & 11) | p.force_flags), "?") if p is not None else "zero"
                 for p, _, _, _ in launches]
 
     def kernel_path(self, order, flags=0):
@@ -293,6 +386,8 @@ class Tabulator:
                     fast = self._lattice_plan(d, order)
                     p = fast if fast is not None else p
                 if fast is None:
+                    if not flags & (FORCE_THREAD_PER_POINT | FORCE_DMMA | NO_VALUE_TABLE | NO_ALPHA_SPLIT | NO_MACRO_MERGED):
+                        flags |= self._self_check_flags(d, order)
                     split = self._alpha_split_plans(d, order, flags)
                     macro = self._macro_merged_plan(d, order, flags) if single else None
                     if macro is not None:
@@ -345,7 +440,86 @@ class Tabulator:
         pts = pts.reshape(-1, pdim) if pts.numel() or pts.ndim < 2 else pts.reshape(pts.shape[0], pdim)
         return pts.contiguous()
 
+    # -- elements that are not polynomial tabulations: HDivTrace, QuadratureElement ---------------------------------
+    def _tabulate_quadrature(self, order, points, entity):
+        """QuadratureElement.tabulate (FIAT/quadrature_element.py:43-61): the identity at its own points."""
+        d = self.desc
+        if entity is not None and tuple(entity) != (int(d["dim"]), 0):
+            raise ValueError('QuadratureElement does not "tabulate" on subentities.')
+        if order:
+            raise ValueError("Derivatives are not defined on a QuadratureElement.")
+        own = numpy.asarray(d["points"], dtype=float)
+        pts = numpy.asarray(points.cpu() if isinstance(points, torch.Tensor) else points, dtype=float).reshape(len(points), -1)
+        if len(pts) != len(own) or abs(pts - own).max() > 1e-12:
+            raise AssertionError("Mismatch of quadrature points!")
+        return {(0,) * int(d["sd"]): torch.eye(len(own), dtype=torch.float64, device=self.device)}
+
+    def _tabulate_trace(self, order, points, entity):
+        """HDivTrace.tabulate (FIAT/hdiv_trace.py:133-233): values only on facets -- the facet's discontinuous element
+        tabulated on the facet and written into that facet's rows; derivative slots hold TraceError objects, like
+        the reference.  entity=None identifies the facet of every point geometrically (simplices; tolerance 1e-10,
+        :22,316-335) on the host, then tabulates facet by facet on the device."""
+        d = self.desc
+        sd, ndofs = int(d["sd"]), int(d["ndofs"])
+        evalkey = (0,) * sd
+        if order < 0:
+            raise ValueError("order must be non-negative")
+        npts = len(points)
+        phivals = {}
+        for alpha in self.alphas(order):
+            phivals[alpha] = torch.zeros((ndofs, npts), dtype=torch.float64, device=self.device) if alpha == evalkey \
+                else TraceError("Gradients on trace elements are not well-defined.")
+        facet_sd = sd - 1
+        facets = d["facets"]
+
+        def fkey(f):
+            return tuple(f["dim"]) if isinstance(f["dim"], list) else f["dim"]
+
+        def facet_table(f, order_, pts_):
+            if f["element"]["kind"] == "point":       # constant on a point facet
+                vals = torch.as_tensor(numpy.asarray(f["element"]["values"], dtype=float), device=self.device)
+                return vals[:, None].expand(-1, len(pts_))
+            return get_tabulator(f["element"], self.device).tabulate(order_, pts_)[(0,) * facet_sd]
+
+        if entity is None or tuple(entity) == (sd, 0):
+            if not d["simplex"]:
+                raise NotImplementedError("Tabulating this element on a non-simplex cell without providing an entity "
+                                          "is not currently supported.")
+            pts = numpy.asarray(points.cpu() if isinstance(points, torch.Tensor) else points, dtype=float).reshape(npts, sd)
+            verts = numpy.asarray(d["vertices"], dtype=float)
+            bary = _barycentric(pts, verts)
+            facet_to_pts, success = _extract_facets(bary)
+            if not success:
+                for key in phivals:
+                    if entity is None:
+                        phivals[key] = torch.full((ndofs, npts), float("nan"), dtype=torch.float64, device=self.device)
+                    else:
+                        phivals[key] = TraceError("The HDivTrace element can only be tabulated on facets.")
+            (f,) = [f for f in facets if fkey(f) == facet_sd]
+            ref_verts = numpy.concatenate([numpy.zeros((1, facet_sd)), numpy.eye(facet_sd)]) if facet_sd else numpy.zeros((1, 0))
+            for facet, ipts in facet_to_pts.items():
+                coords = numpy.delete(bary[ipts], facet, axis=1)           # barycentric coordinates on the facet
+                new_points = coords @ ref_verts
+                vals = facet_table(f, order, new_points)
+                idx = torch.as_tensor(ipts, device=self.device, dtype=torch.long)
+                phivals[evalkey][f["nf"] * facet:f["nf"] * (facet + 1), idx] = vals
+            return phivals
+        edim = tuple(entity[0]) if isinstance(entity[0], (list, tuple)) else entity[0]
+        if not any(fkey(f) == edim for f in facets):
+            return {key: TraceError("The HDivTrace element can only be tabulated on facets.") for key in phivals}
+        offset = 0
+        for f in facets:
+            for i in range(f["count"]):
+                if (fkey(f), i) == (edim, int(entity[1])):
+                    phivals[evalkey][offset:offset + f["nf"]] = facet_table(f, 0, points)
+                offset += f["nf"]
+        return phivals
+
     def tabulate(self, order, points, entity=None, flags=0):
+        if self.kind == "quadrature":
+            return self._tabulate_quadrature(order, points, entity)
+        if self.kind == "trace":
+            return self._tabulate_trace(order, points, entity)
         launches, nrows, pdim, prefix, zero = self._resolve(order, entity, flags)
         pts = self._points(points, pdim)
         npts = pts.shape[0]
@@ -387,7 +561,7 @@ class Tabulator:
                     continue
                 _lib.check(self.lib.fiatb200_tabulate_mapped(
                     p.handle, ctypes.byref(ent) if ent is not None else None, pts.data_ptr(), npts, ld,
-                    optr, row_stride, ctypes.byref(rmap) if rmap is not None else None, cflags, stream))
+                    optr, row_stride, ctypes.byref(rmap) if rmap is not None else None, cflags | p.force_flags, stream))
 
     def _launch(self, p, ent, pts, out, npts, flags, row_stride=None):
         self._run([(p, ent, None, 0)], None, pts, out, npts, npts if row_stride is None else row_stride, flags)
@@ -409,7 +583,7 @@ class Tabulator:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.fiatb200_tabulate_host(
                     p.handle, ctypes.byref(ent) if ent is not None else None, pts.ctypes.data, npts, pdim,
-                    out.ctypes.data, chunk_pts, flags & 11))
+                    out.ctypes.data, chunk_pts, (flags & 11) | p.force_flags))
         elif npts:
             # wrapper elements / per-alpha splits: the launch list goes through the same staged pipeline
             arr = (_lib.LaunchStruct * len(launches))()
@@ -425,7 +599,8 @@ class Tabulator:
                 _lib.check(self.lib.fiatb200_tabulate_host_list(
                     arr, len(launches), len(alphas), nrows, zero.data_ptr() if zero is not None else None,
                     zero.numel() if zero is not None else 0, pts.ctypes.data, npts, pdim, out.ctypes.data, chunk_pts,
-                    flags & 11))
+                    (flags & 11) | functools.reduce(lambda a, b: a | b, (p.force_flags for p, _, _, _ in launches
+                                                                         if p is not None), 0)))
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
     def tabulate_factors(self, order, points, entity=None):
@@ -635,6 +810,8 @@ class Tabulator:
         return mask
 
 
+_LATTICE_VERDICT = {}      # (device, sd, degree, order) -> the product-form kernel reproduced the general one
+SELF_CHECK_TOL = 2e-13     # derived paths must reproduce the jet kernel this well (relative to each table's max), else jets
 _cache_lock = threading.Lock()
 _by_element = weakref.WeakKeyDictionary()
 _by_desc = collections.OrderedDict()        # description dicts are not weak-referenceable: bounded LRU instead

@@ -344,9 +344,43 @@ def _describe_hdivcurl(element):
     return _composite(nd, (sd,), [{"element": inner, "dof_offset": 0, "comp_out": comp_out, "sign": sign}])
 
 
+def _describe_quadrature(element):
+    """QuadratureElement (FIAT/quadrature_element.py:19-66): a set of points pretending to be an element; its
+    "tabulation" at exactly those points is the identity."""
+    cell = element.get_reference_element()
+    return {"kind": "quadrature", "sd": int(cell.get_spatial_dimension()), "dim": int(cell.get_dimension()),
+            "points": numpy.array(element._points, dtype=float).reshape(len(element._points), -1)}
+
+
+def _describe_trace(element):
+    """HDivTrace (FIAT/hdiv_trace.py:35-233): one discontinuous element per facet dimension, tabulated on a facet
+    and written into that facet's block of rows; everything else is zero."""
+    cell = element.get_reference_element()
+    sd = int(cell.get_spatial_dimension())
+    top = cell.get_topology()
+    facets = []
+    for dim in sorted(element.dg_elements):
+        dg = element.dg_elements[dim]
+        if sd == 1:
+            # facets of an interval are points: the "element" there is a constant (PointExpansionSet, expansions.py:646-656)
+            sub = {"kind": "point", "values": numpy.array(dg.tabulate(0, numpy.zeros((1, 0)))[()], dtype=float).reshape(-1)}
+        else:
+            sub = describe_element(dg)
+        facets.append({"dim": list(dim) if isinstance(dim, tuple) else int(dim), "count": len(top[dim]),
+                       "nf": int(dg.space_dimension()), "element": sub})
+    simplex = hasattr(cell, "vertices") and len(cell.get_vertices()) == sd + 1 and not hasattr(cell, "cells")
+    return {"kind": "trace", "sd": sd, "ndofs": int(element.space_dimension()), "simplex": bool(simplex),
+            "vertices": numpy.array(cell.get_vertices(), dtype=float) if simplex else numpy.zeros((0, sd)),
+            "facets": facets}
+
+
 def describe_element(element):
     """Return the plain-data description of a FIAT element (see module docstring)."""
     names = _mro_names(element)
+    if "QuadratureElement" in names:
+        return _describe_quadrature(element)
+    if "HDivTrace" in names:
+        return _describe_trace(element)
     if "FlattenedDimensions" in names:
         return _describe_flattened(element)
     if "TensorProductElement" in names:
@@ -363,5 +397,5 @@ def describe_element(element):
         return _describe_ciarlet(element)
     raise UnsupportedElement(
         f"{type(element).__name__}: only CiarletElement, TensorProductElement, FlattenedDimensions, "
-        "EnrichedElement, MixedElement, DiscontinuousElement and Hdiv/Hcurl wrappers are tabulated "
-        "on the device (no CPU fallback)")
+        "EnrichedElement, MixedElement, DiscontinuousElement, Hdiv/Hcurl wrappers, HDivTrace and QuadratureElement "
+        "are tabulated on the device (no CPU fallback)")

@@ -901,7 +901,7 @@ class TensorLeaf:
 
 
 def _cell_dim(desc):
-    if desc["kind"] == "simplex":
+    if desc["kind"] in ("simplex", "trace", "quadrature"):
         return int(desc["sd"])
     if desc["kind"] == "flattened":
         return _cell_dim(desc["element"])
@@ -912,6 +912,8 @@ def _cell_dim(desc):
 
 def value_shape_of(desc):
     kind = desc["kind"]
+    if kind in ("trace", "quadrature"):
+        return ()
     if kind in ("simplex", "composite"):
         return tuple(int(v) for v in desc["value_shape"])
     if kind == "flattened":
@@ -921,6 +923,10 @@ def value_shape_of(desc):
 
 def num_dofs_of(desc):
     kind = desc["kind"]
+    if kind == "trace":
+        return int(desc["ndofs"])
+    if kind == "quadrature":
+        return int(len(desc["points"]))
     if kind == "simplex":
         return int(desc["coeffs"].shape[0])
     if kind == "composite":

@@ -30,7 +30,14 @@ def load_case(name):
         dim, eid = ent
         case["entity"] = (tuple(dim) if isinstance(dim, list) else dim, eid)
     case["ref"] = {tuple(k): v for k, v in zip(case["keys"], case["values"])}
+    case["error_keys"] = [tuple(k) for k in case.get("error_keys", [])]    # slots holding exception objects (trace elements)
     return case
+
+
+def is_polynomial_case(case):
+    """False for the elements that are not polynomial tabulations (HDivTrace, QuadratureElement): pinned by the golden
+    files directly, no oracle / plan."""
+    return case["desc"]["kind"] not in ("trace", "quadrature")
 
 
 def load_desc(name):

@@ -179,6 +179,9 @@ def write_case(name, element, order, pts, entity=None, with_cells=False, table_s
     all_pts = numpy.asarray(pts, dtype=float)
     pts = all_pts[::table_stride]
     ref = element.tabulate(order, pts, entity)
+    # (trace elements put exception objects into the slots that are not defined, hdiv_trace.py:150-158)
+    errors = [list(k) for k, v in ref.items() if isinstance(v, Exception)]
+    ref = {k: v for k, v in ref.items() if not isinstance(v, Exception)}
     case = {
         "name": name,
         "desc": desc,
@@ -188,6 +191,8 @@ def write_case(name, element, order, pts, entity=None, with_cells=False, table_s
         "keys": [list(k) for k in ref.keys()],
         "values": [numpy.asarray(v, dtype=float) for v in ref.values()],
     }
+    if errors:
+        case["error_keys"] = errors
     if with_cells:
         complex_ = element.get_nodal_basis().get_expansion_set().ref_el
         mpts = all_pts
@@ -199,7 +204,8 @@ def write_case(name, element, order, pts, entity=None, with_cells=False, table_s
             case["mask_points"] = numpy.asarray(mpts, dtype=float)
     path = os.path.join(OUT, f"case_{name}.npz")
     description.save(path, case)
-    print(f"{name:32s} {os.path.getsize(path) / 1024:8.1f} KiB  keys={len(ref)}  shape={next(iter(ref.values())).shape}")
+    shape = next(iter(ref.values())).shape if ref else None
+    print(f"{name:32s} {os.path.getsize(path) / 1024:8.1f} KiB  keys={len(ref)}  shape={shape}")
 
 
 def main():
@@ -396,6 +402,31 @@ def main():
         complex_ = el.get_nodal_basis().get_expansion_set().ref_el
         pts = numpy.concatenate([simplex_points(rng2, 24, 2), adversarial_triangle_points(complex_)[:40]])
         write_case(f"hct{deg}_tri_o2", el, 2, pts, with_cells=True)
+
+    # (e) elements that are not polynomial tabulations: HDivTrace (values on facets only, TraceError objects in the
+    # derivative slots, geometric facet identification for entity=None) and QuadratureElement (identity at its points)
+    from FIAT.reference_element import UFCQuadrilateral as UQ, TensorProductCell
+    tr2, tr3 = FIAT.HDivTrace(T2, 2), FIAT.HDivTrace(T3, 1)
+    write_case("hdivtrace2_tri_facet1_o0", tr2, 0, rng2.random((9, 1)), entity=(1, 1))
+    write_case("hdivtrace2_tri_facet2_o1", tr2, 1, rng2.random((9, 1)), entity=(1, 2))
+    write_case("hdivtrace2_tri_cell_o0", tr2, 0, simplex_points(rng2, 5, 2), entity=(2, 0))      # not on facets
+    tverts = numpy.array(T3.get_vertices(), dtype=float)
+    on_facets = []
+    for f in range(4):
+        fv = numpy.delete(tverts, f, axis=0)
+        on_facets += list(rng2.dirichlet(numpy.ones(3), size=4) @ fv)
+    write_case("hdivtrace1_tet_none_o0", tr3, 0, numpy.array(on_facets)[rng2.permutation(16)])
+    write_case("hdivtrace1_tet_none_o1", tr3, 1, numpy.array(on_facets))
+    write_case("hdivtrace1_tet_interior_o0", tr3, 0, numpy.array(on_facets[:3] + [[0.2, 0.2, 0.2]]))   # -> NaN tables
+    write_case("hdivtrace1_tet_face3_o0", tr3, 0, simplex_points(rng2, 7, 2), entity=(2, 3))
+    write_case("hdivtrace0_line_none_o0", FIAT.HDivTrace(T1, 0), 0, numpy.array([[0.0], [1.0], [1.0]]))
+    write_case("hdivtrace0_line_vertex1_o0", FIAT.HDivTrace(T1, 0), 0, numpy.zeros((2, 0)), entity=(0, 1))
+    write_case("hdivtrace1_quad_edge3_o0", FIAT.HDivTrace(UQ(), 1), 0, rng2.random((6, 1)), entity=(1, 3))
+    trp = FIAT.HDivTrace(TensorProductCell(T2, T1), (1, 2))
+    write_case("hdivtrace_prism_side1_o0", trp, 0, rng2.random((6, 2)), entity=((1, 1), 1))
+    write_case("hdivtrace_prism_top_o0", trp, 0, simplex_points(rng2, 6, 2), entity=((2, 0), 1))
+    qpts = simplex_points(rng2, 6, 2)
+    write_case("quadrature6_tri_o0", FIAT.QuadratureElement(T2, qpts), 0, qpts)
 
     # element descriptions alone, for bench.py and full-size GPU tests
     for nm, el in () if ONLY is not None else (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),

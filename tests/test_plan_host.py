@@ -3,7 +3,7 @@ coefficients and block packing reproduce the reference outputs stored in the gol
 import numpy
 import pytest
 
-from conftest import golden_case_names, load_case, tolerance
+from conftest import golden_case_names, is_polynomial_case, load_case, tolerance
 from fiat_b200 import plan as planmod
 from oracle import fiat_oracle
 import program_emulator as emu
@@ -175,6 +175,8 @@ def _simplex_leaves(desc):
 def test_every_golden_description_compiles(name):
     """Plan compilation (incl. degenerate degree-0 line sets, wrapper elements) needs no GPU."""
     case = load_case(name)
+    if not is_polynomial_case(case):
+        pytest.skip("not a polynomial tabulation")
     for leaf in _simplex_leaves(case["desc"]):
         for order in range(0, case["order"] + 1):
             prog = planmod.compile_simplex(leaf, order)
