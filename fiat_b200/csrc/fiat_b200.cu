@@ -23,10 +23,7 @@ const FbTuning& fb_tuning() {
         v.eval_generic = geti("FIATB200_EVAL_GENERIC");
         v.vals_tpc = geti("FIATB200_VALS_TPC");
         v.vals_j = geti("FIATB200_VALS_J");
-        v.stage = geti("FIATB200_MMA_STAGE");
         v.mma_wl = geti("FIATB200_MMA_WARPLOCAL");
-        v.mma_cons = geti("FIATB200_MMA_CONS");
-        v.mma_slots = geti("FIATB200_MMA_SLOTS");
         return v;
     }();
     return t;
@@ -166,18 +163,7 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
             const bool warp_local = tune.mma_wl != 0 && pt % (threads / 32) == 0 && (ppw_c == 8 || ppw_c == 16 || ppw_c == 32);
             const size_t scratch = warp_local ? (size_t)plan->tab.nsteps * sizeof(StepRec)
                                               : (size_t)6 * pt * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec);
-            // warp-specialised stores (kernels.cuh, WS): value-only tables whose tile is one work item per row block;
-            // the ring of 8-row slots aliases the phase-1 scratch and takes what shared memory is left (2..16 slots)
-            int ncons = 0, nslot = 0;
-            if (P.na == 1 && pt == 8 * go && threads >= 256 && tune.mma_cons != 0) {
-                ncons = tune.mma_cons > 0 ? std::min(tune.mma_cons, threads / 64) : (threads >= 512 ? 4 : 2);
-                const size_t slot = (size_t)8 * (8 * go + 8) * sizeof(double);
-                const size_t room = limit > table ? limit - table : 0;
-                nslot = (int)std::min<size_t>(16, room / slot);
-                if (tune.mma_slots > 0) nslot = std::min(nslot, tune.mma_slots);
-                if (nslot < 2) ncons = nslot = 0;
-            }
-            const size_t bytes = table + std::max(scratch, (size_t)nslot * 8 * (8 * go + 8) * sizeof(double));
+            const size_t bytes = table + scratch;
             if (bytes <= limit) {
                 G->PT = pt;
                 G->logPT = 0;
@@ -185,8 +171,6 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
                 G->ldT = ld;
                 G->maxlev = maxlev;
                 G->ppw = warp_local ? ppw_c : 0;
-                G->ncons = ncons;
-                G->nslot = nslot;
                 G->threads = threads;
                 G->skip = 0;
                 if (tune.mma_skip >= 0) G->skip = tune.mma_skip;    // profiling only
@@ -198,13 +182,13 @@ bool mma_geometry(const fiatb200_plan* plan, const DevSimplex& P, int nrb, MmaGe
     return false;
 }
 
-template <int SD, int ORDER, int PW, bool WS>
+template <int SD, int ORDER, int PW>
 int launch_mma_pw(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                   long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    int rc = fb_set_smem(k_mma<SD, ORDER, PW, WS>, smem);
+    int rc = fb_set_smem(k_mma<SD, ORDER, PW>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
-    k_mma<SD, ORDER, PW, WS><<<grid, G.threads, smem, st>>>(P, tab, E, G, pts, npts, ldp, out, ostride, M);
+    k_mma<SD, ORDER, PW><<<grid, G.threads, smem, st>>>(P, tab, E, G, pts, npts, ldp, out, ostride, M);
     fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -213,12 +197,8 @@ int launch_mma_pw(const DevSimplex& P, const RecTab& tab, const DevEntity& E, co
 template <int SD, int ORDER>
 int launch_mma(const DevSimplex& P, const RecTab& tab, const DevEntity& E, const MmaGeom& G, size_t smem, const double* pts,
                long long npts, long long ldp, double* out, long long ostride, const DevRowMap& M, cudaStream_t st) {
-    if (ORDER == 0 && G.ncons > 0 && M.identity)        // rows in place: warp-specialised stores
-        return launch_mma_pw<SD, 0, 16, true>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
-    MmaGeom G0 = G;
-    G0.ncons = G0.nslot = 0;
-    if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16, false>(P, tab, E, G0, smem, pts, npts, ldp, out, ostride, M, st);
-    return launch_mma_pw<SD, ORDER, 8, false>(P, tab, E, G0, smem, pts, npts, ldp, out, ostride, M, st);
+    if (G.PT >= 16) return launch_mma_pw<SD, ORDER, 16>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
+    return launch_mma_pw<SD, ORDER, 8>(P, tab, E, G, smem, pts, npts, ldp, out, ostride, M, st);
 }
 
 template <int SD>

@@ -141,8 +141,6 @@ struct MmaGeom {
     int ldT;       // doubles between member rows of T (>= na*PT, = 4 or 12 mod 16: conflict-free fragments)
     int logPT;     // log2(PT)
     int maxlev;    // most recurrence steps in one wavefront level
-    int ncons;     // WS kernels: store warps (the last ncons warps of the CTA)
-    int nslot;     // WS kernels: slots of the shared-memory ring (<= 16)
     int ppw;       // > 0: warp-local recurrence, points per warp (8, 16 or 32; tile = warps x ppw); 0: CTA-wide levels
     int threads;   // CTA size: 512 (one CTA per SM) or 256 (two)
     int skip;      // profiling only: bit 0 skips the recurrence, bit 1 the contraction, bit 3 the stores
@@ -161,25 +159,7 @@ __host__ __device__ constexpr int fb_mma_go(int na) {
     return na >= 8 ? 1 : (na >= 5 ? 2 : (na >= 3 ? 4 : (na == 2 ? 8 : 16)));
 }
 
-// WS (value-only tables, tile = one work item per row block): warp specialisation of phase 2.  The last G.ncons warps
-// of the CTA only store: the DMMA warps deposit every finished 8-row x PT-point piece in a ring of shared-memory slots
-// (one 16-byte shared store per octet and lane, conflict free) and go straight back to the tensor pipe; the store
-// warps drain the ring with 512-byte contiguous row stores.  Before, a DMMA warp issued its own 8 KB of stores and sat
-// in that epilogue whenever the SM's store queue was full (measured, 2^20 points: Nedelec 2nd kind deg 4 order 1
-// 2.18 ms with and 1.66 ms without its stores, HBM floor 1.62 ms; P8 tet order 2 5.66 / 5.09 ms).
-// Ring protocol (bounded multi-producer multi-consumer queue): tickets from q_head / q_tail, slot = ticket % nslot,
-// generation = ticket / nslot; seq[slot] == 2 gen: free for that generation, 2 gen + 1: full.
-struct MmaRing {
-    int q_head, q_tail;
-    int seq[16];
-    int rb[16];
-};
-
-__device__ __forceinline__ void fb_spin_until(const int* flag, int want) {
-    while (*reinterpret_cast<const volatile int*>(flag) != want) __nanosleep(32);
-}
-
-template <int SD, int ORDER, int PW, bool WS>
+template <int SD, int ORDER, int PW>
 __global__ void __launch_bounds__(FB_MMA_THREADS, 1)
 k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E, const MmaGeom G,
       const double* __restrict__ pts, long long npts, long long ldp, double* __restrict__ out, long long ostride,
@@ -190,13 +170,8 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     double* s_fa = T + (size_t)P.kpad * G.ldT;          // 3 x PT
     double* s_fb = s_fa + 3 * G.PT;                     // 3 x PT
     __shared__ int s_next;
-    __shared__ MmaRing s_ring;
     const int tid = threadIdx.x;
     const int NT = blockDim.x;                          // 512 (one CTA per SM) or 256 (two)
-    if (WS && tid < 16) {
-        s_ring.seq[tid] = 0;
-        if (tid == 0) s_ring.q_head = s_ring.q_tail = 0;
-    }
     const int PT = G.PT;
     const long long base = (long long)blockIdx.x * PT;
 
@@ -323,45 +298,6 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     const size_t astride = (size_t)M.total_rows * ostride;      // distance between derivative tables
     const double* Tlane = T + g;                        // + member slot * ldT, gathered per block
     const int ldT = G.ldT;
-    // ---- store warps (WS) ----------------------------------------------------------------------------------
-    constexpr int RSW = 8 * GO + 8;                     // ring row stride in doubles (64 mod 128 bytes: conflict-free deposits)
-    double* ring = s_fa;                                // aliases the phase-1 scratch
-    if (WS && (tid >> 5) >= (NT >> 5) - G.ncons) {
-        const bool full = vec_ok && base + PT <= npts;
-        for (;;) {
-            int ticket = 0;
-            if (lane == 0) ticket = atomicAdd(&s_ring.q_tail, 1);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            if (ticket >= nitems) return;
-            const int slot = ticket % G.nslot, gen = ticket / G.nslot;
-            if (lane == 0) fb_spin_until(&s_ring.seq[slot], 2 * gen + 1);
-            __syncwarp();
-            __threadfence_block();
-            const int rbs = *reinterpret_cast<volatile int*>(&s_ring.rb[slot]);
-            const double* src = ring + (size_t)slot * 8 * RSW;
-#pragma unroll 1
-            for (int r = 0; r < 8; ++r) {
-                const int orow = tab.row_perm[rbs * 8 + r];
-                if (orow < 0) continue;
-                double* dst = out + (size_t)orow * ostride + base;
-                if (G.skip & 8) continue;                   // profiling only: no stores
-                if (full) {
-                    // one instruction = 32 lanes x 16 bytes = 512 contiguous bytes of one table row
-#pragma unroll
-                    for (int c = 0; c < 8 * GO; c += 64)
-                        *reinterpret_cast<double2*>(dst + c + 2 * lane) = *reinterpret_cast<const double2*>(src + r * RSW + c + 2 * lane);
-                } else {
-                    for (int c = lane; c < 8 * GO; c += 32)
-                        if (base + c < npts) dst[c] = src[r * RSW + c];
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                *reinterpret_cast<volatile int*>(&s_ring.seq[slot]) = 2 * gen + 2;      // free for the next generation
-            }
-        }
-    }
     // Work items are handed out dynamically (longest row blocks first).  The NEXT item and its first coefficient
     // fragments are fetched before the current item's stores are issued, so that the L2 latency of the fragments and
     // the shared-memory atomic overlap the store epilogue instead of delaying the next item's first DMMA.
@@ -435,26 +371,9 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         const int row = tab.row_perm[rb * 8 + g];           // table row of this lane's packed row (-1: padding)
         const long long p0 = base + oct0 * 8 + 2 * t;
         // warp-uniform: a full 8-row x GO-octet tile with aligned rows and no placement map
-        const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows;
-        if (WS) {
-            // deposit the finished piece in the ring; a store warp writes it out
-            int ticket = 0;
-            if (lane == 0) ticket = atomicAdd(&s_ring.q_head, 1);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            const int slot = ticket % G.nslot, gen = ticket / G.nslot;
-            if (lane == 0) fb_spin_until(&s_ring.seq[slot], 2 * gen);
-            __syncwarp();
-            double* dstrow = ring + (size_t)slot * 8 * RSW + g * RSW + 2 * t;
-#pragma unroll
-            for (int o = 0; o < GO; ++o)
-                *reinterpret_cast<double2*>(dstrow + 8 * o) = make_double2(acc[o][0][0], acc[o][0][1]);
-            __syncwarp();
-            if (lane == 0) {
-                *reinterpret_cast<volatile int*>(&s_ring.rb[slot]) = rb;
-                __threadfence_block();
-                *reinterpret_cast<volatile int*>(&s_ring.seq[slot]) = 2 * gen + 1;      // full
-            }
-        } else if (!(G.skip & 8)) {                         // (bit 3: profiling only, no stores)
+        const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows
+                               && !(G.skip & 32);           // (bit 5: profiling only, plain 8 x 64-byte stores)
+        if (!(G.skip & 8)) {                                // (bit 3: profiling only, no stores)
         if (full_tile) {
             // trade fragments between lane groups g and g^4 so that one store instruction covers
             // 4 rows x 128 contiguous bytes (two octets) instead of 8 rows x 64 bytes
@@ -468,8 +387,9 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                     // lanes g<4 send their octet o+1 piece, lanes g>=4 their octet o piece
                     const double sx = lo ? acc[o + 1][s][0] : acc[o][s][0];
                     const double sy = lo ? acc[o + 1][s][1] : acc[o][s][1];
-                    const double rx = __shfl_xor_sync(0xffffffffu, sx, 16);
-                    const double ry = __shfl_xor_sync(0xffffffffu, sy, 16);
+                    // (bit 4: profiling only, the exchange itself left out -- wrong values, same stores)
+                    const double rx = (G.skip & 16) ? sx : __shfl_xor_sync(0xffffffffu, sx, 16);
+                    const double ry = (G.skip & 16) ? sy : __shfl_xor_sync(0xffffffffu, sy, 16);
                     const int ocol = (o + (lo ? 0 : 1)) * 8;
                     const double2 first = lo ? make_double2(acc[o][s][0], acc[o][s][1]) : make_double2(rx, ry);
                     *reinterpret_cast<double2*>(row_lo + (size_t)s * astride + ocol) = first;

@@ -26,7 +26,7 @@ from dataclasses import dataclass, field
 import numpy
 
 __all__ = ["alpha_list", "compile_simplex", "SimplexProgram", "flatten_tensor", "TensorLeaf", "lattice_rowmap",
-           "alpha_split", "merged_split", "macro_merged", "stacked_derived",
+           "alpha_split", "merged_split", "macro_merged", "stacked_derived", "pullback_description",
            "resolve_parts", "Part", "value_shape_of", "num_dofs_of"]
 
 EXPANSION_CODES = {"dubiner": 0, "legendre_line": 1, "lagrange_line": 2}
@@ -851,6 +851,50 @@ def stacked_derived(desc, order, prog=None):
              cell_node_map=(numpy.arange(nmem, dtype=numpy.int64)[None, :]
                             + nmem * numpy.arange(ncells, dtype=numpy.int64)[:, None]))
     return d
+
+
+PULLBACK_FORM_DEGREES = {
+    "affine": (0,), "covariant piola": (1,), "contravariant piola": (2,), "double covariant piola": (1, 1),
+    "double contravariant piola": (2, 2), "covariant contravariant piola": (1, 2), "contravariant covariant piola": (2, 1),
+}
+
+
+def pullback_description(desc, mapping, J=None, Jinv=None, Jdet=None):
+    """Description of the element whose tabulation is `pullback(element.tabulate(...), mapping, J, Jinv, Jdet)`
+    (FIAT/macro.py:601-645): value axis i of every table is multiplied by Jinv^T (form degree 1) or J / det J (form
+    degree 2).  The map acts on the value axes only and tabulation is linear in the coefficient tensor
+    (FIAT/polynomial_set.py:71), so it is folded into the coefficients once, on the host: the mapped tables come out
+    of the same kernels at no extra cost per point."""
+    try:
+        formdegree = PULLBACK_FORM_DEGREES[mapping]
+    except KeyError:
+        raise ValueError(f"Unrecognized mapping {mapping}")
+    if desc.get("kind") != "simplex":
+        raise NotImplementedError("pullbacks are folded into the coefficients of Ciarlet elements on simplices")
+    if J is None and Jinv is None:
+        raise ValueError("J or Jinv is required")
+    if J is None:
+        J = numpy.linalg.pinv(Jinv)
+    if Jinv is None:
+        Jinv = numpy.linalg.pinv(J)
+    if Jdet is None:
+        Jdet = numpy.linalg.det(J)
+    J, Jinv = numpy.asarray(J, dtype=float), numpy.asarray(Jinv, dtype=float)
+    F1, F2 = Jinv.T, J / Jdet
+    vs = tuple(int(v) for v in desc["value_shape"])
+    coeffs = numpy.asarray(desc["coeffs"], dtype=float)
+    phi = coeffs.reshape((coeffs.shape[0],) + vs + (coeffs.shape[-1],))
+    if len(formdegree) > len(vs) and any(formdegree):
+        raise ValueError(f"{mapping} needs {len(formdegree)} value axes, the element has {len(vs)}")
+    for i, k in enumerate(formdegree):
+        if k == 0:
+            continue
+        F = F1 if k == 1 else F2
+        phi = numpy.moveaxis(numpy.tensordot(phi, F, axes=([i + 1], [1])), -1, i + 1)
+    out = {key: val for key, val in desc.items() if key != "nodes"}
+    out["value_shape"] = numpy.array(phi.shape[1:-1], dtype=numpy.int64)
+    out["coeffs"] = numpy.ascontiguousarray(phi.reshape(phi.shape[0], -1, phi.shape[-1]))
+    return out
 
 
 def macro_merged(desc, order, prog=None):

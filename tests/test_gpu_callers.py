@@ -150,3 +150,28 @@ def test_dmats_match_the_reference(cuda_device):
         got = ExpansionTabulator(es, n, cuda_device).get_dmats(lattice).cpu().numpy()
         assert got.shape == want.shape
         assert abs(got - want).max() <= 1e-9 * max(abs(want).max(), 1.0), label
+
+
+@pytest.mark.parametrize("name,mapping", [("n2curl4_tet_o1", "covariant piola"), ("rt3_tri_o1", "contravariant piola"),
+                                          ("bdm2_tet_o1", "contravariant piola"), ("regge2_tet_o1", "double covariant piola"),
+                                          ("hz3_tri_o1", "double contravariant piola"), ("aw_tri_o2", "covariant contravariant piola"),
+                                          ("p3_tri_o1", "affine")])
+def test_pullback_folded_into_the_coefficients(name, mapping, cuda_device):
+    """Tabulator.mapped(): tables equal the reference's pullback(phi, mapping, J) (FIAT/macro.py:601-645) applied to
+    the golden tabulation, for every mapping type the reference knows."""
+    from fiat_b200.api import Tabulator
+    FIAT = _reference()
+    from FIAT.macro import pullback
+    case = load_case(name)
+    sd = int(case["desc"]["sd"])
+    rng = numpy.random.default_rng(5)
+    J = numpy.eye(sd) + 0.3 * rng.standard_normal((sd, sd))
+    tab = Tabulator(case["desc"], cuda_device).mapped(mapping, J=J)
+    got = tab.tabulate(case["order"], case["points"], case["entity"])
+    for alpha, ref in case["ref"].items():
+        want = pullback(ref, mapping, J=J)
+        g = got[alpha].cpu().numpy()
+        assert g.shape == want.shape
+        assert abs(g - want).max() <= 1e-12 * max(abs(want).max(), 1e-300), (name, alpha)
+    with pytest.raises(ValueError):
+        Tabulator(case["desc"], cuda_device).mapped("no such piola", J=J)

@@ -35,6 +35,8 @@ def test_random_points_against_oracle(name, cuda_device):
     from fiat_b200.api import Tabulator
     case = load_case(name)
     desc = case["desc"]
+    if desc["kind"] in ("trace", "quadrature"):
+        pytest.skip("not a polynomial tabulation (pinned by its golden file)")
     tab = Tabulator(desc, cuda_device)
     # stable across processes (hash() is salted); FIATB200_FUZZ_SEED varies the sweep
     rng = numpy.random.default_rng(zlib.crc32(name.encode()) + int(os.environ.get("FIATB200_FUZZ_SEED", "0")))
