@@ -21,38 +21,41 @@ struct CellsGeom {
     int PT;        // points per tile
     int PTS;       // column capacity: PT + 8 * ncells (subcell ranges padded to octets), multiple of 8
     int ldT;       // doubles between member rows of T (>= PTS, = 4 or 12 mod 16)
-    int maxlev;    // most recurrence steps in one wavefront level
+    int maxlev;    // step records held in shared memory (all steps of the recurrence)
     int threads;   // 256: two CTAs per SM; 512: one CTA with the whole shared memory (wider tile)
 };
 
 #define FB_CELLS_THREADS 512   // upper bound; launched with 256 (two CTAs per SM) or 512 (one)
 #define FB_CELLS_GO 8          // octets of one subcell per column chunk
 
+#define FB_CELLS_CH 8          // coefficient fragments of a segment held in registers (prefetched one segment ahead)
+
 // One (row block, column chunk) segment: the subcell's blocks of the row block against NOCT octets of columns, then
-// the fragments go through the column permutation into the warp's staging rows.  Fragments and column-block
-// numbers are fetched two blocks ahead; the loop stays rolled (code size).
+// the fragments go through the column permutation into the warp's staging rows.  The first FB_CELLS_CH coefficient
+// fragments and their member slots (lane 4 j + t holds slot t of block j) were fetched while the previous segment
+// ran; a segment rarely has more blocks (those are loaded on demand).
 template <int NOCT>
-__device__ __forceinline__ void cells_segment(const double* __restrict__ fp, const int* __restrict__ kp, int nq,
-                                              const double* __restrict__ Tchunk, size_t ldT,
-                                              const int* __restrict__ perm, double* __restrict__ srow) {
+__device__ __forceinline__ void cells_segment(const double (&a)[FB_CELLS_CH], int kb, int t, const double* __restrict__ fp,
+                                              const int* __restrict__ kp, int nq, const double* __restrict__ Tchunk,
+                                              size_t ldT, const int* __restrict__ perm, double* __restrict__ srow) {
     double acc[NOCT][2];
 #pragma unroll
     for (int o = 0; o < NOCT; ++o) acc[o][0] = acc[o][1] = 0.0;
-    // kp points at this lane's member slot of the first block (slot t of block i at kp[4 i]): gather packing
-    double a0 = __ldg(fp), a1 = nq > 1 ? __ldg(fp + 32) : 0.0;
-    int m0 = __ldg(kp), m1 = nq > 1 ? __ldg(kp + 4) : 0;
-#pragma unroll 1
-    for (int i = 0; i < nq; ++i) {
-        const double a = a0;
-        const double* Tb = Tchunk + m0 * ldT;
-        a0 = a1;
-        m0 = m1;
-        if (i + 2 < nq) {
-            a1 = __ldg(fp + (size_t)(i + 2) * 32);
-            m1 = __ldg(kp + 4 * (i + 2));
-        }
 #pragma unroll
-        for (int o = 0; o < NOCT; ++o) dmma_8x8x4(acc[o][0], acc[o][1], a, Tb[o * 8]);
+    for (int j = 0; j < FB_CELLS_CH; ++j) {
+        if (j < nq) {
+            const int slot = __shfl_sync(0xffffffffu, kb, 4 * j + t);
+            const double* Tb = Tchunk + slot * ldT;
+#pragma unroll
+            for (int o = 0; o < NOCT; ++o) dmma_8x8x4(acc[o][0], acc[o][1], a[j], Tb[o * 8]);
+        }
+    }
+#pragma unroll 1
+    for (int i = FB_CELLS_CH; i < nq; ++i) {
+        const double ai = __ldg(fp + (size_t)i * 32);
+        const double* Tb = Tchunk + __ldg(kp + 4 * i) * ldT;
+#pragma unroll
+        for (int o = 0; o < NOCT; ++o) dmma_8x8x4(acc[o][0], acc[o][1], ai, Tb[o * 8]);
     }
 #pragma unroll
     for (int o = 0; o < NOCT; ++o) {
@@ -73,8 +76,8 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     double* T = smem;                                        // kpad x ldT
     double* s_fa = T + (size_t)P.kpad * ldT;                 // 3 x PTS
     double* s_fb = s_fa + 3 * PTS;                           // 3 x PTS
-    StepRec* s_rec = reinterpret_cast<StepRec*>(s_fb + 3 * PTS);         // 2 x maxlev
-    int* s_perm = reinterpret_cast<int*>(s_rec + 2 * G.maxlev);          // PTS: column -> point of the tile (-1 padding)
+    StepRec* s_rec = reinterpret_cast<StepRec*>(s_fb + 3 * PTS);         // all step records
+    int* s_perm = reinterpret_cast<int*>(s_rec + G.maxlev);              // PTS: column -> point of the tile (-1 padding)
     double* s_stage = reinterpret_cast<double*>(s_perm + PTS);           // warps x 8 rows x (PT + 2) (PTS is even)
     const int SP = PT + 2;      // staging row stride: rows of a fragment (same column, 8 rows) land in 8 different banks
     int* s_ptr = reinterpret_cast<int*>(s_stage + (size_t)(NT / 32) * 8 * SP);   // ncells x (nrb + 1) block offsets
@@ -140,33 +143,32 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
         }
         T[(size_t)tab.start_slot * ldT + col] = __ldg(geom + 12);
     }
-    {
-        const int n0 = tab.level_ptr[1] - tab.level_ptr[0];
-        for (int i = tid; i < n0 * 4; i += NT)
-            reinterpret_cast<double*>(s_rec)[i] = reinterpret_cast<const double*>(&tab.steps[tab.level_ptr[0]])[i];
-    }
+    // all step records in shared memory (lanes of a warp work on different steps, which the constant cache would
+    // serialise)
+    for (int i = tid; i < tab.nsteps * 4; i += NT)
+        reinterpret_cast<double*>(s_rec)[i] = reinterpret_cast<const double*>(tab.steps)[i];
     __syncthreads();
     const int ncols = s_cols;
 
-    // ---- phase 1: value recurrence, wavefront order ----------------------------------------------
-    for (int lev = 0; lev < tab.nlevels; ++lev) {
-        const int l0 = tab.level_ptr[lev];
-        const int nst = tab.level_ptr[lev + 1] - l0;
-        const StepRec* rec = s_rec + (lev & 1) * G.maxlev;
-        if (lev + 1 < tab.nlevels) {
-            const int l1 = tab.level_ptr[lev + 1];
-            const int n1 = tab.level_ptr[lev + 2] - l1;
-            double* dst = reinterpret_cast<double*>(s_rec + ((lev + 1) & 1) * G.maxlev);
-            for (int i = tid; i < n1 * 4; i += NT) dst[i] = reinterpret_cast<const double*>(&tab.steps[l1])[i];
+    // ---- phase 1: value recurrence, warp-local -------------------------------------------------------
+    // A warp owns blocks of 16 columns and runs the whole recurrence for them level by level with warp-level
+    // synchronisation only (lane = (step slot, column)); the low wavefront levels have far fewer (step, column) items
+    // than the CTA has threads, so CTA-wide levels would pay a block barrier and a latency-bound round each.
+    for (int cb = tid >> 5; cb * 16 < ncols; cb += NT >> 5) {
+        const int col = cb * 16 + (tid & 15);
+        const bool active = col < ncols;
+        const int cc = active ? col : 0;
+        const double fa[3] = {s_fa[cc], s_fa[PTS + cc], s_fa[2 * PTS + cc]};
+        const double fb[3] = {s_fb[cc], s_fb[PTS + cc], s_fb[2 * PTS + cc]};
+        for (int lev = 0; lev < tab.nlevels; ++lev) {
+            const int l0 = tab.level_ptr[lev], nst = tab.level_ptr[lev + 1] - l0;
+            if (active)
+                for (int sl = (tid & 31) >> 4; sl < nst; sl += 2)
+                    run_step<SD, 0>(P, s_rec[l0 + sl], tab.geom0, fa, fb, T + col, ldT, 1, 1);
+            __syncwarp();
         }
-        for (int it = tid; it < nst * ncols; it += NT) {
-            const int sl = it / ncols, col = it - sl * ncols;
-            const double fa[3] = {s_fa[col], s_fa[PTS + col], s_fa[2 * PTS + col]};
-            const double fb[3] = {s_fb[col], s_fb[PTS + col], s_fb[2 * PTS + col]};
-            run_step<SD, 0>(P, rec[sl], tab.geom0, fa, fb, T + col, ldT, 1, 1);
-        }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- phase 2: block-sparse contraction on the FP64 tensor pipe -----------------------------------
     // Work item = one 8-row block, for ALL columns of the tile: the warp walks the tile's column chunks (<= GO octets
@@ -182,49 +184,79 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     const double* Tlane = T + g;                                     // + member slot * ldT, gathered per block
     double* stage = s_stage + (size_t)warp * 8 * SP;                 // 8 rows x PT points (+ 2 padding)
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0) && base + PT <= npts;
-    for (;;) {
+    // Segments are walked as one software-pipelined stream: while a segment's DMMAs run, the coefficient fragments and
+    // member slots of the NEXT segment (next chunk of the row block, or first chunk of the warp's next row block) are
+    // already in flight, so the L2 latency of a fragment is not paid once per 2-7 block segment.
+    double a_cur[FB_CELLS_CH], a_nxt[FB_CELLS_CH];
+    int kb_cur = 0, kb_nxt = 0;
+    auto fetch_item = [&]() {
         int item = 0;
         if (lane == 0) item = atomicAdd(&s_next, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= nrb) break;
-        const int rb = tab.rb_order[item];
-#pragma unroll 1
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const int chunk = s_chunk[ch];
-            const int c = chunk & 255, oct0 = (chunk >> 8) & 4095, noct = chunk >> 20;
-            const int q0 = s_ptr[c * (nrb + 1) + rb], q1 = s_ptr[c * (nrb + 1) + rb + 1];
-            const double* fp = P.blk_frag + (size_t)q0 * 32 + lane;
-            const double* Tchunk = Tlane + oct0 * 8;
-            const int* perm = s_perm + oct0 * 8 + 2 * t;
-            double* srow = stage + g * SP;
-            // one specialisation per number of octets: exactly noct DMMAs per block (an `if (o < noct)` in an unrolled
-            // loop becomes predicated DMMAs that still occupy the tensor pipe) and no dispatch inside the block loop
-            switch (noct) {
-                case 1: cells_segment<1>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-                case 2: cells_segment<2>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-                case 3: cells_segment<3>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-                case 4: cells_segment<4>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-                case 5: cells_segment<5>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-                case 6: cells_segment<6>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-                case 7: cells_segment<7>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-                default: cells_segment<8>(fp, P.blk_kb + 4 * q0 + t, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            }
+        return item < nrb ? (int)tab.rb_order[item] : -1;
+    };
+    int rb = nchunk > 0 ? fetch_item() : -1, ch = 0;
+    if (rb >= 0) {
+        const int c = s_chunk[0] & 255;
+        const int q0 = s_ptr[c * (nrb + 1) + rb], q1 = s_ptr[c * (nrb + 1) + rb + 1];
+#pragma unroll
+        for (int j = 0; j < FB_CELLS_CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
+        if (4 * q0 + lane < 4 * q1) kb_cur = __ldg(P.blk_kb + 4 * q0 + lane);
+    }
+    while (rb >= 0) {
+        const int chunk = s_chunk[ch];
+        const int c = chunk & 255, oct0 = (chunk >> 8) & 4095, noct = chunk >> 20;
+        const int q0 = s_ptr[c * (nrb + 1) + rb], q1 = s_ptr[c * (nrb + 1) + rb + 1];
+        // next segment and its first fragments
+        const bool last = ch + 1 == nchunk;
+        const int rb_n = last ? fetch_item() : rb, ch_n = last ? 0 : ch + 1;
+        kb_nxt = 0;
+        if (rb_n >= 0) {
+            const int cn = s_chunk[ch_n] & 255;
+            const int n0 = s_ptr[cn * (nrb + 1) + rb_n], n1 = s_ptr[cn * (nrb + 1) + rb_n + 1];
+#pragma unroll
+            for (int j = 0; j < FB_CELLS_CH; ++j) a_nxt[j] = (n0 + j < n1) ? __ldg(P.blk_frag + (size_t)(n0 + j) * 32 + lane) : 0.0;
+            if (4 * n0 + lane < 4 * n1) kb_nxt = __ldg(P.blk_kb + 4 * n0 + lane);
         }
-        __syncwarp();
-#pragma unroll 1
-        for (int r = 0; r < 8; ++r) {
-            const int row = tab.row_perm[rb * 8 + r];
-            if (row < 0) continue;
-            double* rowp = out + (size_t)row * ostride + base;
-            if (vec_ok) {
-                for (int i = lane * 2; i < PT; i += 64)
-                    *reinterpret_cast<double2*>(rowp + i) = *reinterpret_cast<const double2*>(stage + r * SP + i);
-            } else {
-                for (int i = lane; i < PT; i += 32)
-                    if (base + i < npts) rowp[i] = stage[r * SP + i];
-            }
+        const double* fp = P.blk_frag + (size_t)q0 * 32 + lane;
+        const int* kp = P.blk_kb + 4 * q0 + t;
+        const double* Tchunk = Tlane + oct0 * 8;
+        const int* perm = s_perm + oct0 * 8 + 2 * t;
+        double* srow = stage + g * SP;
+        // one specialisation per number of octets: exactly noct DMMAs per block (an `if (o < noct)` in an unrolled
+        // loop becomes predicated DMMAs that still occupy the tensor pipe) and no dispatch inside the block loop
+        switch (noct) {
+            case 1: cells_segment<1>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 2: cells_segment<2>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 3: cells_segment<3>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 4: cells_segment<4>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 5: cells_segment<5>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 6: cells_segment<6>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 7: cells_segment<7>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            default: cells_segment<8>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
         }
-        __syncwarp();
+        if (last) {
+            __syncwarp();
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) {
+                const int row = tab.row_perm[rb * 8 + r];
+                if (row < 0) continue;
+                double* rowp = out + (size_t)row * ostride + base;
+                if (vec_ok) {
+                    for (int i = lane * 2; i < PT; i += 64)
+                        *reinterpret_cast<double2*>(rowp + i) = *reinterpret_cast<const double2*>(stage + r * SP + i);
+                } else {
+                    for (int i = lane; i < PT; i += 32)
+                        if (base + i < npts) rowp[i] = stage[r * SP + i];
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < FB_CELLS_CH; ++j) a_cur[j] = a_nxt[j];
+        kb_cur = kb_nxt;
+        rb = rb_n;
+        ch = ch_n;
     }
 
     // ---- phase 3: points shared by several subcells -------------------------------------------------

@@ -9,9 +9,7 @@ bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
     if (P.blk_cells < 2 || P.blk_cells != P.ncells || P.expansion != 0 || P.order != 0 || P.nblk == 0 || plan->tab.nrb == 0)
         return false;
     if (P.sd < 2) return false;
-    int maxlev = 1;
-    for (int l = 0; l < plan->tab.nlevels; ++l)
-        maxlev = std::max(maxlev, (int)plan->tab.level_ptr[l + 1] - (int)plan->tab.level_ptr[l]);
+    const int maxlev = std::max(1, plan->tab.nsteps);        // all step records sit in shared memory (cells.cuh)
     if (P.ncells > 32) return false;
     // widest tile first (the per-block loop overhead is amortised over the octets a subcell has in the tile):
     // 256 threads and two CTAs per SM, or 512 threads and one CTA with all of the shared memory
@@ -23,7 +21,7 @@ bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
             const int pts_cap = pt + 8 * P.ncells;
             int ld = pts_cap;
             while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
-            const size_t bytes = ((size_t)P.kpad * ld + 6 * pts_cap) * sizeof(double) + 2 * (size_t)maxlev * sizeof(StepRec)
+            const size_t bytes = ((size_t)P.kpad * ld + 6 * pts_cap) * sizeof(double) + (size_t)maxlev * sizeof(StepRec)
                                  + (size_t)pts_cap * sizeof(int) + (size_t)(threads / 32) * 8 * (pt + 2) * sizeof(double)
                                  + ((size_t)P.ncells * (plan->tab.nrb + 1) + pts_cap / 8 + 32) * sizeof(int) + 64;
             if (bytes <= limit) {

@@ -371,8 +371,7 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
         const int row = tab.row_perm[rb * 8 + g];           // table row of this lane's packed row (-1: padding)
         const long long p0 = base + oct0 * 8 + 2 * t;
         // warp-uniform: a full 8-row x GO-octet tile with aligned rows and no placement map
-        const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows
-                               && !(G.skip & 32);           // (bit 5: profiling only, plain 8 x 64-byte stores)
+        const bool full_tile = GO >= 2 && vec_ok && M.identity && base + (oct0 + GO) * 8 <= npts && rb * 8 + 8 <= P.nrows;
         if (!(G.skip & 8)) {                                // (bit 3: profiling only, no stores)
         if (full_tile) {
             // trade fragments between lane groups g and g^4 so that one store instruction covers
@@ -387,9 +386,8 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
                     // lanes g<4 send their octet o+1 piece, lanes g>=4 their octet o piece
                     const double sx = lo ? acc[o + 1][s][0] : acc[o][s][0];
                     const double sy = lo ? acc[o + 1][s][1] : acc[o][s][1];
-                    // (bit 4: profiling only, the exchange itself left out -- wrong values, same stores)
-                    const double rx = (G.skip & 16) ? sx : __shfl_xor_sync(0xffffffffu, sx, 16);
-                    const double ry = (G.skip & 16) ? sy : __shfl_xor_sync(0xffffffffu, sy, 16);
+                    const double rx = __shfl_xor_sync(0xffffffffu, sx, 16);
+                    const double ry = __shfl_xor_sync(0xffffffffu, sy, 16);
                     const int ocol = (o + (lo ? 0 : 1)) * 8;
                     const double2 first = lo ? make_double2(acc[o][s][0], acc[o][s][1]) : make_double2(rx, ry);
                     *reinterpret_cast<double2*>(row_lo + (size_t)s * astride + ocol) = first;
