@@ -28,21 +28,20 @@ struct CellsGeom {
 #define FB_CELLS_THREADS 512   // upper bound; launched with 256 (two CTAs per SM) or 512 (one)
 #define FB_CELLS_GO 8          // octets of one subcell per column chunk
 
-#define FB_CELLS_CH 8          // coefficient fragments of a segment held in registers (prefetched one segment ahead)
 
 // One (row block, column chunk) segment: the subcell's blocks of the row block against NOCT octets of columns, then
-// the fragments go through the column permutation into the warp's staging rows.  The first FB_CELLS_CH coefficient
+// the fragments go through the column permutation into the warp's staging rows.  The first CH coefficient
 // fragments and their member slots (lane 4 j + t holds slot t of block j) were fetched while the previous segment
-// ran; a segment rarely has more blocks (those are loaded on demand).
-template <int NOCT>
-__device__ __forceinline__ void cells_segment(const double (&a)[FB_CELLS_CH], int kb, int t, const double* __restrict__ fp,
+// ran (CH = 2, 4 or 8, chosen from the plan's longest segment); longer segments load the rest on demand.
+template <int NOCT, int CH>
+__device__ __forceinline__ void cells_segment(const double (&a)[CH], int kb, int t, const double* __restrict__ fp,
                                               const int* __restrict__ kp, int nq, const double* __restrict__ Tchunk,
                                               size_t ldT, const int* __restrict__ perm, double* __restrict__ srow) {
     double acc[NOCT][2];
 #pragma unroll
     for (int o = 0; o < NOCT; ++o) acc[o][0] = acc[o][1] = 0.0;
 #pragma unroll
-    for (int j = 0; j < FB_CELLS_CH; ++j) {
+    for (int j = 0; j < CH; ++j) {
         if (j < nq) {
             const int slot = __shfl_sync(0xffffffffu, kb, 4 * j + t);
             const double* Tb = Tchunk + slot * ldT;
@@ -51,7 +50,7 @@ __device__ __forceinline__ void cells_segment(const double (&a)[FB_CELLS_CH], in
         }
     }
 #pragma unroll 1
-    for (int i = FB_CELLS_CH; i < nq; ++i) {
+    for (int i = CH; i < nq; ++i) {
         const double ai = __ldg(fp + (size_t)i * 32);
         const double* Tb = Tchunk + __ldg(kp + 4 * i) * ldT;
 #pragma unroll
@@ -65,7 +64,7 @@ __device__ __forceinline__ void cells_segment(const double (&a)[FB_CELLS_CH], in
     }
 }
 
-template <int SD>
+template <int SD, int CH>
 __global__ void __launch_bounds__(FB_CELLS_THREADS, 1)
 k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid_constant__ SmallTab st,
             const DevEntity E, const CellsGeom G, const double* __restrict__ pts, long long npts, long long ldp,
@@ -187,7 +186,7 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     // Segments are walked as one software-pipelined stream: while a segment's DMMAs run, the coefficient fragments and
     // member slots of the NEXT segment (next chunk of the row block, or first chunk of the warp's next row block) are
     // already in flight, so the L2 latency of a fragment is not paid once per 2-7 block segment.
-    double a_cur[FB_CELLS_CH], a_nxt[FB_CELLS_CH];
+    double a_cur[CH], a_nxt[CH];
     int kb_cur = 0, kb_nxt = 0;
     auto fetch_item = [&]() {
         int item = 0;
@@ -200,7 +199,7 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
         const int c = s_chunk[0] & 255;
         const int q0 = s_ptr[c * (nrb + 1) + rb], q1 = s_ptr[c * (nrb + 1) + rb + 1];
 #pragma unroll
-        for (int j = 0; j < FB_CELLS_CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
+        for (int j = 0; j < CH; ++j) a_cur[j] = (q0 + j < q1) ? __ldg(P.blk_frag + (size_t)(q0 + j) * 32 + lane) : 0.0;
         if (4 * q0 + lane < 4 * q1) kb_cur = __ldg(P.blk_kb + 4 * q0 + lane);
     }
     while (rb >= 0) {
@@ -215,7 +214,7 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
             const int cn = s_chunk[ch_n] & 255;
             const int n0 = s_ptr[cn * (nrb + 1) + rb_n], n1 = s_ptr[cn * (nrb + 1) + rb_n + 1];
 #pragma unroll
-            for (int j = 0; j < FB_CELLS_CH; ++j) a_nxt[j] = (n0 + j < n1) ? __ldg(P.blk_frag + (size_t)(n0 + j) * 32 + lane) : 0.0;
+            for (int j = 0; j < CH; ++j) a_nxt[j] = (n0 + j < n1) ? __ldg(P.blk_frag + (size_t)(n0 + j) * 32 + lane) : 0.0;
             if (4 * n0 + lane < 4 * n1) kb_nxt = __ldg(P.blk_kb + 4 * n0 + lane);
         }
         const double* fp = P.blk_frag + (size_t)q0 * 32 + lane;
@@ -226,14 +225,14 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
         // one specialisation per number of octets: exactly noct DMMAs per block (an `if (o < noct)` in an unrolled
         // loop becomes predicated DMMAs that still occupy the tensor pipe) and no dispatch inside the block loop
         switch (noct) {
-            case 1: cells_segment<1>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            case 2: cells_segment<2>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            case 3: cells_segment<3>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            case 4: cells_segment<4>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            case 5: cells_segment<5>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            case 6: cells_segment<6>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            case 7: cells_segment<7>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
-            default: cells_segment<8>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 1: cells_segment<1, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 2: cells_segment<2, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 3: cells_segment<3, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 4: cells_segment<4, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 5: cells_segment<5, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 6: cells_segment<6, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            case 7: cells_segment<7, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
+            default: cells_segment<8, CH>(a_cur, kb_cur, t, fp, kp, q1 - q0, Tchunk, (size_t)ldT, perm, srow); break;
         }
         if (last) {
             __syncwarp();
@@ -253,7 +252,7 @@ k_mma_cells(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
             __syncwarp();
         }
 #pragma unroll
-        for (int j = 0; j < FB_CELLS_CH; ++j) a_cur[j] = a_nxt[j];
+        for (int j = 0; j < CH; ++j) a_cur[j] = a_nxt[j];
         kb_cur = kb_nxt;
         rb = rb_n;
         ch = ch_n;

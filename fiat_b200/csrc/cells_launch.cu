@@ -34,14 +34,14 @@ bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
     return false;
 }
 
-template <int SD>
+template <int SD, int CH>
 int launch_cells(const fiatb200_plan* plan, const DevEntity& E, const CellsGeom& G, size_t smem, const double* pts,
                  long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
-    int rc = fb_set_smem(k_mma_cells<SD>, smem);
+    int rc = fb_set_smem(k_mma_cells<SD, CH>, smem);
     if (rc) return rc;
     const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
-    k_mma_cells<SD><<<grid, G.threads, smem, st>>>(plan->simplex, plan->tab, plan->small_tab, E, G, pts, npts, ldp,
-                                                          out, ostride);
+    k_mma_cells<SD, CH><<<grid, G.threads, smem, st>>>(plan->simplex, plan->tab, plan->small_tab, E, G, pts, npts, ldp,
+                                                              out, ostride);
     fb_launches++;
     FB_CUDA(cudaGetLastError());
     return FIATB200_OK;
@@ -61,6 +61,13 @@ int fb_dispatch_cells(const fiatb200_plan* plan, const DevEntity& E, const doubl
     size_t smem = 0;
     if (!cells_geometry(plan, &G, &smem))
         return fb_fail(FIATB200_ERR_UNSUPPORTED, "split-cell tile kernel not applicable to this plan");
-    if (plan->simplex.sd == 2) return launch_cells<2>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
-    return launch_cells<3>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+    // fragments prefetched per segment: enough for the plan's longest (row block, subcell) segment, at most 8
+    const int seg = plan->max_segment;
+#define FB_CELLS_LAUNCH(SD_)                                                                                   \
+    if (seg <= 2) return launch_cells<SD_, 2>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);             \
+    if (seg <= 4) return launch_cells<SD_, 4>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);             \
+    return launch_cells<SD_, 8>(plan, E, G, smem, pts, npts, ldp, out, ostride, st);
+    if (plan->simplex.sd == 2) { FB_CELLS_LAUNCH(2) }
+    FB_CELLS_LAUNCH(3)
+#undef FB_CELLS_LAUNCH
 }

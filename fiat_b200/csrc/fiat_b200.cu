@@ -367,6 +367,7 @@ fiatb200_plan* new_plan() {
     memset(&plan->tensor, 0, sizeof(plan->tensor));
     memset(&plan->lattice, 0, sizeof(plan->lattice));
     plan->max_smem_optin = plan->num_sms = 0;
+    plan->max_segment = 0;
     for (int i = 0; i < 2; ++i) { plan->host_stream[i] = nullptr; plan->host_pts[i] = nullptr; plan->host_out[i] = nullptr; }
     plan->host_pts_cap = plan->host_out_cap = 0;
     return plan;
@@ -496,6 +497,9 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     P.cderiv_len = has_cderiv ? (int)h->cderiv_len : 0;
     P.ncp = has_cderiv ? h->ncp : 0;
     P.blk_cells = blk_cells > 1 ? blk_cells : 0;
+    plan->max_segment = 0;
+    for (int i = 0; i < blk_cells * (h->nrb + 1) - 1; ++i)
+        if ((i + 1) % (h->nrb + 1) != 0) plan->max_segment = std::max(plan->max_segment, h->blk_ptr[i + 1] - h->blk_ptr[i]);
     *out = plan;
     return FIATB200_OK;
 }

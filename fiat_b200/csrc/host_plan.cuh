@@ -45,6 +45,7 @@ struct fiatb200_plan {
     DevLattice lattice;
     int max_smem_optin;
     int num_sms;
+    int max_segment;        // split-cell block streams: most blocks of one (row block, subcell) segment
     // staging for fiatb200_tabulate_host: two streams with one points/result buffer each, kept
     // across calls so that the end-to-end path issues no allocation or stream creation per call
     std::mutex host_mutex;
