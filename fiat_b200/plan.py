@@ -402,6 +402,44 @@ def slots_from_colours(colour):
     return perm
 
 
+DROP_BUDGET = 1e-13         # the dropped entries of a row may together contribute this fraction of their table's largest entry
+
+
+def significant_entries(desc, t, folded, nstack=1):
+    """Boolean mask of the coefficient entries the block packing must keep, per subcell matrix `folded[c]`
+    (rows x member slots).  The entries of a row are dropped smallest first, by their largest possible contribution
+    |C[r, m]| max_x |psi_m(x)|, as long as the dropped ones together stay below DROP_BUDGET of the largest entry of the
+    table the row belongs to (rows come in `nstack` equal groups: the derivative tables of a stacked derived
+    element) -- the north-star tolerance is 1e-12 of that maximum.  (A threshold relative to the largest
+    COEFFICIENT, as in round 1, is not enough once the members' magnitudes differ by orders of magnitude: the stacked
+    P12 triangle lost 1e-12 of its first-derivative tables that way.)  Member bounds and table maxima are sampled on a
+    lattice of the default simplex plus random points."""
+    sd, n = int(desc["sd"]), int(desc["degree"])
+    lat = n + 3
+    idx = numpy.array([i for i in numpy.ndindex(*([lat + 1] * sd)) if sum(i) <= lat], dtype=float)
+    rng = numpy.random.default_rng(20261020)
+    u = numpy.sort(rng.random((256, sd)), axis=1)
+    rnd = numpy.diff(numpy.concatenate([numpy.zeros((256, 1)), u], axis=1), axis=1)
+    x = numpy.concatenate([2.0 * idx / lat - 1.0, 2.0 * rnd - 1.0]).T          # (sd, npts) on the default simplex
+    V = numpy.empty((t["nslots"], x.shape[1]))
+    V[numpy.asarray(t["slot_of"])] = _member_values(t, sd, x)                  # by slot
+    bound = numpy.abs(V).max(axis=1)
+    keep = []
+    for c, F in enumerate(folded):
+        scale = abs(float(t["geom"][c, 12]))
+        rowmax = numpy.abs(F @ V).max(axis=1) * scale
+        grp = rowmax.reshape(nstack, -1).max(axis=1)                            # largest entry of each stacked table
+        tabmax = numpy.repeat(grp, len(rowmax) // nstack)
+        w = numpy.abs(F) * (bound * scale)[None, :]
+        order = numpy.argsort(w, axis=1)
+        spent = numpy.cumsum(numpy.take_along_axis(w, order, axis=1), axis=1)
+        drop_sorted = spent <= DROP_BUDGET * tabmax[:, None]
+        k = numpy.ones_like(w, dtype=bool)
+        numpy.put_along_axis(k, order, ~drop_sorted, axis=1)
+        keep.append(k & (F != 0.0))
+    return keep
+
+
 CLUSTER_ITERS = 100000      # swap rounds of the row clustering (P8 tet order 2, 1650 x 165: 0.4 s, 2826 -> 2406 blocks)
 
 
@@ -644,6 +682,12 @@ def alpha_split(desc, order, prog=None):
     return out
 
 
+def _nstack(desc, nrows):
+    """Number of equal row groups (stacked derivative tables) of a derived description; 1 for ordinary elements."""
+    ns = int(desc.get("nstack", 1))
+    return ns if ns >= 1 and nrows % ns == 0 else 1
+
+
 def compile_simplex(desc, order):
     """Build the SimplexProgram of a `kind == "simplex"` description for one derivative order."""
     sd, n = int(desc["sd"]), int(desc["degree"])
@@ -671,10 +715,10 @@ def compile_simplex(desc, order):
                 for (tgt, src), w in zip(t["fix_idx"], t["fix_w"]):
                     f0[:, src] -= w * base[:, tgt]
                 wide.append(f0)
-            wide = numpy.concatenate(wide, axis=1)
-            tol0 = 1e-14 * max(numpy.abs(wide).max(), 1e-300)
-            packed_rows = cluster_rows(wide, tol0, nseg=ncells)[0]
-            colour, _ = colour_members(wide, packed_rows, tol0, nseg=ncells)
+            keep0 = significant_entries(desc, t, wide, _nstack(desc, nrows))
+            wide = numpy.concatenate([numpy.where(k, f, 0.0) for k, f in zip(keep0, wide)], axis=1)
+            packed_rows = cluster_rows(wide, 0.0, nseg=ncells)[0]
+            colour, _ = colour_members(wide, packed_rows, 0.0, nseg=ncells)
             t = _dubiner_tables(desc, order, slot_perm=slots_from_colours(colour))
             t["packed_rows"] = packed_rows          # row supports do not depend on the slot numbering
         fold = t["fold_by_slot"]
@@ -740,11 +784,11 @@ def compile_simplex(desc, order):
             for (tgt, src), w in zip(prog.fix_idx, prog.fix_w):
                 f[:, src] -= w * ccell[c][:, tgt]
             folded.append(f)
-        wide = numpy.concatenate(folded, axis=1)
-        tol = 1e-14 * (numpy.abs(wide).max() if wide.size else 0.0)
+        keep = significant_entries(desc, t, folded, _nstack(desc, nrows))
+        wide = numpy.concatenate([numpy.where(k, f, 0.0) for k, f in zip(keep, folded)], axis=1)
         # row blocks of the packed matrix are clusters of rows with similar member support
-        rows_order = t["packed_rows"] if "packed_rows" in t else cluster_rows(wide, tol, nseg=ncells)[0]
-        bp, bi, prog.blk_frag, prog.rb_order, prog.kpad = pack_blocks(wide[rows_order], tol, nseg=ncells, min_one=ncells > 1)
+        rows_order = t["packed_rows"] if "packed_rows" in t else cluster_rows(wide, 0.0, nseg=ncells)[0]
+        bp, bi, prog.blk_frag, prog.rb_order, prog.kpad = pack_blocks(wide[rows_order], 0.0, nseg=ncells, min_one=ncells > 1)
         prog.blk_ptr = numpy.ascontiguousarray(bp.reshape(-1), dtype=numpy.int32)
         prog.blk_kb = numpy.ascontiguousarray(bi.reshape(-1), dtype=numpy.int32)
         prog.row_perm = numpy.asarray(rows_order, dtype=numpy.int32)
@@ -815,6 +859,7 @@ def merged_split(desc, order, split):
             stacked[j * ndofs:(j + 1) * ndofs, :, :d["coeffs"].shape[2]] = d["coeffs"]
     out = dict(top)
     out["coeffs"] = stacked
+    out["nstack"] = len(split)
     return out
 
 
@@ -928,7 +973,7 @@ def macro_merged(desc, order, prog=None):
     d = {key: val for key, val in desc.items() if key not in ("nodes", "coeffs", "cell_node_map", "c0")}
     # first-match binning of the original tabulation (continuity is not None and order == 0, expansions.py:452)
     # must survive: the derived element is always tabulated at order 0 and is not a C0 set
-    d.update(c0=False, raw_members=True, unique=int(bool(desc["c0"]) and order == 0),
+    d.update(c0=False, raw_members=True, unique=int(bool(desc["c0"]) and order == 0), nstack=len(alphas),
              coeffs=numpy.ascontiguousarray(stacked.reshape(len(alphas) * ndofs, ncomp, ncells * nmem)),
              cell_node_map=(numpy.arange(nmem, dtype=numpy.int64)[None, :]
                             + nmem * numpy.arange(ncells, dtype=numpy.int64)[:, None]))

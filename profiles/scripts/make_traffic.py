@@ -1,28 +1,39 @@
-"""Summaries (profiles/r01_ncu_*.txt) and profiles/traffic.json from the `ncu --set full` reports pulled into
-gpurun_out/ by capture_r1.sh.  traffic = dram__bytes_read.sum + dram__bytes_write.sum over the launches of one
-step, keyed workload|kernel path|points per launch like bench.py looks it up."""
-import csv, json, os, subprocess, sys
+"""Summaries (profiles/rNN_ncu_*.txt) and profiles/traffic.json from the `ncu --set full` reports pulled into
+gpurun_out/ by capture_rN.sh.  traffic = dram__bytes_read.sum + dram__bytes_write.sum over the launches of one
+step, keyed workload|kernel path|points per launch like bench.py looks it up, and stamped with the hash of the
+kernel sources the captures were taken at (bench.py quotes an entry only while the stamp matches).
+usage: python profiles/scripts/make_traffic.py [r02]"""
+import csv, hashlib, json, os, subprocess, sys
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CAPS = {  # report -> (workload, kernel path, batch)
     "lattice_p8": ("p8_tet_o2", "lattice", 1 << 20), "mma_p8": ("p8_tet_o2", "simplex", 1 << 20),
-    "mma_n2curl_merged": ("n2curl4_tet_o1", "simplex", 1 << 20), "vals_hct": ("hct_o2", "simplex", 10_000_000),
+    "mma_p8_spectral": ("p8_spectral_tet_o2", "simplex", 1 << 20), "lattice_p3": ("p3_tri_o1", "lattice", 1 << 20),
+    "cells_walkington": ("walkington_tet_o2", "simplex", 1 << 20),
+    "mma_n2curl": ("n2curl4_tet_o1", "simplex", 1 << 20), "vals_hct": ("hct_o2", "simplex", 10_000_000),
     "vals_ps6": ("ps6_o2", "simplex", 10_000_000), "vals_ps12": ("ps12_o2", "simplex", 10_000_000),
     "tensor_hex": ("gll_q10_hex_o1", "tensor", 1 << 20),
 }
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+h = hashlib.sha256()
+src = os.path.join(ROOT, "fiat_b200", "csrc")
+for fname in sorted(os.listdir(src)):
+    if fname.endswith((".cu", ".cuh")):
+        h.update(open(os.path.join(src, fname), "rb").read())
 traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step from `ncu --set full` "
-                       "captures (profiles/r01_ncu_*.txt); key = workload|kernel path|points per launch"}
+                       f"captures (profiles/{TAG}_ncu_*.txt); key = workload|kernel path|points per launch",
+           "_csrc_stamp": h.hexdigest()[:16]}
 for name, (workload, path, batch) in CAPS.items():
-    rep = os.path.join(ROOT, "gpurun_out", f"r01_raw_{name}.csv")
+    rep = os.path.join(ROOT, "gpurun_out", f"{TAG}_raw_{name}.csv")
     if not os.path.exists(rep):
         print("missing", rep)
         continue
     summary = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "scripts", "ncu_summary.py"), rep],
                              capture_output=True, text=True).stdout
-    out = os.path.join(ROOT, "profiles", f"r01_ncu_{name}.txt")
+    out = os.path.join(ROOT, "profiles", f"{TAG}_ncu_{name}.txt")
     with open(out, "w") as f:
         f.write(f"# ncu --set full --clock-control none, the launches of one bench step ({workload}, {batch} points); "
-                f"raw metric page: r01_raw_{name}.csv (gpurun_out/, not tracked)\n" + summary)
+                f"raw metric page: {TAG}_raw_{name}.csv (gpurun_out/, not tracked)\n" + summary)
     raw = open(rep).read()
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]

@@ -6,7 +6,7 @@ import numpy
 from fiat_b200.plan import alpha_list
 
 
-def _jets(prog, cell, x):
+def _jets(prog, cell, x, fixups=True):
     """Run the Dubiner program of one cell at default-simplex coordinates x (sd, npts)."""
     sd, na = prog.sd, prog.na
     npts = x.shape[1]
@@ -39,13 +39,16 @@ def _jets(prog, cell, x):
                     if prog.low2[j, k] >= 0:
                         v = v + prog.mul2[j, k] * ddG[k] * T[prv, prog.low2[j, k]]
             T[nxt, j] = v
-    for (t, s), w in zip(prog.fix_idx, prog.fix_w):
-        T[t] -= w * T[s]
+    if fixups:
+        for (t, s), w in zip(prog.fix_idx, prog.fix_w):
+            T[t] -= w * T[s]
     return T
 
 
-def run_simplex(prog, pts, near):
-    """out[alpha_index, row, point] for already-transformed points and a membership matrix."""
+def run_simplex(prog, pts, near, packed=False):
+    """out[alpha_index, row, point] for already-transformed points and a membership matrix.
+    packed=True contracts with the matrices rebuilt from the 8x4 block packing (what the tile kernels multiply:
+    fix-ups folded in, insignificant entries dropped) instead of the dense per-cell matrices."""
     assert prog.expansion == 0
     sd = prog.sd
     npts = len(pts)
@@ -58,8 +61,8 @@ def run_simplex(prog, pts, near):
         A = prog.geom[c, :sd * sd].reshape(sd, sd)
         b = prog.geom[c, 9:9 + sd]
         x = (pts[ip] @ A.T + b).T
-        T = _jets(prog, c, x)
-        vals = numpy.einsum("rk,kap->arp", prog.ccell[c], T)
+        T = _jets(prog, c, x, fixups=not packed)
+        vals = numpy.einsum("rk,kap->arp", blocks_to_dense(prog, c) if packed else prog.ccell[c], T)
         out[:, :, ip] += vals / (1.0 if prog.unique else mult[None, None, ip])
     return out
 
