@@ -407,36 +407,51 @@ DROP_BUDGET = 1e-13         # the dropped entries of a row may together contribu
 
 def significant_entries(desc, t, folded, nstack=1):
     """Boolean mask of the coefficient entries the block packing must keep, per subcell matrix `folded[c]`
-    (rows x member slots).  The entries of a row are dropped smallest first, by their largest possible contribution
-    |C[r, m]| max_x |psi_m(x)|, as long as the dropped ones together stay below DROP_BUDGET of the largest entry of the
-    table the row belongs to (rows come in `nstack` equal groups: the derivative tables of a stacked derived
-    element) -- the north-star tolerance is 1e-12 of that maximum.  (A threshold relative to the largest
-    COEFFICIENT, as in round 1, is not enough once the members' magnitudes differ by orders of magnitude: the stacked
-    P12 triangle lost 1e-12 of its first-derivative tables that way.)  Member bounds and table maxima are sampled on a
-    lattice of the default simplex plus random points."""
+    (rows x member slots).  The folded matrices carry entries that are rounding noise of the reference's own
+    coefficient computation (exact zeros by symmetry that come out as 1e-16 of the largest coefficient); dropping
+    them is what makes the packing sparse.  First guess: everything below 1e-14 of the largest coefficient.  The guess
+    is then VERIFIED on sample points (a lattice of the default simplex plus random points): at every sample point the
+    function that a row loses, |sum_dropped C[r, m] psi_m(x)|, must stay below DROP_BUDGET of the largest entry
+    that the row's table has at that same point (rows come in `nstack` equal groups: the derivative tables of a
+    stacked derived element) -- the north-star tolerance is 1e-12 of the table's maximum over the caller's points,
+    whatever those are.  Rows that fail (members whose magnitudes differ by orders of magnitude: the stacked P12
+    triangle lost 1e-12 of its first-derivative tables to the first guess alone) get their entries dropped smallest
+    contribution first only as far as the same pointwise test allows."""
     sd, n = int(desc["sd"]), int(desc["degree"])
-    lat = n + 3
+    lat = n + 2
     idx = numpy.array([i for i in numpy.ndindex(*([lat + 1] * sd)) if sum(i) <= lat], dtype=float)
     rng = numpy.random.default_rng(20261020)
-    u = numpy.sort(rng.random((256, sd)), axis=1)
-    rnd = numpy.diff(numpy.concatenate([numpy.zeros((256, 1)), u], axis=1), axis=1)
-    x = numpy.concatenate([2.0 * idx / lat - 1.0, 2.0 * rnd - 1.0]).T          # (sd, npts) on the default simplex
+    u = numpy.sort(rng.random((192, sd)), axis=1)
+    rnd = numpy.diff(numpy.concatenate([numpy.zeros((192, 1)), u], axis=1), axis=1)
+    x = numpy.concatenate([2.0 * idx / lat - 1.0, 2.0 * rnd - 1.0])
+    if len(x) > 640:
+        x = x[rng.choice(len(x), 640, replace=False)]
+    x = x.T                                                                    # (sd, npts) on the default simplex
     V = numpy.empty((t["nslots"], x.shape[1]))
     V[numpy.asarray(t["slot_of"])] = _member_values(t, sd, x)                  # by slot
     bound = numpy.abs(V).max(axis=1)
+    cmax = max((float(numpy.abs(F).max()) if F.size else 0.0) for F in folded)
     keep = []
     for c, F in enumerate(folded):
-        scale = abs(float(t["geom"][c, 12]))
-        rowmax = numpy.abs(F @ V).max(axis=1) * scale
-        grp = rowmax.reshape(nstack, -1).max(axis=1)                            # largest entry of each stacked table
-        tabmax = numpy.repeat(grp, len(rowmax) // nstack)
-        w = numpy.abs(F) * (bound * scale)[None, :]
-        order = numpy.argsort(w, axis=1)
-        spent = numpy.cumsum(numpy.take_along_axis(w, order, axis=1), axis=1)
-        drop_sorted = spent <= DROP_BUDGET * tabmax[:, None]
-        k = numpy.ones_like(w, dtype=bool)
-        numpy.put_along_axis(k, order, ~drop_sorted, axis=1)
-        keep.append(k & (F != 0.0))
+        nrows = F.shape[0]
+        per = nrows // nstack
+        tab = numpy.abs(F @ V)                                                  # (rows, points); the cell's scale cancels
+        scale = numpy.maximum(tab.reshape(nstack, per, -1).max(axis=1), 1e-300)  # (nstack, points): table maximum at x
+        drop = numpy.abs(F) <= 1e-14 * cmax
+        lost = numpy.abs(numpy.where(drop, F, 0.0) @ V)                          # what every row loses, pointwise
+        grp = numpy.arange(nrows) // per
+        bad = numpy.flatnonzero((lost / scale[grp]).max(axis=1) > DROP_BUDGET)
+        for r0 in range(0, len(bad), 32):
+            rows = bad[r0:r0 + 32]
+            A = F[rows]
+            order = numpy.argsort(numpy.abs(A) * bound[None, :], axis=1)
+            As = numpy.take_along_axis(A, order, axis=1)                        # ascending contribution
+            cum = numpy.abs(numpy.cumsum(As[:, :, None] * V[order], axis=1))     # (R, K, points): lost function of a prefix
+            ratio = numpy.maximum.accumulate((cum / scale[grp[rows]][:, None, :]).max(axis=2), axis=1)
+            kr = numpy.ones(A.shape, dtype=bool)
+            numpy.put_along_axis(kr, order, ratio > DROP_BUDGET, axis=1)
+            drop[rows] = ~kr
+        keep.append(~drop & (F != 0.0))
     return keep
 
 
