@@ -352,7 +352,7 @@ def run_leg(workload, device, sampler, batch=None, flags=0, steps=10, parity_pts
     vpp, sd = values_per_point(desc, order)
     batch = batch or default_batch(workload, vpp)
     na = len(planmod.alpha_list(sd, order))
-    time.sleep(1.0)          # every leg starts from an idle GPU, like the headline (power / clocks settle)
+    time.sleep(2.5)          # every leg starts from an idle GPU, like the headline (the power cap's running average settles)
     t0 = time.perf_counter()
     tab = Tabulator(desc, device)
     pts = device_points(kind, batch, 4242, device)
