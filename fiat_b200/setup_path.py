@@ -1,6 +1,7 @@
 """Device versions of the reference's setup-path tabulations of an expansion set:
 
     ExpansionSet.tabulate / tabulate_derivatives / tabulate_jet   FIAT/expansions.py:601-637
+    ExpansionSet.tabulate_normal_jumps                             FIAT/expansions.py:492-530
     ExpansionSet.tabulate_jumps                                    FIAT/expansions.py:532-575
     ExpansionSet.get_dmats                                         FIAT/expansions.py:577-599
 
@@ -93,6 +94,45 @@ class ExpansionTabulator:
         v = self._cell_tabulator(cell).tabulate(1, lattice_points)
         rhs = torch.stack([v[a].T for a in planmod.multi_indices(sd, 1)])
         return torch.linalg.solve(v[(0,) * sd].T.unsqueeze(0).expand(sd, -1, -1), rhs)
+
+    # -- ExpansionSet.tabulate_normal_jumps(n, ref_pts, facet, order) ----------------------------------------------
+    def tabulate_normal_jumps(self, ref_pts, facet, order=0):
+        """tensor (order + 1, num_members, npts): jumps of the r-th normal derivative (r = 0..order) across parent
+        facet `facet` at points given on the reference facet (FIAT/expansions.py:492-530).  The r-th normal derivative
+        of a member is sum_{|alpha| = r} r! / alpha! n^alpha D^alpha phi; per-subcell tables come from the device,
+        subcell membership from the device binning."""
+        import math
+        es, sd = self.es, self.sd
+        complex_ = es.ref_el
+        transform = complex_.get_entity_transform(sd - 1, facet)
+        pts = numpy.ascontiguousarray(numpy.asarray(transform(numpy.asarray(ref_pts, dtype=float)), dtype=numpy.float64)).reshape(-1, sd)
+        cell_node_map = es.get_cell_node_map(self.n)
+        ncells = int(self.desc["ncells"])
+        if ncells > 1:
+            mask = self.tab.locate_subcells(pts, unique=False).cpu().numpy().astype(numpy.int64)
+        else:
+            mask = numpy.ones(len(pts), dtype=numpy.int64)
+        results = torch.zeros((order + 1, int(es.get_num_members(self.n)), len(pts)), dtype=torch.float64, device=self.device)
+        facet_normal = numpy.asarray(complex_.compute_normal(facet), dtype=float)
+        for cell in range(ncells):
+            ipts = numpy.flatnonzero((mask >> cell) & 1)
+            if len(ipts) == 0:
+                continue
+            normal = numpy.asarray(complex_.compute_normal(facet, cell=cell), dtype=float)
+            side = float(numpy.dot(normal, facet_normal))
+            phi = self._cell_tabulator(cell).tabulate(order, pts[ipts])
+            rows = torch.as_tensor(numpy.asarray(cell_node_map[cell]), device=self.device, dtype=torch.long)
+            cols = torch.as_tensor(ipts, device=self.device, dtype=torch.long)
+            for r in range(order + 1):
+                vr = None
+                for alpha in planmod.multi_indices(sd, r):
+                    w = math.factorial(r)
+                    for k, a in enumerate(alpha):
+                        w = w / math.factorial(a) * normal[k] ** a
+                    vr = w * phi[alpha] if vr is None else vr + w * phi[alpha]
+                sign = -1.0 if (r % 2 == 0 and side < 0) else 1.0
+                results[r][rows[:, None], cols[None, :]] += sign * vr
+        return results
 
     # -- ExpansionSet.tabulate_jumps(n, points, order) --------------------------------------------------------------
     def tabulate_jumps(self, points, order=0):

@@ -175,3 +175,23 @@ def test_pullback_folded_into_the_coefficients(name, mapping, cuda_device):
         assert abs(g - want).max() <= 1e-12 * max(abs(want).max(), 1e-300), (name, alpha)
     with pytest.raises(ValueError):
         Tabulator(case["desc"], cuda_device).mapped("no such piola", J=J)
+
+
+def test_expansion_set_normal_jumps_match_the_reference(cuda_device):
+    """ExpansionSet.tabulate_normal_jumps (FIAT/expansions.py:492-530): jumps of normal derivatives across a facet of
+    the split complex (interior facets have a subcell on either side) at points given on the reference facet."""
+    from fiat_b200.setup_path import ExpansionTabulator
+    FIAT = _reference()
+    rng = numpy.random.default_rng(23)
+    for label, es, n in _sets(FIAT):
+        sd = es.ref_el.get_spatial_dimension()
+        if sd == 1 or not es.ref_el.is_macrocell():      # the reference needs the complex's cell connectivity
+            continue
+        dev = ExpansionTabulator(es, n, cuda_device)
+        nfacets = len(es.ref_el.get_topology()[sd - 1])
+        for facet in range(0, nfacets, max(1, nfacets // 6)):
+            ref_pts = rng.random((9, 1)) if sd == 2 else _points(es, rng, 9)[:, :2]
+            want = es.tabulate_normal_jumps(n, ref_pts, facet, order=2)
+            got = dev.tabulate_normal_jumps(ref_pts, facet, order=2).cpu().numpy()
+            assert got.shape == want.shape, (label, facet)
+            assert abs(got - want).max() <= 1e-11 * max(abs(want).max(), 1.0), (label, facet)
