@@ -315,8 +315,11 @@ def _describe_hdivcurl(element):
     """Hdiv(...) / Hcurl(...) of a tensor-product element (FIAT/hdivcurl.py:43-108,165-254): the plain
     tensor-product table with its components placed (possibly rotated and sign-flipped) into a
     vector of the cell's dimension.  The placement is read off by comparing the wrapper's table with
-    the wrapped one at a few points, which covers every branch of the reference without re-deriving
-    its case analysis."""
+    the wrapped one at a few points (the wrapper only copies, permutes and negates values, so the
+    comparison is exact).  This covers every branch of the reference without re-deriving its case
+    analysis -- including the branch that does not do what its comment says (Hdiv of a covariant-Piola
+    second factor, hdivcurl.py:100-107, places the components un-rotated): the drop-in has to reproduce the
+    reference's tables, whatever they are."""
     inner = _describe_tensor(element)
     cell = element.get_reference_element()
     sd = int(cell.get_spatial_dimension())
