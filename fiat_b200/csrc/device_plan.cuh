@@ -28,7 +28,7 @@ struct RecTab {
     short fix_src[FB_MAX_FIX];
     double fix_w[FB_MAX_FIX];
     double geom0[FB_GEOM_DOUBLES];  // geometry of cell 0 (single-cell elements)
-    int nrb;                        // block-sparse coefficient matrix: row blocks, longest first
+    int nrb;                        // block-sparse coefficient matrix: row blocks in hand-out order (plan.py: schedule_row_blocks)
     short rb_order[FB_MAX_RB];
     int blk_ptr[FB_MAX_RB + 1];
     short row_perm[FB_MAX_RB * 8];  // packed row -> table row (-1: padding)

@@ -298,7 +298,8 @@ k_mma(const DevSimplex P, const __grid_constant__ RecTab tab, const DevEntity E,
     const size_t astride = (size_t)M.total_rows * ostride;      // distance between derivative tables
     const double* Tlane = T + g;                        // + member slot * ldT, gathered per block
     const int ldT = G.ldT;
-    // Work items are handed out dynamically (longest row blocks first).  The NEXT item and its first coefficient
+    // Work items are handed out dynamically (long and short row blocks alternate, plan.py: schedule_row_blocks, so that
+    // the warps do not reach their store epilogues in lockstep).  The NEXT item and its first coefficient
     // fragments are fetched before the current item's stores are issued, so that the L2 latency of the fragments and
     // the shared-memory atomic overlap the store epilogue instead of delaying the next item's first DMMA.
     double a_cur[CH], a_nxt[CH];

@@ -81,7 +81,8 @@ typedef struct {
     const int32_t* blk_ptr;    /* nrb + 1 */
     const int32_t* blk_kb;     /* 4 x nblk member slots */
     const double* blk_frag;    /* nblk x 32 */
-    const int32_t* rb_order;   /* nrb, longest row block first */
+    const int32_t* rb_order;   /* nrb: order in which row blocks are handed out to the warps (long and short
+                                  blocks alternate, fiat_b200/plan.py: schedule_row_blocks) */
     const int32_t* row_perm;   /* nrows: packed row i holds table row row_perm[i] (rows are clustered by member
                                   support so that fewer blocks are stored) */
     /* Derivative-folded coefficients for the value-table kernel (optional, ncp == 0: absent).  D^alpha of an
