@@ -429,6 +429,14 @@ class Tabulator:
         return launches, total_rows, pdim, (ndofs,) + vs, zero
 
     # -- calls --------------------------------------------------------------------------------
+    def _single_point(self, points, pdim):
+        """One point given as a bare coordinate tuple, shape (sd,): the reference's tables then have no point axis
+        (CiarletElement only; test/FIAT/unit/test_fiat.py test_single_point_tabulation, test_regge_hhj.py)."""
+        if self.kind != "simplex" or pdim == 0:
+            return False
+        shape = tuple(points.shape) if isinstance(points, (torch.Tensor, numpy.ndarray)) else numpy.shape(points)
+        return shape == (pdim,)
+
     def _points(self, points, pdim):
         if isinstance(points, torch.Tensor):
             pts = points.to(device=self.device, dtype=torch.float64)
@@ -526,6 +534,8 @@ class Tabulator:
         alphas = self.alphas(order)
         out = torch.empty((len(alphas), nrows, npts), dtype=torch.float64, device=self.device)
         self._run(launches, zero, pts, out, npts, npts, flags)
+        if self._single_point(points, pdim):
+            return {a: out[j].reshape(prefix) for j, a in enumerate(alphas)}
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
     def tabulate_into(self, out, order, points, entity=None, flags=0):
@@ -603,6 +613,8 @@ class Tabulator:
                     zero.numel() if zero is not None else 0, pts.ctypes.data, npts, pdim, out.ctypes.data, chunk_pts,
                     (flags & 11) | functools.reduce(lambda a, b: a | b, (p.force_flags for p, _, _, _ in launches
                                                                          if p is not None), 0)))
+        if self._single_point(points, pdim):
+            return {a: out[j].reshape(prefix) for j, a in enumerate(alphas)}
         return {a: out[j].reshape(prefix + (npts,)) for j, a in enumerate(alphas)}
 
     def tabulate_factors(self, order, points, entity=None):

@@ -1113,15 +1113,30 @@ def resolve_parts(desc, entity=None):
 
 
 def _flat(key):
-    return sum(key) if isinstance(key, (list, tuple)) else int(key)
+    return sum(_flat(k) for k in key) if isinstance(key, (list, tuple)) else int(key)
+
+
+def _norm_key(key):
+    return [_norm_key(k) for k in key] if isinstance(key, (list, tuple)) else int(key)
 
 
 def _count(top, key):
-    key = list(key) if isinstance(key, (list, tuple)) else int(key)
+    key = _norm_key(key)
     for k, cnt in top:
-        if k == key:
+        if _norm_key(k) == key:
             return cnt
     raise KeyError(f"no entities of dimension {key}")
+
+
+def dimension_key(desc):
+    """ref_el.get_dimension() of the described element: an int on simplices and flattened cells, a (possibly
+    nested) tuple on tensor-product cells (FIAT/reference_element.py TensorProductCell.get_dimension)."""
+    kind = desc["kind"]
+    if kind == "tensor":
+        return (dimension_key(desc["A"]), dimension_key(desc["B"]))
+    if kind == "composite":
+        return dimension_key(desc["parts"][0]["element"])
+    return _cell_dim(desc)
 
 
 def flatten_tensor(desc, entity=None, point_offset=0):
@@ -1149,7 +1164,7 @@ def flatten_tensor(desc, entity=None, point_offset=0):
     if kind != "tensor":
         raise ValueError(kind)
     if entity is None:
-        entity = ((_cell_dim(desc["A"]), _cell_dim(desc["B"])), 0)
+        entity = (dimension_key(desc), 0)
     (dA, dB), eid = entity
     shape = (_count(desc["topA"], dA), _count(desc["topB"], dB))
     if not 0 <= eid < shape[0] * shape[1]:

@@ -442,6 +442,11 @@ def _tabulate_simplex(desc, order, pts, entity):
     sd = int(desc["sd"])
     pts = numpy.asarray(pts, dtype=float)
     tr = resolve_entity(desc, entity)
+    # one point given as a bare coordinate tuple: tables without a point axis (numpy broadcasting in
+    # expansions.py:411-447; test/FIAT/unit/test_fiat.py test_single_point_tabulation)
+    single = pts.ndim == 1 and pts.shape[0] > 0 and pts.shape[0] == (sd if tr is None else tr[0].shape[0])
+    if single:
+        pts = pts[None, :]
     if tr is not None:
         C, off = tr
         pts = pts.reshape(len(pts), C.shape[0])
@@ -455,19 +460,32 @@ def _tabulate_simplex(desc, order, pts, entity):
     for j, alpha in enumerate(all_alphas(sd, order)):
         # polynomial_set.py:71 -- same contraction, laid out so that numpy hands it to dgemm
         vals = numpy.dot(flat, numpy.ascontiguousarray(base[:, j, :]))
-        result[alpha] = vals.reshape((coeffs.shape[0],) + vs + (pts.shape[0],))
+        result[alpha] = vals.reshape((coeffs.shape[0],) + vs + (() if single else (pts.shape[0],)))
     return result
+
+
+def _norm_key(key):
+    return [_norm_key(k) for k in key] if isinstance(key, (list, tuple)) else int(key)
 
 
 def _key_count(top, key):
     for k, cnt in top:
-        if k == key or (isinstance(k, list) and list(key) == k):
+        if _norm_key(k) == _norm_key(key):
             return cnt
     raise KeyError(key)
 
 
 def _flat_dim(key):
-    return sum(key) if isinstance(key, (list, tuple)) else int(key)
+    return sum(_flat_dim(k) for k in key) if isinstance(key, (list, tuple)) else int(key)
+
+
+def dimension_key(desc):
+    """ref_el.get_dimension(): nested tuples on (nested) tensor-product cells -- FIAT/tensor_product.py:234-235."""
+    if desc["kind"] == "tensor":
+        return (dimension_key(desc["A"]), dimension_key(desc["B"]))
+    if desc["kind"] == "composite":
+        return dimension_key(desc["parts"][0]["element"])
+    return cell_dimension(desc)
 
 
 def cell_dimension(desc):
@@ -484,7 +502,7 @@ def _tabulate_tensor(desc, order, pts, entity):
     """TensorProductElement.tabulate, scalar x scalar -- FIAT/tensor_product.py:231-292."""
     sdA, sdB = cell_dimension(desc["A"]), cell_dimension(desc["B"])
     if entity is None:
-        entity = ((sdA, sdB), 0)
+        entity = (dimension_key(desc), 0)
     (dA, dB), eid = entity
     dA = tuple(dA) if isinstance(dA, (list, tuple)) else dA
     dB = tuple(dB) if isinstance(dB, (list, tuple)) else dB

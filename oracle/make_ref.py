@@ -9,6 +9,9 @@ without /root/reference can import them:
                                     the package __init__ is left empty so that the rest of gem is not pulled in)
     oracle/_ref/recursivenodes/  <- tests/golden/gen/recursivenodes/     (our stand-in for the un-vendored PyPI
                                     package; construction-time only)
+    oracle/_ref/ref_tests/       <- /root/reference/test/FIAT/unit/test_*.py  (the reference's own unit tests, run by
+                                    tests/test_reference_suite.py with the tabulation path swapped out,
+                                    oracle/dropin_plugin.py)
 
 Run by `__graft_entry__.build()` in the build container whenever /root/reference is present; on the GPU box the
 already materialised copy is used.  Nothing under oracle/_ref/ is committed.
@@ -39,6 +42,12 @@ def make(force=False):
     open(os.path.join(OUT, "gem", "__init__.py"), "w").close()
     shutil.copytree(os.path.join(HERE, "..", "tests", "golden", "gen", "recursivenodes"),
                     os.path.join(OUT, "recursivenodes"), ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    tests_src = os.path.join(REF, "test", "FIAT", "unit")
+    if os.path.isdir(tests_src):
+        os.makedirs(os.path.join(OUT, "ref_tests"))
+        for name in sorted(os.listdir(tests_src)):
+            if name.startswith("test_") and name.endswith(".py"):
+                shutil.copy(os.path.join(tests_src, name), os.path.join(OUT, "ref_tests", name))
     os.utime(stamp)
     return OUT
 

@@ -20,6 +20,10 @@ def golden_case_names():
                   for p in glob.glob(os.path.join(GOLDEN, "case_*.npz")))
 
 
+def _as_tuples(key):
+    return tuple(_as_tuples(k) for k in key) if isinstance(key, list) else key
+
+
 def load_case(name):
     from fiat_b200 import description
     case = description.load(os.path.join(GOLDEN, f"case_{name}.npz"))
@@ -28,7 +32,7 @@ def load_case(name):
         case["entity"] = None
     else:
         dim, eid = ent
-        case["entity"] = (tuple(dim) if isinstance(dim, list) else dim, eid)
+        case["entity"] = (_as_tuples(dim), eid)
     case["ref"] = {tuple(k): v for k, v in zip(case["keys"], case["values"])}
     case["error_keys"] = [tuple(k) for k in case.get("error_keys", [])]    # slots holding exception objects (trace elements)
     return case

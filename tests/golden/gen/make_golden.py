@@ -170,6 +170,10 @@ def membership(complex_, pts, unique):
 ONLY = None        # set by `--only name1,name2`: write just these cases (the rng stream is still consumed in order)
 
 
+def _as_lists(key):
+    return [_as_lists(k) for k in key] if isinstance(key, tuple) else int(key)
+
+
 def write_case(name, element, order, pts, entity=None, with_cells=False, table_stride=1):
     """table_stride > 1: the reference tables are stored for pts[::table_stride] only (large adversarial sets);
     the subcell membership matrices always cover all points (`mask_points`)."""
@@ -187,7 +191,7 @@ def write_case(name, element, order, pts, entity=None, with_cells=False, table_s
         "desc": desc,
         "order": order,
         "points": numpy.asarray(pts, dtype=float),
-        "entity": "none" if entity is None else [entity[0] if not isinstance(entity[0], tuple) else list(entity[0]), int(entity[1])],
+        "entity": "none" if entity is None else [_as_lists(entity[0]), int(entity[1])],
         "keys": [list(k) for k in ref.keys()],
         "values": [numpy.asarray(v, dtype=float) for v in ref.values()],
     }
@@ -427,6 +431,17 @@ def main():
     write_case("hdivtrace_prism_top_o0", trp, 0, simplex_points(rng2, 6, 2), entity=((2, 0), 1))
     qpts = simplex_points(rng2, 6, 2)
     write_case("quadrature6_tri_o0", FIAT.QuadratureElement(T2, qpts), 0, qpts)
+
+    # (round 2, found by running the reference's own unit tests over the drop-in) tensor products of tensor products
+    # that are NOT flattened: the default entity and entity keys are nested tuples (tensor_product.py:234-250)
+    rng3 = numpy.random.default_rng(20261020)
+    nested = TPE(TPE(P1, DP1), P2)
+    write_case("nested_tpe_o1", nested, 1, rng3.random((7, 3)))
+    write_case("nested_tpe_o2", TPE(TPE(P2, P1), TPE(DP1, P2)), 2, rng3.random((7, 4)))
+    write_case("nested_tpe_face_o1", nested, 1, rng3.random((7, 2)), entity=(((1, 0), 1), 1))
+    write_case("nested_tpe_edge_o1", nested, 1, rng3.random((7, 1)), entity=(((0, 0), 1), 3))
+    write_case("nested_prism_x_interval_o1", TPE(TPE(FIAT.Lagrange(T2, 2), P1), DP1), 1,
+               numpy.concatenate([simplex_points(rng3, 7, 2), rng3.random((7, 2))], axis=1))
 
     # element descriptions alone, for bench.py and full-size GPU tests
     for nm, el in () if ONLY is not None else (("p8_tet", FIAT.Lagrange(T3, 8)), ("n2curl4_tet", FIAT.NedelecSecondKind(T3, 4)),

@@ -185,6 +185,27 @@ def test_point_containers_and_error_contract(cuda_device):
         tab.tabulate(1, numpy.array([[object(), object()]], dtype=object))
 
 
+@pytest.mark.parametrize("name,entity", [("p3_tri_o1", None), ("regge2_tet_o1", None), ("p2_tri_facet1_o1", (1, 1)),
+                                         ("hct_o2", None)])
+def test_single_point_without_point_axis(name, entity, cuda_device):
+    """A bare coordinate tuple of shape (sd,) is ONE point and the tables lose their point axis, like the reference's
+    (test/FIAT/unit/test_fiat.py test_single_point_tabulation, test_regge_hhj.py); found by running the reference's
+    unit tests over the drop-in (tests/test_reference_suite.py)."""
+    from fiat_b200.api import Tabulator
+    case = load_case(name)
+    tab = Tabulator(case["desc"], cuda_device)
+    p = tuple(float(x) for x in numpy.asarray(case["points"])[3])
+    batched = tab.tabulate(1, [p], entity)
+    want = fiat_oracle.tabulate(case["desc"], 1, p, entity)
+    for got in (tab.tabulate(1, p, entity), tab.tabulate(1, numpy.array(p), entity), tab.tabulate_host(1, p, entity)):
+        assert list(got) == list(batched)
+        for alpha, v in got.items():
+            assert tuple(v.shape) == tuple(batched[alpha].shape[:-1]) == want[alpha].shape
+            assert numpy.array_equal(numpy.asarray(v.cpu() if isinstance(v, torch.Tensor) else v),
+                                     batched[alpha][..., 0].cpu().numpy())
+    _compare(case["desc"], tab.tabulate(1, p, entity), want)
+
+
 def test_empty_point_set(cuda_device):
     from fiat_b200.api import Tabulator
     case = load_case("p3_tri_o1")

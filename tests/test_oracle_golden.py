@@ -30,3 +30,17 @@ def test_oracle_subcell_assignment_bit_exact(name):
     desc, pts = case["desc"], case.get("mask_points", case["points"])
     assert numpy.array_equal(fiat_oracle.locate_cells(desc, pts, unique=False), case["near_all"])
     assert numpy.array_equal(fiat_oracle.locate_cells(desc, pts, unique=True), case["near_unique"])
+
+
+@pytest.mark.parametrize("name,entity", [("p3_tri_o1", None), ("regge2_tet_o1", None), ("p2_tri_facet1_o1", (1, 1))])
+def test_oracle_single_point_has_no_point_axis(name, entity):
+    """test/FIAT/unit/test_fiat.py test_single_point_tabulation: a bare coordinate tuple is one point and the
+    tables have shape (ndofs,) + value_shape."""
+    case = load_case(name)
+    p = tuple(float(x) for x in numpy.asarray(case["points"])[3])
+    one = fiat_oracle.tabulate(case["desc"], 1, p, entity)
+    batched = fiat_oracle.tabulate(case["desc"], 1, [p], entity)
+    for alpha, v in one.items():
+        assert v.shape == batched[alpha].shape[:-1]
+        assert numpy.array_equal(v, batched[alpha][..., 0])
+        assert numpy.allclose(v, case["ref"][alpha][..., 3], rtol=0, atol=1e-12 * max(abs(case["ref"][alpha]).max(), 1.0))

@@ -1,0 +1,72 @@
+"""The reference's OWN unit tests, run with `tabulate` swapped for the drop-in.
+
+`oracle/make_ref.py` materialises the reference package and its `test/FIAT/unit/test_*.py` files under the git-ignored
+`oracle/_ref/` (it travels to the GPU box); `oracle/dropin_plugin.py` replaces every `tabulate` on the hot path
+before those tests are collected.  The reference's known-answer tests -- exact Dubiner values, nodality, partition of
+unity, macro-element continuity, tensor-product dof order, trace elements -- then judge
+
+    not gpu:  the CPU oracle (`FIATB200_DROPIN=oracle`) -- pins the oracle with the reference's own assertions
+    gpu:      the CUDA path  (`FIATB200_DROPIN=device`, numpy in / numpy out through the C ABI)
+
+The default selection is the files that exercise tabulation most (about 680 tests); `FIATB200_REF_SUITE=full` runs all
+36 files.  Tests that need `gem` / `sympy`-through-gem (absent here: test_precision.py, test_macro.py::test_macro_gem /
+test_macro_sympy) fail the same way without the plugin and are left out.
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+REF_TESTS = os.path.join(REF, "ref_tests")
+DEFAULT_FILES = ["test_fiat.py", "test_tensor_product.py", "test_regge_hhj.py", "test_macro.py", "test_hdivtrace.py",
+                 "test_discontinuous_taylor.py", "test_serendipity.py", "test_quadrature_element.py"]
+NEEDS_GEM = "not macro_gem and not macro_sympy"
+
+
+def _run(mode, tmp_path, workers):
+    if not os.path.isdir(REF_TESTS):
+        pytest.skip("oracle/_ref/ref_tests absent (python -c 'import __graft_entry__ as g; g.build()' makes it where "
+                    "/root/reference exists)")
+    if os.environ.get("FIATB200_REF_SUITE") == "full":
+        targets = [REF_TESTS, f"--ignore={os.path.join(REF_TESTS, 'test_precision.py')}"]
+    else:
+        targets = [os.path.join(REF_TESTS, f) for f in DEFAULT_FILES]
+    stats_file = tmp_path / "dropin_stats.jsonl"
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([REF, ROOT]), FIATB200_DROPIN=mode,
+               FIATB200_DROPIN_STATS=str(stats_file))
+    cmd = [sys.executable, "-m", "pytest", "-p", "oracle.dropin_plugin", "-q", "-p", "no:cacheprovider",
+           "-c", os.devnull, "--rootdir", str(tmp_path), "-k", NEEDS_GEM, "-n", str(workers)] + targets
+    res = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=3000)
+    tail = res.stdout[-4000:] + res.stderr[-2000:]
+    assert res.returncode == 0, tail
+    m = re.search(r"(\d+) passed", res.stdout)
+    assert m and int(m.group(1)) >= 600, tail
+    replaced = fallback = 0
+    reasons = {}
+    with open(stats_file) as f:
+        for line in f:
+            rec = json.loads(line)
+            replaced += rec["replaced"]
+            fallback += rec["fallback"]
+            reasons.update(rec["fallback_reasons"])
+    # the replacement must actually have been what the tests judged
+    assert replaced >= 700, (replaced, fallback, reasons)
+    assert fallback <= replaced // 10, (replaced, fallback, reasons)
+    # nothing but what the docstring of the plugin lists is handed back to the reference
+    for reason in reasons:
+        assert "symbolic points" in reason or "elements on a point" in reason, reasons
+    return replaced, fallback
+
+
+def test_reference_unit_tests_judge_the_oracle(tmp_path):
+    _run("oracle", tmp_path, workers=4)
+
+
+@pytest.mark.gpu
+def test_reference_unit_tests_judge_the_device_path(tmp_path):
+    _run("device", tmp_path, workers=2)
