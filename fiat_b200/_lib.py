@@ -29,6 +29,7 @@ class SimplexProgramStruct(ctypes.Structure):
         ("nrb", c_i32), ("kpad", c_i32), ("nblk", c_i32),
         ("blk_ptr", p_i32), ("blk_kb", p_i32), ("blk_frag", p_dbl), ("rb_order", p_i32), ("row_perm", p_i32),
         ("cderiv", p_dbl), ("cderiv_len", c_i64), ("ncp", c_i32), ("blk_cells", c_i32),
+        ("cstream", p_dbl), ("cstream_len", c_i64), ("cstep_ptr", p_i32), ("cnsteps", c_i32), ("crb", c_i32),
     ]
 
 
@@ -158,6 +159,8 @@ def simplex_struct(prog):
     s.blk_ptr, s.blk_kb, s.blk_frag, s.rb_order = i32(prog.blk_ptr), i32(prog.blk_kb), f64(prog.blk_frag), i32(prog.rb_order)
     s.row_perm = i32(prog.row_perm if len(prog.row_perm) else numpy.arange(prog.nrows))
     s.cderiv, s.cderiv_len, s.ncp = f64(prog.cderiv), int(numpy.size(prog.cderiv)), int(prog.ncp)
+    s.cstream, s.cstream_len = f64(prog.cstream), int(numpy.size(prog.cstream))
+    s.cstep_ptr, s.cnsteps, s.crb = i32(prog.cstep_ptr), len(prog.cstep_ptr) - 1, int(prog.crb)
     return s, keep
 
 

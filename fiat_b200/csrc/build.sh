@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 mkdir -p _obj
 deps_fiat_b200="fiat_b200.cu host_plan.cuh device_plan.cuh expansion.cuh kernels.cuh lattice.cuh ../../include/fiat_b200.h"
 deps_small_launch="small_launch.cu host_plan.cuh device_plan.cuh expansion.cuh small.cuh ../../include/fiat_b200.h"
-deps_cells_launch="cells_launch.cu host_plan.cuh device_plan.cuh expansion.cuh cells.cuh ../../include/fiat_b200.h"
+deps_cells_launch="cells_launch.cu host_plan.cuh device_plan.cuh expansion.cuh cells.cuh cells_reg.cuh ../../include/fiat_b200.h"
 deps_vals_launch="vals_launch.cu host_plan.cuh device_plan.cuh expansion.cuh small.cuh vals.cuh ../../include/fiat_b200.h"
 deps_cluster="cluster.cu ../../include/fiat_b200.h"
 pids=""

@@ -1,6 +1,7 @@
-// Launcher of the split-cell tile kernel (cells.cuh); its own translation unit (parallel compilation).
+// Launchers of the split-cell tile kernels (cells_reg.cuh, cells.cuh); their own translation unit (parallel compilation).
 #include "host_plan.cuh"
 #include "cells.cuh"
+#include "cells_reg.cuh"
 
 namespace {
 
@@ -34,6 +35,43 @@ bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
     return false;
 }
 
+// register-operand kernel (cells_reg.cuh): 16 warps x 2 octets of columns, fixed-k block stream
+bool cells_reg_geometry(const fiatb200_plan* plan, CellsRegGeom* G, size_t* smem_out) {
+    const DevSimplex& P = plan->simplex;
+    if (fb_tuning().cells_reg == 0) return false;                  // FIATB200_CELLS_REG=0: segment kernel (experiments)
+    if (P.cnsteps <= 0 || P.crb <= 0 || P.kpad > 64 || P.ncells < 2 || P.ncells > 24 || P.sd < 2) return false;
+    if (P.expansion != 0 || P.order != 0 || plan->tab.nrb == 0 || plan->tab.nrb > P.cnsteps * P.crb) return false;
+    const int threads = 512, pts_cap = (threads / 32) * 16;
+    const int pt = pts_cap - 8 * P.ncells;                        // subcell ranges are padded to octets
+    int ld = pts_cap;
+    while ((ld & 15) != 8) ++ld;
+    const int maxlev = std::max(1, plan->tab.nsteps);
+    const int sp = pt + 2;
+    const int astage = (P.cmaxstep + 1) & ~1;
+    const int uoff = ((pts_cap + pts_cap / 8 + 1) / 2 + 1) & ~1;
+    const size_t phase01 = (size_t)P.kpad * ld + 6 * (size_t)pts_cap + 4 * (size_t)maxlev;
+    const size_t phase2 = 2 * (size_t)P.crb * 8 * sp + 2 * (size_t)astage;
+    const size_t bytes = ((size_t)uoff + std::max(phase01, phase2)) * sizeof(double) + 64;
+    if (bytes > (size_t)plan->max_smem_optin - 1024) return false;
+    G->PT = pt; G->PTS = pts_cap; G->ldT = ld; G->maxlev = maxlev; G->threads = threads; G->SP = sp;
+    G->astage = astage; G->uoff = uoff;
+    *smem_out = bytes;
+    return true;
+}
+
+template <int SD, int KB>
+int launch_cells_reg(const fiatb200_plan* plan, const DevEntity& E, const CellsRegGeom& G, size_t smem, const double* pts,
+                     long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
+    int rc = fb_set_smem(k_cells_reg<SD, KB>, smem);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((npts + G.PT - 1) / G.PT);
+    k_cells_reg<SD, KB><<<grid, G.threads, smem, st>>>(plan->simplex, plan->tab, plan->small_tab, E, G, pts, npts, ldp,
+                                                              out, ostride);
+    fb_launches++;
+    FB_CUDA(cudaGetLastError());
+    return FIATB200_OK;
+}
+
 template <int SD, int CH>
 int launch_cells(const fiatb200_plan* plan, const DevEntity& E, const CellsGeom& G, size_t smem, const double* pts,
                  long long npts, long long ldp, double* out, long long ostride, cudaStream_t st) {
@@ -51,14 +89,28 @@ int launch_cells(const fiatb200_plan* plan, const DevEntity& E, const CellsGeom&
 
 bool fb_cells_applicable(const fiatb200_plan* plan) {
     CellsGeom G;
+    CellsRegGeom R;
     size_t smem = 0;
-    return cells_geometry(plan, &G, &smem);
+    return cells_reg_geometry(plan, &R, &smem) || cells_geometry(plan, &G, &smem);
 }
 
 int fb_dispatch_cells(const fiatb200_plan* plan, const DevEntity& E, const double* pts, long long npts, long long ldp,
                       double* out, long long ostride, cudaStream_t st) {
     CellsGeom G;
     size_t smem = 0;
+    CellsRegGeom R;
+    if (cells_reg_geometry(plan, &R, &smem)) {
+        const int kb = plan->simplex.kpad / 4;
+#define FB_CELLS_REG_LAUNCH(SD_)                                                                                   \
+    if (kb <= 3) return launch_cells_reg<SD_, 3>(plan, E, R, smem, pts, npts, ldp, out, ostride, st);              \
+    if (kb <= 6) return launch_cells_reg<SD_, 6>(plan, E, R, smem, pts, npts, ldp, out, ostride, st);              \
+    if (kb <= 9) return launch_cells_reg<SD_, 9>(plan, E, R, smem, pts, npts, ldp, out, ostride, st);              \
+    if (kb <= 14) return launch_cells_reg<SD_, 14>(plan, E, R, smem, pts, npts, ldp, out, ostride, st);            \
+    return launch_cells_reg<SD_, 16>(plan, E, R, smem, pts, npts, ldp, out, ostride, st);
+        if (plan->simplex.sd == 2) { FB_CELLS_REG_LAUNCH(2) }
+        FB_CELLS_REG_LAUNCH(3)
+#undef FB_CELLS_REG_LAUNCH
+    }
     if (!cells_geometry(plan, &G, &smem))
         return fb_fail(FIATB200_ERR_UNSUPPORTED, "split-cell tile kernel not applicable to this plan");
     // fragments prefetched per segment: enough for the plan's longest (row block, subcell) segment, at most 8

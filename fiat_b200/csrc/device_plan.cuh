@@ -56,6 +56,9 @@ struct DevSimplex {
     const double* cderiv;       // derivative-folded coefficients of the value-table kernel (ncp == 0: absent)
     int cderiv_len, ncp;
     int blk_cells;              // > 1: blk_ptr is blk_cells x (nrb + 1), one block-sparse matrix per subcell
+    const double* cstream;      // fixed-k block stream of the register-operand split-cell kernel (cnsteps == 0: absent)
+    const int* cstep_ptr;       // cnsteps + 1 offsets in doubles
+    int cnsteps, crb, cmaxstep; // steps, row blocks per step, longest step in doubles
 };
 
 // Placement of a kernel's rows inside a larger table (wrapper elements: enriched, mixed, H(div)/H(curl)

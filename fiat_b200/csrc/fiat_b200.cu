@@ -24,6 +24,7 @@ const FbTuning& fb_tuning() {
         v.vals_tpc = geti("FIATB200_VALS_TPC");
         v.vals_j = geti("FIATB200_VALS_J");
         v.mma_wl = geti("FIATB200_MMA_WARPLOCAL");
+        v.cells_reg = geti("FIATB200_CELLS_REG");
         return v;
     }();
     return t;
@@ -464,6 +465,13 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     const size_t o_rb_order = A.add(h->rb_order, sizeof(int32_t) * h->nrb);
     const bool has_cderiv = h->ncp > 0 && h->cderiv && h->cderiv_len > 0;
     const size_t o_cderiv = A.add(h->cderiv, has_cderiv ? sizeof(double) * (size_t)h->cderiv_len : 0);
+    const bool has_cstream = h->cstream && h->cstream_len > 0 && h->cstep_ptr && h->cnsteps > 0 && h->crb > 0;
+    if (has_cstream && (h->cstep_ptr[h->cnsteps] != h->cstream_len || h->cnsteps * h->crb * 8 < h->nrows)) {
+        delete plan;
+        return fb_fail(FIATB200_ERR_ARG, "fixed-k block stream does not match its step table");
+    }
+    const size_t o_cstream = A.add(h->cstream, has_cstream ? sizeof(double) * (size_t)h->cstream_len : 0);
+    const size_t o_cstep = A.add(h->cstep_ptr, has_cstream ? sizeof(int32_t) * (size_t)(h->cnsteps + 1) : 0);
 
     cudaError_t e = cudaMalloc(&plan->blob, A.host.size() + 256);
     if (e == cudaSuccess) e = cudaMemcpy(plan->blob, A.host.data(), A.host.size(), cudaMemcpyHostToDevice);
@@ -497,6 +505,12 @@ int fiatb200_simplex_plan_create(const fiatb200_simplex_program* h, fiatb200_pla
     P.cderiv_len = has_cderiv ? (int)h->cderiv_len : 0;
     P.ncp = has_cderiv ? h->ncp : 0;
     P.blk_cells = blk_cells > 1 ? blk_cells : 0;
+    P.cstream = at<double>(b, o_cstream);
+    P.cstep_ptr = at<int>(b, o_cstep);
+    P.cnsteps = has_cstream ? h->cnsteps : 0;
+    P.crb = has_cstream ? h->crb : 0;
+    P.cmaxstep = 0;
+    for (int i = 0; i < P.cnsteps; ++i) P.cmaxstep = std::max(P.cmaxstep, h->cstep_ptr[i + 1] - h->cstep_ptr[i]);
     plan->max_segment = 0;
     for (int i = 0; i < blk_cells * (h->nrb + 1) - 1; ++i)
         if ((i + 1) % (h->nrb + 1) != 0) plan->max_segment = std::max(plan->max_segment, h->blk_ptr[i + 1] - h->blk_ptr[i]);

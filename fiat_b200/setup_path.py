@@ -4,14 +4,14 @@
     ExpansionSet.tabulate_normal_jumps                             FIAT/expansions.py:492-530
     ExpansionSet.tabulate_jumps                                    FIAT/expansions.py:532-575
     ExpansionSet.get_dmats                                         FIAT/expansions.py:577-599
+    DualSet.to_riesz                                               FIAT/dual_set.py:86-206   (to_riesz below)
 
 All of them are `ExpansionSet._tabulate` (:449-490) or `_tabulate_on_cell` (:411-447) of the set itself, i.e. the
 tabulation of the "element" whose coefficient tensor is the identity (extract.describe_expansion_set), followed by
 re-packing of the tables; they run through the same plans and kernels as `FiniteElement.tabulate`.  The reference uses
 them while it CONSTRUCTS elements (macro.py, polynomial_set.py), where results feed linear solves whose output must
 stay bit-compatible with numpy for the coefficients to be identical -- so these are offered beside the reference
-(parity to the tabulation tolerance), not wired into element construction.  `DualSet.to_riesz`
-(FIAT/dual_set.py:86-206) is not covered.
+(parity to the tabulation tolerance), not wired into element construction.
 """
 import numpy
 import torch
@@ -20,7 +20,7 @@ from . import plan as planmod
 from .api import Tabulator
 from .extract import describe_expansion_set
 
-__all__ = ["ExpansionTabulator"]
+__all__ = ["ExpansionTabulator", "to_riesz"]
 
 
 class ExpansionTabulator:
@@ -180,3 +180,98 @@ class ExpansionTabulator:
                     cur += len(ipts)
             jumps[r] = jr
         return jumps
+
+
+def _is_moment(ell):
+    """isinstance(ell, (functional.IntegralMoment, functional.IntegralMomentOfDerivative)) without importing the
+    reference (FIAT/dual_set.py:128): these carry their own quadrature rule `Q`."""
+    return any(c.__name__ in ("IntegralMoment", "IntegralMomentOfDerivative") for c in type(ell).__mro__)
+
+
+def _quadratures_to_points(nodes, deriv):
+    """FIAT/dual_set.py:121-149: functionals grouped by the quadrature rule they integrate with (None: point
+    functionals), the points of every group, and the sorted union of all points."""
+    from collections import defaultdict
+    groups = defaultdict(list)
+    for i, ell in enumerate(nodes):
+        if len(ell.deriv_dict if deriv else ell.pt_dict) == 0:
+            continue
+        groups[ell.Q if _is_moment(ell) else None].append(i)
+    pts, group_pts = set(), {}
+    for Q, ells in groups.items():
+        if Q is None:
+            cur = set()
+            for i in ells:
+                cur.update((nodes[i].deriv_dict if deriv else nodes[i].pt_dict).keys())
+            cur = tuple(cur)
+        else:
+            cur = tuple(map(tuple, Q.pts))
+        group_pts[Q] = cur
+        pts.update(cur)
+    return groups, group_pts, sorted(pts)
+
+
+def to_riesz(dual_set, poly_set, device=None):
+    """Device version of `DualSet.to_riesz(poly_set)` (FIAT/dual_set.py:86-206): the action of every functional of
+    the dual set on every member of the expansion set underlying `poly_set`, tensor
+    (num_nodes, *target_shape, num_members).  The two tabulations of the expansion set (values at all evaluation /
+    quadrature points, derivatives at the points of the derivative functionals) run through the device tabulator;
+    the weight matrices are assembled on the host exactly like the reference's and contracted on the device."""
+    nodes = dual_set.nodes
+    tshape = tuple(nodes[0].target_shape)
+    es = poly_set.get_expansion_set()
+    ed = poly_set.get_embedded_degree()
+    num_exp = int(es.get_num_members(ed))
+    dev = ExpansionTabulator(es, ed, device)
+    mat = torch.zeros((len(nodes),) + tshape + (num_exp,), dtype=torch.float64, device=dev.device)
+
+    def accumulate(ells, wts, values):
+        # mat[ells] += wts . values   (wts: (len(ells), *tshape, npts), values: (npts, num_exp))
+        w = torch.as_tensor(wts, device=dev.device)
+        idx = torch.as_tensor(ells, device=dev.device, dtype=torch.long)
+        mat.index_add_(0, idx, (w.reshape(-1, w.shape[-1]) @ values).reshape(w.shape[:-1] + (num_exp,)))
+
+    groups, group_pts, pts = _quadratures_to_points(nodes, deriv=False)
+    if pts:
+        values = dev.tabulate(numpy.asarray(pts, dtype=float)).T.contiguous()              # (npts, num_exp)
+        where = {pt: j for j, pt in enumerate(pts)}
+        for Q, ells in groups.items():
+            cur = group_pts[Q]
+            wts = numpy.zeros((len(ells),) + tshape + (len(cur),))
+            if Q is None:
+                col = {pt: j for j, pt in enumerate(cur)}
+                for i, k in enumerate(ells):
+                    for pt, wc_list in nodes[k].pt_dict.items():
+                        for w, c in wc_list:
+                            wts[i][c][col[pt]] = w
+            else:
+                for i, k in enumerate(ells):
+                    wts[i][nodes[k].comp][:] = nodes[k].f_at_qpts
+                wts *= Q.get_weights()
+            rows = torch.as_tensor([where[pt] for pt in cur], device=dev.device, dtype=torch.long)
+            accumulate(ells, wts, values[rows])
+
+    max_deriv_order = max(ell.max_deriv_order for ell in nodes)
+    if max_deriv_order > 0:
+        groups, group_pts, pts = _quadratures_to_points(nodes, deriv=True)
+        if pts:
+            dvals = dev.tab.tabulate(max_deriv_order, numpy.asarray(pts, dtype=float))      # alpha -> (num_exp, npts)
+            where = {pt: j for j, pt in enumerate(pts)}
+            for Q, ells in groups.items():
+                cur = group_pts[Q]
+                dwts = {alpha: numpy.zeros((len(ells),) + tshape + (len(cur),)) for alpha in dvals if sum(alpha) > 0}
+                if Q is None:
+                    col = {pt: j for j, pt in enumerate(cur)}
+                    for i, k in enumerate(ells):
+                        for pt, wac_list in nodes[k].deriv_dict.items():
+                            for w, alpha, c in wac_list:
+                                dwts[tuple(alpha)][i][c][col[pt]] = w
+                else:
+                    for i, k in enumerate(ells):
+                        for alpha in nodes[k].weights:
+                            dwts[tuple(alpha)][i][nodes[k].comp][:] = nodes[k].weights[alpha]
+                rows = torch.as_tensor([where[pt] for pt in cur], device=dev.device, dtype=torch.long)
+                for alpha, wts in dwts.items():
+                    if wts.any():
+                        accumulate(ells, wts, dvals[alpha].T[rows])
+    return mat

@@ -98,6 +98,16 @@ typedef struct {
      * at least one, possibly zero, block), and all subcells share rb_order, row_perm and the member slots; 0: single
      * matrix as described above. */
     int32_t blk_cells;
+    /* Fixed-k block stream for the register-operand split-cell kernel (optional; cstream_len == 0: absent).
+     * k-block j = member slots 4 j .. 4 j + 3.  The packed row blocks are cut into steps of crb row blocks; step s is
+     * the run of doubles cstream[cstep_ptr[s] .. cstep_ptr[s + 1]):  ncells * crb int32 records
+     * (mask | first block << 16, subcell-major; bit j of mask: k-block j of that (subcell, row block) is stored),
+     * padded to a multiple of 16 bytes, then the step's blocks (subcell, row block, k-block ascending), 32 doubles
+     * each in mma.m8n8k4 A-fragment order (fiat_b200/plan.py: pack_fixed_stream). */
+    const double* cstream;
+    int64_t cstream_len;
+    const int32_t* cstep_ptr;  /* cnsteps + 1 offsets in doubles (even) */
+    int32_t cnsteps, crb;
 } fiatb200_simplex_program;
 
 /* Entity transform x_cell = x_entity * C + offset (FIAT/reference_element.py:570-609);

@@ -195,3 +195,19 @@ def test_expansion_set_normal_jumps_match_the_reference(cuda_device):
             got = dev.tabulate_normal_jumps(ref_pts, facet, order=2).cpu().numpy()
             assert got.shape == want.shape, (label, facet)
             assert abs(got - want).max() <= 1e-11 * max(abs(want).max(), 1.0), (label, facet)
+
+
+def test_to_riesz_matches_the_reference(cuda_device):
+    """DualSet.to_riesz (FIAT/dual_set.py:86-206): point evaluations, derivatives (Hermite, Argyris, Morley, Bell),
+    integral moments against quadrature rules (RT, Nedelec, BDM, Regge, MTW), macro elements (HCT, Guzman-Neilan):
+    the expansion-set tabulations run on the device, the result equals the reference's matrix."""
+    _reference()
+    import FIAT
+    from fiat_b200.setup_path import to_riesz
+    from test_setup_path_host import riesz_elements
+    for element in riesz_elements(FIAT):
+        poly_set, dual = element.get_nodal_basis(), element.dual
+        want = dual.to_riesz(poly_set)
+        got = to_riesz(dual, poly_set, device=cuda_device)
+        assert got.is_cuda and tuple(got.shape) == want.shape
+        assert abs(got.cpu().numpy() - want).max() <= 1e-12 * abs(want).max(), type(element).__name__

@@ -509,6 +509,34 @@ def test_host_buffer_out_is_validated(cuda_device):
             tab.tabulate_host(1, pts, out=bad)
 
 
+@pytest.mark.parametrize("name", ["walkington_tet_o2", "gn_tet_o2", "hct5_tri_o2", "hct6_tri_o2", "alfeld_sorokina_tet_adv_o2"])
+def test_split_cell_tile_kernel_many_tiles(name, cuda_device):
+    """The split-cell tile kernels (cells_reg.cuh: expansion values in registers, coefficient steps streamed through
+    shared memory) over many tiles and a ragged last tile, against the thread-per-point jet kernel on the same points;
+    the set includes points on interior facets / vertices of the split (several subcells) and NaN points (none)."""
+    from fiat_b200 import api
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    sd = int(desc["sd"])
+    tab = api.Tabulator(desc, cuda_device)
+    assert "mma_cells" in tab.kernel_names(order, None)
+    assert tab._self_check_flags(desc, order) == 0
+    rng = numpy.random.default_rng(7)
+    lam = rng.dirichlet(numpy.ones(sd + 1), size=5003)
+    verts = numpy.asarray(desc["vertices"], dtype=float)[:sd + 1]
+    pts = lam @ verts
+    pts[100] = verts.mean(axis=0)                      # the split point of Alfeld-type complexes: every subcell
+    pts[101] = 0.5 * (verts[0] + verts.mean(axis=0))   # on an interior edge
+    pts[4000] = numpy.nan
+    pts[5002] = verts[1]
+    got = tab.tabulate(order, pts)
+    want = tab.tabulate(order, pts, flags=api.FORCE_THREAD_PER_POINT)
+    for alpha in got:
+        g, w = got[alpha].cpu().numpy(), want[alpha].cpu().numpy()
+        assert not numpy.isnan(g).any() and not g[..., 4000].any()
+        assert abs(g - w).max() <= 2e-13 * max(abs(w).max(), 1e-300), alpha
+
+
 @pytest.mark.parametrize("name", ["hct_o2", "n2curl4_tet_o1", "gn_tet_o2", "p4_spectral_tri_o2", "p8_spectral_tet_o2"])
 def test_derived_paths_are_self_checked_on_the_device(name, cuda_device, monkeypatch):
     """Paths that replace the derivative jets by host-folded derivative matrices (value table, stacked derived element,
