@@ -419,7 +419,17 @@ def latency_legs(device):
             tab.tabulate(order, dpts)
         torch.cuda.synchronize(device)
         out[f"device_points_{n}"] = (time.perf_counter() - t0) / reps * 1e6
-    out["unit"] = "us per call (first_call_ms in ms)"
+    # first call on the headline element (P8 tet, order 2): 1000 points take the quick plan (thread-per-point kernels,
+    # no plan-time optimisation, api.QUICK_NPTS), 2^16 points build the streaming plans (lattice check, packing, ...)
+    dname, order, kind, _ = WORKLOADS["p8_tet_o2"]
+    desc = load_desc(dname)
+    for label, n in (("first_call_ms_p8_tet_o2_1000_points", 1000), ("first_call_ms_p8_tet_o2_65536_points", 1 << 16)):
+        pts = host_points(kind, n, 7)
+        t0 = time.perf_counter()
+        Tabulator(desc, device).tabulate(order, pts)
+        torch.cuda.synchronize(device)
+        out[label] = (time.perf_counter() - t0) * 1e3
+    out["unit"] = "us per call (first_call_ms* in ms)"
     return out
 
 

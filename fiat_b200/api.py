@@ -16,6 +16,7 @@ are cached per element and order.  There is no CPU fallback: unsupported element
 `NotImplementedError`, a missing CUDA library or device raises.
 """
 import collections
+import os
 import ctypes
 import functools
 import threading
@@ -103,6 +104,29 @@ class _Plan:
             pass
 
 
+def _quick_description(desc):
+    """The same element with every simplex description marked `dense_only`: plan.compile_simplex then builds only the
+    recurrence tables and dense per-cell matrices (about a millisecond), none of the row clustering, block packing,
+    value tables or derived elements (up to seconds) that pay off on large point sets."""
+    kind = desc["kind"]
+    if kind == "simplex":
+        return dict(desc, dense_only=True)
+    if kind == "tensor":
+        return dict(desc, A=_quick_description(desc["A"]), B=_quick_description(desc["B"]))
+    if kind == "flattened":
+        return dict(desc, element=_quick_description(desc["element"]))
+    if kind == "composite":
+        return dict(desc, parts=[dict(part, element=_quick_description(part["element"])) for part in desc["parts"]])
+    return desc
+
+
+# Calls with at most this many points go to the quick plan (thread-per-point kernels, no plan-time optimisation) as long
+# as no larger call has built the optimised plan for that (order, entity): the typical use of the reference --
+# an element tabulated once at a quadrature rule -- then costs milliseconds instead of the seconds of plan time the
+# streaming kernels need.  FIATB200_QUICK_NPTS=0 switches it off (the GPU tests do: they are about those kernels).
+QUICK_NPTS = int(os.environ.get("FIATB200_QUICK_NPTS", "4096"))
+
+
 class Tabulator:
     """Device tabulation of one element (description) on one CUDA device."""
 
@@ -115,6 +139,18 @@ class Tabulator:
         self.kind = desc["kind"]
         self._plans = {}
         self._lock = threading.Lock()
+        self._quick = None
+
+    def _quick_for(self, order, entity, npts, flags):
+        """The quick-plan tabulator for a small call, or None (see QUICK_NPTS)."""
+        if flags or npts > QUICK_NPTS or self.kind in ("trace", "quadrature") or self.desc.get("dense_only"):
+            return None
+        if ("resolved", order, None if entity is None else str(entity), 0) in self._plans:
+            return None                         # the optimised plan exists already
+        with self._lock:
+            if self._quick is None:
+                self._quick = Tabulator(_quick_description(self.desc), self.device)
+        return self._quick
 
     # -- shapes -------------------------------------------------------------------------------
     def cell_dimension(self):
@@ -528,6 +564,9 @@ class Tabulator:
             return self._tabulate_quadrature(order, points, entity)
         if self.kind == "trace":
             return self._tabulate_trace(order, points, entity)
+        quick = self._quick_for(order, entity, len(points) if hasattr(points, "__len__") else QUICK_NPTS + 1, flags)
+        if quick is not None:
+            return quick.tabulate(order, points, entity, FORCE_THREAD_PER_POINT)
         launches, nrows, pdim, prefix, zero = self._resolve(order, entity, flags)
         pts = self._points(points, pdim)
         npts = pts.shape[0]
@@ -578,6 +617,9 @@ class Tabulator:
 
     def tabulate_host(self, order, points, entity=None, chunk_pts=1 << 16, flags=0, out=None):
         """End-to-end with host (numpy) buffers: returns a dict of numpy arrays, like the reference."""
+        quick = self._quick_for(order, entity, len(points) if hasattr(points, "__len__") else QUICK_NPTS + 1, flags)
+        if quick is not None:
+            return quick.tabulate_host(order, points, entity, chunk_pts, FORCE_THREAD_PER_POINT, out)
         launches, nrows, pdim, prefix, zero = self._resolve(order, entity, flags)
         pts = numpy.ascontiguousarray(numpy.asarray(points, dtype=numpy.float64)).reshape(-1, pdim)
         npts = pts.shape[0]

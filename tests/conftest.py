@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The GPU tests are about the streaming kernels: small calls must not be diverted to the quick plan (api.QUICK_NPTS).
+# tests/test_gpu_parity.py::test_quick_plan_for_small_calls and the reference's unit tests over the drop-in
+# (tests/test_reference_suite.py, run in a subprocess with the default) cover the quick plan itself.
+os.environ.setdefault("FIATB200_QUICK_NPTS", "0")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

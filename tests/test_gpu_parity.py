@@ -206,6 +206,30 @@ def test_single_point_without_point_axis(name, entity, cuda_device):
     _compare(case["desc"], tab.tabulate(1, p, entity), want)
 
 
+@pytest.mark.parametrize("name", ["p8_tet_o2", "n2curl4_tet_o1", "hct_o2", "gn_tet_o2", "gll_q3_hex_face4_o2", "rtcf1_quad_o1",
+                                  "nested_tpe_o1", "p2_tri_facet1_o1"])
+def test_quick_plan_for_small_calls(name, cuda_device, monkeypatch):
+    """Small calls (<= api.QUICK_NPTS points) before any large one run on a quick plan -- thread-per-point kernels on a
+    description marked dense_only, no clustering / packing / derived elements / self-checks -- and match the
+    reference; a large call then builds the streaming plan, which small calls use from then on."""
+    from fiat_b200 import api
+    monkeypatch.setattr(api, "QUICK_NPTS", 4096)
+    case = load_case(name)
+    tab = api.Tabulator(case["desc"], cuda_device)
+    got = tab.tabulate(case["order"], case["points"], case["entity"])
+    assert tab._quick is not None and not any(k[0] == "resolved" for k in tab._plans)
+    _compare(case["desc"], got, case["ref"])
+    _compare(case["desc"], tab.tabulate_host(case["order"], case["points"], case["entity"]), case["ref"])
+    pts = numpy.asarray(case["points"], dtype=float)
+    big = numpy.tile(pts, (-(-5000 // max(len(pts), 1)), 1))
+    wide = tab.tabulate(case["order"], big, case["entity"])
+    assert any(k[0] == "resolved" for k in tab._plans)
+    again = tab.tabulate(case["order"], case["points"], case["entity"])
+    for alpha in got:
+        assert torch.equal(again[alpha], wide[alpha][..., :len(pts)])
+    _compare(case["desc"], again, case["ref"])
+
+
 def test_empty_point_set(cuda_device):
     from fiat_b200.api import Tabulator
     case = load_case("p3_tri_o1")

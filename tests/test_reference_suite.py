@@ -39,6 +39,7 @@ def _run(mode, tmp_path, workers):
     stats_file = tmp_path / "dropin_stats.jsonl"
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([REF, ROOT]), FIATB200_DROPIN=mode,
                FIATB200_DROPIN_STATS=str(stats_file))
+    env.pop("FIATB200_QUICK_NPTS", None)         # the library's default: small calls take the quick plan
     cmd = [sys.executable, "-m", "pytest", "-p", "oracle.dropin_plugin", "-q", "-p", "no:cacheprovider",
            "-c", os.devnull, "--rootdir", str(tmp_path), "-k", NEEDS_GEM, "-n", str(workers)] + targets
     res = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=3000)
