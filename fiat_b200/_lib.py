@@ -65,6 +65,11 @@ class LibraryError(RuntimeError):
     pass
 
 
+class UnsupportedByLibrary(LibraryError, NotImplementedError):
+    """FIATB200_ERR_UNSUPPORTED: a size or element the device path does not take (expansion degree above the device
+    tables, more than 32 subcells, ...); callers that have the reference at hand may fall back on it."""
+
+
 _lib = None
 
 EXPORTS = [
@@ -119,7 +124,8 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().fiatb200_last_error()
-        raise LibraryError(f"fiat_b200 error {rc}: {msg.decode() if msg else '?'}")
+        text = f"fiat_b200 error {rc}: {msg.decode() if msg else '?'}"
+        raise UnsupportedByLibrary(text) if rc == 3 else LibraryError(text)
 
 
 def _ptr(arr, ctype):

@@ -617,6 +617,10 @@ class Tabulator:
 
     def tabulate_host(self, order, points, entity=None, chunk_pts=1 << 16, flags=0, out=None):
         """End-to-end with host (numpy) buffers: returns a dict of numpy arrays, like the reference."""
+        if self.kind in ("trace", "quadrature"):
+            # not polynomial tabulations: facet by facet / the identity (slots that are not defined hold TraceError)
+            res = self.tabulate(order, points, entity)
+            return {a: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for a, v in res.items()}
         quick = self._quick_for(order, entity, len(points) if hasattr(points, "__len__") else QUICK_NPTS + 1, flags)
         if quick is not None:
             return quick.tabulate_host(order, points, entity, chunk_pts, FORCE_THREAD_PER_POINT, out)

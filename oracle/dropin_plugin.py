@@ -43,8 +43,11 @@ def _wrap(original):
                 raise NotImplementedError("symbolic points")
             if MODE == "device":
                 import fiat_b200
+                from FIAT.hdiv_trace import TraceError as ReferenceTraceError
                 out = fiat_b200.tabulate_host(self, order, points, entity)
-                out = {k: (v if isinstance(v, Exception) else numpy.array(v)) for k, v in out.items()}
+                # (the binding layer hands the reference's own exception type to the reference's callers)
+                out = {k: (ReferenceTraceError(getattr(v, "msg", str(v))) if isinstance(v, Exception) else numpy.array(v))
+                       for k, v in out.items()}
             else:
                 from fiat_b200.extract import describe_element
                 from oracle import fiat_oracle

@@ -40,6 +40,16 @@ def test_matches_reference_golden(name, cuda_device):
         assert isinstance(v, Exception) or (v.is_cuda and v.dtype == torch.float64)
 
 
+@pytest.mark.parametrize("name", [n for n in golden_case_names() if "hdivtrace" in n or "quadrature" in n])
+def test_trace_and_quadrature_elements_with_host_buffers(name, cuda_device):
+    """HDivTrace / QuadratureElement through the numpy-in / numpy-out call (what the reference-side binding uses)."""
+    from fiat_b200.api import Tabulator
+    case = load_case(name)
+    got = Tabulator(case["desc"], cuda_device).tabulate_host(case["order"], case["points"], case["entity"])
+    _compare(case["desc"], got, case["ref"], case["error_keys"])
+    assert all(isinstance(v, (Exception, numpy.ndarray)) for v in got.values())
+
+
 @pytest.mark.parametrize("name", golden_case_names())
 def test_both_kernels_agree_with_oracle(name, cuda_device):
     """Single-cell Dubiner elements run on the thread-per-point kernel and on the DMMA tile kernel."""
