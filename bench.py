@@ -287,13 +287,12 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
-def csrc_stamp():
-    """Hash of the kernel sources: profiles/traffic.json entries are only quoted while it matches."""
+def csrc_stamp(sources):
+    """Hash of the kernel's own source files (under fiat_b200/csrc): a profiles/traffic.json entry is only quoted
+    while the files its kernel is compiled from are the ones the ncu capture was taken at."""
     h = hashlib.sha256()
-    src = os.path.join(ROOT, "fiat_b200", "csrc")
-    for name in sorted(os.listdir(src)):
-        if name.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(src, name), "rb").read())
+    for name in sorted(sources):
+        h.update(open(os.path.join(ROOT, "fiat_b200", "csrc", name), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -301,7 +300,7 @@ def measured_traffic(key):
     try:
         table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         hit = table.get(key)
-        if hit and table.get("_csrc_stamp") == csrc_stamp():
+        if hit and hit.get("stamp") == csrc_stamp(hit["kernel_sources"]):
             return hit.get("bytes")
     except Exception:
         pass
@@ -607,7 +606,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_point": bytes_per_point, "algorithmic_bytes_per_launch": bytes_per_point * tile,
                          "kernel_ms": ms / max(launches, 1), "launches_per_step": per_step, "kernel": kernel,
-                         "traffic_source": "profiles/traffic.json (ncu --set full), quoted only while the csrc hash matches",
+                         "traffic_source": "profiles/traffic.json (ncu --set full), quoted only while the hash of the kernel's source files matches",
                          "fp64_peak_tflops_measured": FP64_PEAK_TFLOPS},
             "clocks": clocks,
         }
