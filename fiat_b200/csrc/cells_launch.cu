@@ -38,11 +38,22 @@ bool cells_geometry(const fiatb200_plan* plan, CellsGeom* G, size_t* smem_out) {
 // register-operand kernel (cells_reg.cuh): 16 warps x 2 octets of columns, fixed-k block stream
 bool cells_reg_geometry(const fiatb200_plan* plan, CellsRegGeom* G, size_t* smem_out) {
     const DevSimplex& P = plan->simplex;
-    if (fb_tuning().cells_reg == 0) return false;                  // FIATB200_CELLS_REG=0: segment kernel (experiments)
+    // Measured against the segment kernel (2^20 points, ms): Guzman-Neilan (20 members per subcell) 2.05 / 2.24,
+    // Alfeld-Sorokina (10) 2.33 / 3.11 -- but HCT degree 5 (21) 0.70 / 0.66, degree 6 (28) 1.02 / 0.88, Walkington
+    // (56) 2.89 / 2.71: with many members the segments of cells.cuh are long enough.  FIATB200_CELLS_REG=0 / 1 force
+    // the segment / this kernel (experiments).
+    if (fb_tuning().cells_reg == 0) return false;
+    if (fb_tuning().cells_reg != 1 && P.kpad > 20) return false;
     if (P.cnsteps <= 0 || P.crb <= 0 || P.kpad > 64 || P.ncells < 2 || P.ncells > 24 || P.sd < 2) return false;
     if (P.expansion != 0 || P.order != 0 || plan->tab.nrb == 0 || plan->tab.nrb > P.cnsteps * P.crb) return false;
-    const int threads = 512, pts_cap = (threads / 32) * 16;
+    // one CTA of 16 warps per SM; two CTAs of 8 warps (FIATB200_CELLS_THREADS=256: one CTA's binning, recurrence
+    // and barriers would overlap the other's steps) measured 6-18 % slower on every element
+    int threads = 512;
+    if (fb_tuning().cells_threads == 256 || fb_tuning().cells_threads == 512) threads = fb_tuning().cells_threads;
+    if (threads == 256 && 128 - 8 * P.ncells < 64) threads = 512;    // many subcells: the padding would eat the tile
+    const int pts_cap = (threads / 32) * 16;
     const int pt = pts_cap - 8 * P.ncells;                        // subcell ranges are padded to octets
+    if (pt < 32) return false;
     int ld = pts_cap;
     while ((ld & 15) != 8) ++ld;
     const int maxlev = std::max(1, plan->tab.nsteps);

@@ -9,7 +9,7 @@
 //   * a warp owns two octets of COLUMNS for the whole tile and reads their B fragments -- the member values of its 16
 //     points, k-block j = member slots 4j..4j+3 -- from the expansion table into registers ONCE (KB x 2 doubles);
 //   * all warps walk the row blocks in lockstep, RB at a time ("step"); a step's coefficient blocks of all subcells
-//     (fixed-k packing, plan.py: pack_fixed_stream) are one contiguous run of global memory that the CTA copies into
+//     (prefix packing of fixed k-blocks, plan.py: pack_fixed_stream) are one contiguous run of global memory that the CTA copies into
 //     shared memory with cp.async one step ahead; per block a warp issues one conflict-free LDS.64 and one DMMA
 //     per octet (both octets in the same subcell, the usual case for sorted columns, share the LDS);
 //   * the 8 x 8 results go through the column permutation into a CTA-wide staging buffer (double-buffered) and the
@@ -38,6 +38,65 @@ __device__ __forceinline__ void fb_cp_async16(void* dst_shared, const void* src_
 }
 __device__ __forceinline__ void fb_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void fb_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// The n stored k-blocks (a prefix 0 .. n - 1, plan.py: pack_fixed_stream) of one (subcell, row block) against the
+// warp's B fragments: ONE jump on n into an unrolled fall-through run of blocks, each a shared-memory load with an
+// immediate offset and one DMMA per octet -- the B fragment must be a compile-time register, and a per-block test
+// costs more than the block.  (Two earlier forms of this loop, measured on Walkington's element against the segment
+// kernel's 2.7 ms: an unrolled `if (mask & (1 << kb))` chain is if-converted into KB *predicated* DMMAs per row
+// block, and a predicated-off DMMA still takes its slot in the tensor pipe -- 148 M issued for 65 M wanted, 3.9 ms;
+// a loop over the set bits with a switch on the k-block number costs 28 instructions per block -- 5.4 ms.)
+#define FB_CELLS_REG_BLOCK(K)                                                    \
+    if (K < KB) {                                                                \
+        const double a = f[(K < KB ? K : 0) * 32];                               \
+        dmma_8x8x4(a00, a01, a, B0[K < KB ? K : 0]);                             \
+        if (JOINT) dmma_8x8x4(a10, a11, a, B1[K < KB ? K : 0]);                  \
+    }
+
+template <int KB, bool JOINT>
+__device__ __forceinline__ void cells_reg_blocks(int n, const double* __restrict__ f, const double (&B0)[KB],
+                                                 const double (&B1)[KB], double& a00, double& a01, double& a10,
+                                                 double& a11) {
+    // binary search for the entry point (a `switch` became a linear chain of 14 compare-and-branch groups);
+    // entering at E<n> runs blocks n - 1, ..., 0
+    if (n >= 9) {
+        if (n >= 13) {
+            if (n >= 15) { if (n >= 16) goto E16; goto E15; }
+            if (n >= 14) goto E14;
+            goto E13;
+        }
+        if (n >= 11) { if (n >= 12) goto E12; goto E11; }
+        if (n >= 10) goto E10;
+        goto E9;
+    }
+    if (n >= 5) {
+        if (n >= 7) { if (n >= 8) goto E8; goto E7; }
+        if (n >= 6) goto E6;
+        goto E5;
+    }
+    if (n >= 3) { if (n >= 4) goto E4; goto E3; }
+    if (n >= 2) goto E2;
+    if (n >= 1) goto E1;
+    goto E0;
+E16: FB_CELLS_REG_BLOCK(15)
+E15: FB_CELLS_REG_BLOCK(14)
+E14: FB_CELLS_REG_BLOCK(13)
+E13: FB_CELLS_REG_BLOCK(12)
+E12: FB_CELLS_REG_BLOCK(11)
+E11: FB_CELLS_REG_BLOCK(10)
+E10: FB_CELLS_REG_BLOCK(9)
+E9: FB_CELLS_REG_BLOCK(8)
+E8: FB_CELLS_REG_BLOCK(7)
+E7: FB_CELLS_REG_BLOCK(6)
+E6: FB_CELLS_REG_BLOCK(5)
+E5: FB_CELLS_REG_BLOCK(4)
+E4: FB_CELLS_REG_BLOCK(3)
+E3: FB_CELLS_REG_BLOCK(2)
+E2: FB_CELLS_REG_BLOCK(1)
+E1: FB_CELLS_REG_BLOCK(0)
+E0:;
+}
+#undef FB_CELLS_REG_BLOCK
 
 template <int SD, int KB>
 __global__ void __launch_bounds__(512, 1)
@@ -157,40 +216,52 @@ k_cells_reg(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
     __syncthreads();                                         // T is dead: its memory becomes the staging buffers
 
     // ---- phase 2: steps of RB row blocks ----------------------------------------------------------------
+    // One loop body, every piece of it written once (no lambdas: their captured pointers lose the shared address
+    // space and every access then pays a generic-to-shared conversion): iteration s waits for the coefficients of
+    // step s, issues the copy of step s + 1, stores the rows of step s - 1 and computes step s.
     const int nsteps = P.cnsteps;
     const int hdr = ((P.ncells * RB + 3) >> 2) * 2;          // doubles of the step's int32 records
     const bool vec_ok = ((ostride & 1) == 0) && ((((size_t)out) & 15) == 0) && ((base & 1) == 0) && base + PT <= npts;
-    auto stage_step = [&](int s) {
-        const int b0 = __ldg(P.cstep_ptr + s), b1 = __ldg(P.cstep_ptr + s + 1);
-        const double* src = P.cstream + b0;
-        double* dst = Abuf + (size_t)(s & 1) * G.astage;
-        for (int i = tid * 2; i < b1 - b0; i += NT * 2) fb_cp_async16(dst + i, src + i);
-        fb_cp_async_commit();
-    };
-    auto store_rows = [&](int s) {
-        const double* Ob = O + (size_t)(s & 1) * R8 * SP;
-        for (int r = warp; r < R8; r += nwarp) {
-            const int rbi = s * RB + (r >> 3);
-            const int row = rbi < tab.nrb ? (int)tab.row_perm[rbi * 8 + (r & 7)] : -1;
-            if (row < 0) continue;
-            double* rowp = out + (size_t)row * ostride + base;
-            const double* src = Ob + (size_t)r * SP;
-            if (vec_ok) {
-                for (int i = lane * 2; i < PT; i += 64)
-                    *reinterpret_cast<double2*>(rowp + i) = *reinterpret_cast<const double2*>(src + i);
-            } else {
-                for (int i = lane; i < PT; i += 32)
-                    if (base + i < npts) rowp[i] = src[i];
+    const unsigned a_shared = (unsigned)__cvta_generic_to_shared(Abuf);
+    const size_t stage_bytes = (size_t)G.astage * sizeof(double);
+    for (int s = -1; s <= nsteps; ++s) {
+        if (s >= 0 && s < nsteps) fb_cp_async_wait_all();
+        __syncthreads();          // step s staged; every warp is done with step s - 1 and with the stores of step s - 2
+        if (s + 1 < nsteps) {
+            const int b0 = __ldg(P.cstep_ptr + s + 1), b1 = __ldg(P.cstep_ptr + s + 2);
+            const char* src = reinterpret_cast<const char*>(P.cstream + b0) + tid * 16;
+            unsigned dst = a_shared + (unsigned)(((s + 1) & 1) * stage_bytes) + tid * 16;
+            for (int i = tid * 2; i < b1 - b0; i += NT * 2, src += NT * 16, dst += NT * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+            fb_cp_async_commit();
+        }
+        if (s >= 1) {             // rows of step s - 1: full-width coalesced row stores
+            const double* Ob = O + (size_t)((s - 1) & 1) * R8 * SP;
+            for (int r = warp; r < R8; r += nwarp) {
+                const int rbi = (s - 1) * RB + (r >> 3);
+                const int row = rbi < tab.nrb ? (int)tab.row_perm[rbi * 8 + (r & 7)] : -1;
+                if (row < 0) continue;
+                double* rowp = out + (size_t)row * ostride + base;
+                const double* src = Ob + (size_t)r * SP;
+                if (vec_ok) {
+                    // <= 128 double2 per row (PTS <= 256): all loads first, then all stores
+                    const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
+                    double2* d2 = reinterpret_cast<double2*>(rowp) + lane;
+                    const int n2 = PT >> 1;
+                    double2 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (lane + 32 * k < n2) v[k] = s2[32 * k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (lane + 32 * k < n2) d2[32 * k] = v[k];
+                } else {
+                    for (int i = lane; i < PT; i += 32)
+                        if (base + i < npts) rowp[i] = src[i];
+                }
             }
         }
-    };
-    if (nsteps > 0) stage_step(0);
-    for (int s = 0; s < nsteps; ++s) {
-        fb_cp_async_wait_all();
-        __syncthreads();          // step s staged; every warp is done with step s - 1 and with the stores of step s - 2
-        if (s + 1 < nsteps) stage_step(s + 1);
-        if (s > 0) store_rows(s - 1);
-        if (c0 < 0) continue;
+        if (s < 0 || s >= nsteps || c0 < 0) continue;
         const double* Ab = Abuf + (size_t)(s & 1) * G.astage;
         const int* meta = reinterpret_cast<const int*>(Ab);
         const double* frag = Ab + hdr + lane;
@@ -201,35 +272,12 @@ k_cells_reg(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
             const int m0 = meta[c0 * RB + r];
             const double* f = frag + (size_t)(m0 >> 16) * 32;
             if (c1 == c0) {
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    if (m0 & (1 << kb)) {
-                        const double a = *f;
-                        f += 32;
-                        dmma_8x8x4(a00, a01, a, B0[kb]);
-                        dmma_8x8x4(a10, a11, a, B1[kb]);
-                    }
-                }
+                cells_reg_blocks<KB, true>(m0 & 0xffff, f, B0, B1, a00, a01, a10, a11);
             } else {
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    if (m0 & (1 << kb)) {
-                        const double a = *f;
-                        f += 32;
-                        dmma_8x8x4(a00, a01, a, B0[kb]);
-                    }
-                }
+                cells_reg_blocks<KB, false>(m0 & 0xffff, f, B0, B0, a00, a01, a10, a11);
                 if (c1 >= 0) {
                     const int m1 = meta[c1 * RB + r];
-                    f = frag + (size_t)(m1 >> 16) * 32;
-#pragma unroll
-                    for (int kb = 0; kb < KB; ++kb) {
-                        if (m1 & (1 << kb)) {
-                            const double a = *f;
-                            f += 32;
-                            dmma_8x8x4(a10, a11, a, B1[kb]);
-                        }
-                    }
+                    cells_reg_blocks<KB, false>(m1 & 0xffff, frag + (size_t)(m1 >> 16) * 32, B1, B1, a10, a11, a00, a01);
                 }
             }
             double* orow = Ob + (size_t)r * 8 * SP;
@@ -240,7 +288,6 @@ k_cells_reg(const DevSimplex P, const __grid_constant__ RecTab tab, const __grid
         }
     }
     __syncthreads();
-    if (nsteps > 0) store_rows(nsteps - 1);
 
     // ---- phase 3: points shared by several subcells, or in none -----------------------------------------
     if (!__syncthreads_or(valid && mult != 1)) return;

@@ -25,6 +25,7 @@ const FbTuning& fb_tuning() {
         v.vals_j = geti("FIATB200_VALS_J");
         v.mma_wl = geti("FIATB200_MMA_WARPLOCAL");
         v.cells_reg = geti("FIATB200_CELLS_REG");
+        v.cells_threads = geti("FIATB200_CELLS_THREADS");
         return v;
     }();
     return t;

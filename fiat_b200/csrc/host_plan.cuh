@@ -28,7 +28,7 @@ extern std::atomic<long long> fb_launches;
 // Tuning overrides for experiments, read from the environment ONCE, the first time a launch
 // asks for them; -1 = not set.  Nothing on the per-launch path calls getenv.
 struct FbTuning {
-    int mma_pt, mma_skip, mma_threads, tensor_bp, eval_bp, eval_generic, vals_tpc, vals_j, mma_wl, cells_reg;
+    int mma_pt, mma_skip, mma_threads, tensor_bp, eval_bp, eval_generic, vals_tpc, vals_j, mma_wl, cells_reg, cells_threads;
 };
 const FbTuning& fb_tuning();
 

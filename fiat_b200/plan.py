@@ -483,11 +483,12 @@ def schedule_row_blocks(counts):
     return numpy.array(out, dtype=numpy.int32)
 
 
-def group_members(C, nseg=1, iters=6000, seed=1):
-    """Slot permutation (perm[new slot] = old slot) for FIXED k-blocks: members 4j..4j+3 of the new numbering form
-    k-block j, and a (row block, subcell) pair costs one 8x4 block per k-block any of its rows touches.  Swap local
-    search from the given order (which is by degree, so the low-degree members every derivative row uses already sit
-    together): Walkington tet order 2 2150 -> 1865 blocks (gather packing: 1651), Guzman-Neilan 711 -> 640 (523)."""
+def prefix_members(C, nseg=1, iters=4000, seed=1):
+    """Slot permutation (perm[new slot] = old slot) for PREFIX packing: k-block j = new slots 4j..4j+3, and a
+    (row block, subcell) pair stores the k-blocks 0 .. n-1 up to the last one any of its rows touches.  Members are
+    ordered by how many (row block, subcell) pairs use them -- the low-degree members that every derivative row
+    uses come first -- then improved by swaps.  Walkington tet order 2: 2 350 blocks before the swaps (gather packing
+    1 651, dense 4 592); Guzman-Neilan 661 (523, 1 800)."""
     nrows, ncols = C.shape
     K = ncols // nseg
     if K <= 4:
@@ -497,30 +498,29 @@ def group_members(C, nseg=1, iters=6000, seed=1):
     Cp[:nrows] = C != 0.0
     U = Cp.reshape(nrb, 8, nseg, K).any(axis=1).reshape(nrb * nseg, K)
     U = U[U.any(axis=1)]
-    Kp = -(-K // 4) * 4
-    Ue = numpy.concatenate([U, numpy.zeros((U.shape[0], Kp - K + 1), dtype=bool)], axis=1)    # empty positions last
-    perm = numpy.arange(Kp)
+    perm = numpy.argsort(-U.sum(axis=0), kind="stable")
 
-    def group_cost(g):
-        return int(Ue[:, perm[4 * g:4 * g + 4]].any(axis=1).sum())
+    def cost(pm):
+        last = K - numpy.argmax(U[:, pm][:, ::-1], axis=1)          # prefix length in members (every row of U is used)
+        return int(numpy.ceil(last / 4.0).sum())
 
     rng = numpy.random.default_rng(seed)
-    cost = [group_cost(g) for g in range(Kp // 4)]
+    best = cost(perm)
     for _ in range(iters):
         i, j = (int(v) for v in rng.integers(0, K, 2))
-        gi, gj = i // 4, j // 4
-        if gi == gj:
+        if i // 4 == j // 4:
             continue
         perm[i], perm[j] = perm[j], perm[i]
-        ci, cj = group_cost(gi), group_cost(gj)
-        if ci + cj <= cost[gi] + cost[gj]:
-            cost[gi], cost[gj] = ci, cj
+        c = cost(perm)
+        if c <= best:
+            best = c
         else:
             perm[i], perm[j] = perm[j], perm[i]
-    return perm[:K].astype(numpy.int64)
+    return perm.astype(numpy.int64)
 
 
-CELLS_STEP_RB = 2           # row blocks per step of the register-operand split-cell kernel (16 rows = its 16 warps)
+CELLS_REG_MAX_MEMBERS = 20  # members per subcell up to which the register-operand split-cell kernel wins (cells_launch.cu)
+CELLS_STEP_RB = 4           # row blocks per step of the register-operand split-cell kernel (two rows per warp; 2 was 3-6 % slower)
 
 
 def pack_fixed_stream(C, nseg, rb_per_step=CELLS_STEP_RB):
@@ -529,11 +529,13 @@ def pack_fixed_stream(C, nseg, rb_per_step=CELLS_STEP_RB):
     holds the matching B fragments of its columns in registers, so blocks cannot gather).  The stream is cut into
     steps of `rb_per_step` row blocks; one step is one contiguous run of doubles
 
-        [ nseg * rb_per_step int32 records: mask | first block << 16 ]  padded to a multiple of 16 bytes
-        [ the step's blocks, subcell-major then row block then k-block ascending, 32 doubles each in
+        [ nseg * rb_per_step int32 records: n | first block << 16 ]  padded to a multiple of 16 bytes
+        [ the step's blocks, subcell-major then row block then k-block 0 .. n - 1, 32 doubles each in
           mma.m8n8k4 A-fragment order: lane l holds C[8 rb + l // 4, 4 j + l % 4] ]
 
-    where bit j of `mask` says k-block j of that (subcell, row block) is stored.  -> (stream, step_ptr in doubles)."""
+    where n is the PREFIX of k-blocks that (subcell, row block) stores: everything up to the last k-block one of its
+    rows touches (plan.prefix_members orders the slots so that prefixes are short); the kernel then enters an
+    unrolled run of n blocks with ONE jump and no per-block test.  -> (stream, step_ptr in doubles)."""
     nrows, ncols = C.shape
     K = ncols // nseg
     KB = -(-K // 4)
@@ -552,12 +554,12 @@ def pack_fixed_stream(C, nseg, rb_per_step=CELLS_STEP_RB):
         frs, nb = [], 0
         for c in range(nseg):
             for r in range(rb_per_step):
-                mask = 0
-                for kb in numpy.flatnonzero(present[s, c, r]):
-                    mask |= 1 << int(kb)
+                used = numpy.flatnonzero(present[s, c, r])
+                n = int(used[-1]) + 1 if len(used) else 0
+                for kb in range(n):
                     frs.append(blocks[s, c, r, kb].reshape(32))
-                meta[c * rb_per_step + r] = mask | (nb << 16)
-                nb += int(present[s, c, r].sum())
+                meta[c * rb_per_step + r] = n | (nb << 16)
+                nb += n
         if nb >= 1 << 15:
             return numpy.zeros(0), numpy.zeros(1, numpy.int32)
         out.append(meta.view(numpy.float64))
@@ -842,9 +844,10 @@ def compile_simplex(desc, order):
             keep0 = significant_entries(desc, t, wide, _nstack(desc, nrows))
             wide = numpy.concatenate([numpy.where(k, f, 0.0) for k, f in zip(keep0, wide)], axis=1)
             packed_rows = cluster_rows(wide, 0.0, nseg=ncells)[0]
-            if tile_cells and nexp_total // ncells <= 64:
-                # split cells: the register-operand kernel multiplies FIXED k-blocks of four consecutive slots
-                slot_perm = group_members(wide[packed_rows], nseg=ncells)
+            if tile_cells and nexp_total // ncells <= CELLS_REG_MAX_MEMBERS:
+                # split cells with few members per subcell go to the register-operand kernel, which multiplies a
+                # PREFIX of fixed k-blocks (four consecutive slots)
+                slot_perm = prefix_members(wide[packed_rows], nseg=ncells)
             else:
                 colour, _ = colour_members(wide, packed_rows, 0.0, nseg=ncells)
                 slot_perm = slots_from_colours(colour)
@@ -923,8 +926,7 @@ def compile_simplex(desc, order):
         prog.row_perm = numpy.asarray(rows_order, dtype=numpy.int32)
         prog.blk_cells = ncells if ncells > 1 else 0
         if ncells > 1 and nslots <= 64:
-            # (few members per subcell: short steps, so four row blocks per block barrier instead of two)
-            rb_step = 2 * CELLS_STEP_RB if nslots <= 24 else CELLS_STEP_RB
+            rb_step = int(os.environ.get("FIATB200_CELLS_RB", CELLS_STEP_RB))         # (override: experiments)
             prog.cstream, prog.cstep_ptr = pack_fixed_stream(wide[rows_order], ncells, rb_step)
             prog.crb = rb_step if len(prog.cstream) else 0
     return prog

@@ -120,7 +120,7 @@ def blocks_to_dense(prog, cell=0):
 
 def stream_to_dense(prog, cell=0):
     """The same matrix rebuilt from the fixed-k block stream of the register-operand split-cell kernel
-    (plan.pack_fixed_stream): steps of crb row blocks, int32 records mask | first block << 16, k-block j = slots 4j..4j+3."""
+    (plan.pack_fixed_stream): steps of crb row blocks, int32 records n | first block << 16 (the k-blocks 0 .. n - 1 are stored), k-block j = slots 4j..4j+3."""
     ncells, RB = prog.ncells, prog.crb
     nstep = len(prog.cstep_ptr) - 1
     hdr = -(-(ncells * RB) // 4) * 2
@@ -132,12 +132,10 @@ def stream_to_dense(prog, cell=0):
         frags = step[hdr:].reshape(-1, 8, 4)
         for r in range(RB):
             m = int(meta[cell * RB + r])
-            q = m >> 16
-            assert (m & 0xFFFF) >> KB == 0
-            for kb in range(KB):
-                if m & (1 << kb):
-                    C[(s * RB + r) * 8:(s * RB + r) * 8 + 8, 4 * kb:4 * kb + 4] = frags[q]
-                    q += 1
+            q, n = m >> 16, m & 0xFFFF
+            assert n <= KB
+            for kb in range(n):
+                C[(s * RB + r) * 8:(s * RB + r) * 8 + 8, 4 * kb:4 * kb + 4] = frags[q + kb]
     out = numpy.zeros((prog.nrows, prog.nslots))
     out[prog.row_perm] = C[:prog.nrows, :prog.nslots]
     return out

@@ -120,7 +120,7 @@ def test_macro_merged_reproduces_reference(name):
         ptr = prog.blk_ptr[c * (nrb + 1):(c + 1) * (nrb + 1)]
         assert (numpy.diff(ptr) >= 1).all()
     # the fixed-k stream of the register-operand kernel holds the same matrices, step by step
-    assert prog.crb in (2, 4) and len(prog.cstream) == prog.cstep_ptr[-1] and (numpy.diff(prog.cstep_ptr) % 2 == 0).all()
+    assert prog.crb == planmod.CELLS_STEP_RB and len(prog.cstream) == prog.cstep_ptr[-1] and (numpy.diff(prog.cstep_ptr) % 2 == 0).all()
     assert (len(prog.cstep_ptr) - 1) * prog.crb >= nrb
     for c in range(prog.ncells):
         assert numpy.array_equal(emu.stream_to_dense(prog, c), emu.blocks_to_dense(prog, c))

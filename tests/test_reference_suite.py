@@ -8,8 +8,9 @@ unity, macro-element continuity, tensor-product dof order, trace elements -- the
     not gpu:  the CPU oracle (`FIATB200_DROPIN=oracle`) -- pins the oracle with the reference's own assertions
     gpu:      the CUDA path  (`FIATB200_DROPIN=device`, numpy in / numpy out through the C ABI)
 
-The default selection is the files that exercise tabulation most (about 680 tests); `FIATB200_REF_SUITE=full` runs all
-36 files.  Tests that need `gem` / `sympy`-through-gem (absent here: test_precision.py, test_macro.py::test_macro_gem /
+The default selection is the files that exercise tabulation most (about 690 tests; on the GPU without test_macro.py,
+whose element construction on the host dominates: about 460 tests, 3-4 minutes); `FIATB200_REF_SUITE=full` runs
+all 36 files.  Tests that need `gem` / `sympy`-through-gem (absent here: test_precision.py, test_macro.py::test_macro_gem /
 test_macro_sympy) fail the same way without the plugin and are left out.
 """
 import json
@@ -28,25 +29,25 @@ DEFAULT_FILES = ["test_fiat.py", "test_tensor_product.py", "test_regge_hhj.py", 
 NEEDS_GEM = "not macro_gem and not macro_sympy"
 
 
-def _run(mode, tmp_path, workers):
+def _run(mode, tmp_path, workers, files=DEFAULT_FILES, min_passed=600, min_replaced=700, timeout=3000):
     if not os.path.isdir(REF_TESTS):
         pytest.skip("oracle/_ref/ref_tests absent (python -c 'import __graft_entry__ as g; g.build()' makes it where "
                     "/root/reference exists)")
     if os.environ.get("FIATB200_REF_SUITE") == "full":
         targets = [REF_TESTS, f"--ignore={os.path.join(REF_TESTS, 'test_precision.py')}"]
     else:
-        targets = [os.path.join(REF_TESTS, f) for f in DEFAULT_FILES]
+        targets = [os.path.join(REF_TESTS, f) for f in files]
     stats_file = tmp_path / "dropin_stats.jsonl"
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([REF, ROOT]), FIATB200_DROPIN=mode,
                FIATB200_DROPIN_STATS=str(stats_file))
     env.pop("FIATB200_QUICK_NPTS", None)         # the library's default: small calls take the quick plan
     cmd = [sys.executable, "-m", "pytest", "-p", "oracle.dropin_plugin", "-q", "-p", "no:cacheprovider",
            "-c", os.devnull, "--rootdir", str(tmp_path), "-k", NEEDS_GEM, "-n", str(workers)] + targets
-    res = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=3000)
+    res = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=timeout)
     tail = res.stdout[-4000:] + res.stderr[-2000:]
     assert res.returncode == 0, tail
     m = re.search(r"(\d+) passed", res.stdout)
-    assert m and int(m.group(1)) >= 600, tail
+    assert m and int(m.group(1)) >= min_passed, tail
     replaced = fallback = 0
     reasons = {}
     with open(stats_file) as f:
@@ -56,7 +57,7 @@ def _run(mode, tmp_path, workers):
             fallback += rec["fallback"]
             reasons.update(rec["fallback_reasons"])
     # the replacement must actually have been what the tests judged
-    assert replaced >= 700, (replaced, fallback, reasons)
+    assert replaced >= min_replaced, (replaced, fallback, reasons)
     assert fallback <= replaced // 10, (replaced, fallback, reasons)
     # nothing but what the docstring of the plugin lists is handed back to the reference
     for reason in reasons:
@@ -70,4 +71,5 @@ def test_reference_unit_tests_judge_the_oracle(tmp_path):
 
 @pytest.mark.gpu
 def test_reference_unit_tests_judge_the_device_path(tmp_path):
-    _run("device", tmp_path, workers=2)
+    _run("device", tmp_path, workers=3, files=[f for f in DEFAULT_FILES if f != "test_macro.py"],
+         min_passed=400, min_replaced=300, timeout=1500)
