@@ -236,7 +236,8 @@ def test_quick_plan_for_small_calls(name, cuda_device, monkeypatch):
     assert any(k[0] == "resolved" for k in tab._plans)
     again = tab.tabulate(case["order"], case["points"], case["entity"])
     for alpha in got:
-        assert torch.equal(again[alpha], wide[alpha][..., :len(pts)])
+        scale = max(float(wide[alpha].abs().max()), 1e-300)
+        assert float((again[alpha] - wide[alpha][..., :len(pts)]).abs().max()) <= 1e-14 * scale
     _compare(case["desc"], again, case["ref"])
 
 
