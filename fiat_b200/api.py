@@ -879,7 +879,7 @@ class Tabulator:
 _LATTICE_VERDICT = {}      # (device, sd, degree, order) -> the product-form kernel reproduced the general one
 SELF_CHECK_TOL = 2e-13     # derived paths must reproduce the jet kernel this well (relative to each table's max), else jets
 #                            (the thread-per-point jet kernel stays within 2e-15 of the reference up to degree 12)
-_cache_lock = threading.Lock()
+_cache_lock = threading.RLock()
 _by_element = weakref.WeakKeyDictionary()
 _by_desc = collections.OrderedDict()        # description dicts are not weak-referenceable: bounded LRU instead
 MAX_CACHED_DESCRIPTIONS = 64
@@ -906,9 +906,14 @@ def get_tabulator(element, device=None):
         except TypeError:          # not weak-referenceable
             per_dev = element.__dict__.setdefault("_fiat_b200_tabulators", {})
         tab = per_dev.get(str(dev))
-        if tab is None:
-            tab = per_dev[str(dev)] = Tabulator(describe_element(element), dev)
-        return tab
+    if tab is None:
+        # described OUTSIDE the lock: describe_element may tabulate sub-elements of the reference (the point facets
+        # of an interval trace, extract._describe_trace), and where the reference's `tabulate` is bound to this
+        # library -- the maintainer's integration, oracle/dropin_plugin.py -- that call comes back in here
+        new = Tabulator(describe_element(element), dev)
+        with _cache_lock:
+            tab = per_dev.setdefault(str(dev), new)
+    return tab
 
 
 def tabulate(element, order, points, entity=None, device=None):

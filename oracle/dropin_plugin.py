@@ -9,6 +9,10 @@ hdiv_trace.py:133, quadrature_element.py:43) -- is replaced by a call into
 
     FIATB200_DROPIN=device   the CUDA drop-in (`fiat_b200.tabulate_host`, numpy in / numpy out through the C ABI)
     FIATB200_DROPIN=oracle   the CPU oracle (`oracle.fiat_oracle.tabulate` on `describe_element(element)`)
+    FIATB200_DROPIN=emulate  the device mode's HOST logic on a machine without a GPU: `fiat_b200.api.Tabulator` with
+                             the kernel launches of polynomial elements answered by the oracle, so that what the
+                             device mode adds in Python -- trace / quadrature elements, the single-point form, the
+                             exception types handed back -- is judged by the reference's tests on the CPU too
 
 so that the reference's known-answer tests (exact Dubiner values, nodality, partition of unity, macro-element
 continuity, tensor-product dof ordering, ...) judge the replacement directly.  What neither path takes on --
@@ -41,10 +45,10 @@ def _wrap(original):
             pts = numpy.asarray(points)
             if pts.dtype == object:
                 raise NotImplementedError("symbolic points")
-            if MODE == "device":
+            if MODE in ("device", "emulate"):
                 import fiat_b200
                 from FIAT.hdiv_trace import TraceError as ReferenceTraceError
-                out = fiat_b200.tabulate_host(self, order, points, entity)
+                out = fiat_b200.tabulate_host(self, order, points, entity, device="cpu" if MODE == "emulate" else None)
                 # (the binding layer hands the reference's own exception type to the reference's callers)
                 out = {k: (ReferenceTraceError(getattr(v, "msg", str(v))) if isinstance(v, Exception) else numpy.array(v))
                        for k, v in out.items()}
@@ -68,15 +72,45 @@ def _wrap(original):
     return tabulate
 
 
+def _install_cpu_tabulator():
+    """emulate mode: a Tabulator without a device whose polynomial tabulations come from the oracle."""
+    import threading
+    import torch
+    from fiat_b200 import api
+    from oracle import fiat_oracle
+
+    Base = api.Tabulator
+
+    class CpuTabulator(Base):
+        def __init__(self, desc, device=None):
+            self.lib, self.desc, self.device, self.kind = None, desc, torch.device("cpu"), desc["kind"]
+            self._plans, self._lock, self._quick = {}, threading.Lock(), None
+
+        def tabulate(self, order, points, entity=None, flags=0):
+            if self.kind in ("trace", "quadrature"):
+                return Base.tabulate(self, order, points, entity, flags)
+            pts = numpy.asarray(points.cpu() if isinstance(points, torch.Tensor) else points, dtype=float)
+            return {a: torch.as_tensor(v) for a, v in fiat_oracle.tabulate(self.desc, order, pts, entity).items()}
+
+        def tabulate_host(self, order, points, entity=None, chunk_pts=1 << 16, flags=0, out=None):
+            if self.kind in ("trace", "quadrature"):
+                return Base.tabulate_host(self, order, points, entity, chunk_pts, flags, out)
+            return fiat_oracle.tabulate(self.desc, order, numpy.asarray(points, dtype=float), entity)
+
+    api.Tabulator = CpuTabulator
+
+
 def pytest_configure(config):
-    if MODE not in ("device", "oracle"):
+    if MODE not in ("device", "oracle", "emulate"):
         return
+    if MODE == "emulate":
+        _install_cpu_tabulator()
     import FIAT  # noqa: F401  (the live reference, from oracle/_ref on sys.path)
     from FIAT import finite_element, tensor_product, enriched, mixed, discontinuous, hdiv_trace, quadrature_element
     targets = [(finite_element.CiarletElement, "tabulate"), (tensor_product.TensorProductElement, "tabulate"),
                (tensor_product.FlattenedDimensions, "tabulate"), (enriched.EnrichedElement, "tabulate"),
                (mixed.MixedElement, "tabulate"), (discontinuous.DiscontinuousElement, "tabulate")]
-    if MODE == "device":            # the oracle has no trace / quadrature elements (pinned by golden files instead)
+    if MODE in ("device", "emulate"):    # the oracle has no trace / quadrature elements (pinned by golden files instead)
         targets += [(hdiv_trace.HDivTrace, "tabulate"), (quadrature_element.QuadratureElement, "tabulate")]
     for cls, name in targets:
         method = cls.__dict__.get(name)
@@ -87,14 +121,14 @@ def pytest_configure(config):
 def pytest_sessionfinish(session):
     """Under pytest-xdist every worker has its own counters: each appends them to $FIATB200_DROPIN_STATS."""
     path = os.environ.get("FIATB200_DROPIN_STATS")
-    if path and MODE in ("device", "oracle") and (stats["replaced"] or stats["fallback"]):
+    if path and MODE in ("device", "oracle", "emulate") and (stats["replaced"] or stats["fallback"]):
         import json
         with open(path, "a") as f:
             f.write(json.dumps(stats) + "\n")
 
 
 def pytest_terminal_summary(terminalreporter):
-    if MODE in ("device", "oracle"):
+    if MODE in ("device", "oracle", "emulate"):
         path = os.environ.get("FIATB200_DROPIN_STATS")
         if path and os.path.exists(path):
             import json

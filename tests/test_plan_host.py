@@ -233,3 +233,37 @@ def test_stacked_derived_reproduces_reference(name):
     for j, alpha in enumerate(alphas):
         ref = case["ref"][alpha].reshape(-1, len(pts))
         assert abs(out[j * nrows:(j + 1) * nrows] - ref).max() <= tolerance(desc, alpha) * max(abs(ref).max(), 1e-300), alpha
+
+
+@pytest.mark.parametrize("name", ["p8_tet_o2", "rtcf1_quad_o1", "nested_tpe_o1", "gll_q3_hex_face4_o2", "gn_tet_o2"])
+def test_quick_description_builds_only_dense_tables(name):
+    """api._quick_description (small calls): every simplex description in the tree is marked dense_only, and
+    compile_simplex then builds no block packing, value table or fixed-k stream -- and the same dense matrices."""
+    from fiat_b200 import api
+    case = load_case(name)
+    quick = api._quick_description(case["desc"])
+
+    def leaves(d):
+        kind = d["kind"]
+        if kind == "simplex":
+            yield d
+        elif kind == "tensor":
+            yield from leaves(d["A"])
+            yield from leaves(d["B"])
+        elif kind == "flattened":
+            yield from leaves(d["element"])
+        elif kind == "composite":
+            for part in d["parts"]:
+                yield from leaves(part["element"])
+
+    full_leaves, quick_leaves = list(leaves(case["desc"])), list(leaves(quick))
+    assert len(full_leaves) == len(quick_leaves) >= 1
+    assert not any(d.get("dense_only") for d in full_leaves)          # the caller's description is left alone
+    for d_full, d_quick in zip(full_leaves, quick_leaves):
+        assert d_quick["dense_only"] is True
+        prog = planmod.compile_simplex(d_quick, case["order"])
+        assert len(prog.blk_kb) == 0 and len(prog.cstream) == 0 and prog.ncp == 0
+        ref = planmod.compile_simplex(d_full, case["order"])
+        if ref.nslots == prog.nslots and len(ref.blk_kb) == 0:
+            assert numpy.array_equal(ref.ccell_morton, prog.ccell_morton)
+        assert prog.ccell_morton.shape == ref.ccell_morton.shape

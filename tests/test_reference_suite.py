@@ -6,6 +6,11 @@ before those tests are collected.  The reference's known-answer tests -- exact D
 unity, macro-element continuity, tensor-product dof order, trace elements -- then judge
 
     not gpu:  the CPU oracle (`FIATB200_DROPIN=oracle`) -- pins the oracle with the reference's own assertions
+    not gpu:  the device mode's host logic (`FIATB200_DROPIN=emulate`: `fiat_b200.api` with the kernel launches of
+              polynomial elements answered by the oracle) -- trace / quadrature elements, the single-point form, the
+              exception types, and the re-entrancy of the binding: `describe_element` tabulates sub-elements of the
+              reference, which comes back into the library when `tabulate` is bound to it; `get_tabulator` used to
+              hold its cache lock across that call and dead-locked on every interval trace element (found here)
     gpu:      the CUDA path  (`FIATB200_DROPIN=device`, numpy in / numpy out through the C ABI)
 
 The default selection of the CPU test is the files that exercise tabulation most (about 690 tests, 40 s).  On the GPU
@@ -48,7 +53,8 @@ def _run(mode, tmp_path, workers, files=DEFAULT_FILES, min_passed=600, min_repla
                FIATB200_DROPIN_STATS=str(stats_file))
     env.pop("FIATB200_QUICK_NPTS", None)         # the library's default: small calls take the quick plan
     cmd = [sys.executable, "-m", "pytest", "-p", "oracle.dropin_plugin", "-q", "-p", "no:cacheprovider",
-           "-c", os.devnull, "--rootdir", str(tmp_path), "-k", NEEDS_GEM, "-n", str(workers)] + targets
+           "-c", os.devnull, "--rootdir", str(tmp_path), "-k", NEEDS_GEM, "-n", str(workers),
+           "--timeout", "300"] + targets          # (per test: a hang fails that test instead of the whole run)
     try:
         res = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=timeout)
     except subprocess.TimeoutExpired:
@@ -76,6 +82,10 @@ def _run(mode, tmp_path, workers, files=DEFAULT_FILES, min_passed=600, min_repla
 
 def test_reference_unit_tests_judge_the_oracle(tmp_path):
     _run("oracle", tmp_path, workers=4)
+
+
+def test_reference_unit_tests_judge_the_device_host_logic(tmp_path):
+    _run("emulate", tmp_path, workers=4)
 
 
 @pytest.mark.gpu
