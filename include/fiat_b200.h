@@ -101,9 +101,10 @@ typedef struct {
     /* Fixed-k block stream for the register-operand split-cell kernel (optional; cstream_len == 0: absent).
      * k-block j = member slots 4 j .. 4 j + 3.  The packed row blocks are cut into steps of crb row blocks; step s is
      * the run of doubles cstream[cstep_ptr[s] .. cstep_ptr[s + 1]):  ncells * crb int32 records
-     * (mask | first block << 16, subcell-major; bit j of mask: k-block j of that (subcell, row block) is stored),
-     * padded to a multiple of 16 bytes, then the step's blocks (subcell, row block, k-block ascending), 32 doubles
-     * each in mma.m8n8k4 A-fragment order (fiat_b200/plan.py: pack_fixed_stream). */
+     * (n | first block << 16, subcell-major; n = the PREFIX of k-blocks that (subcell, row block) stores: 0 .. n - 1,
+     * everything up to the last k-block one of its rows touches), padded to a multiple of 16 bytes, then the step's
+     * blocks (subcell, row block, k-block ascending), 32 doubles each in mma.m8n8k4 A-fragment order
+     * (fiat_b200/plan.py: pack_fixed_stream; prefix_members orders the slots so that prefixes are short). */
     const double* cstream;
     int64_t cstream_len;
     const int32_t* cstep_ptr;  /* cnsteps + 1 offsets in doubles (even) */
