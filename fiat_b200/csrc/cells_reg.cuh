@@ -1,5 +1,6 @@
 // Split-cell tile kernel with the expansion values in REGISTERS (B operand) and the coefficient blocks streamed
-// through shared memory (A operand): elements on split (macro) complexes with <= 64 members per subcell.
+// through shared memory (A operand): elements on split (macro) complexes with <= 64 members per subcell; the launcher
+// (cells_launch.cu) takes it for <= 20 members, where it beats the segment kernel of cells.cuh.
 //
 // Same input as cells.cuh (the order-0 derived element of fiat_b200/plan.py: macro_merged, one block-sparse
 // coefficient matrix per subcell; FIAT/expansions.py:449-490), other orientation.  cells.cuh gives a warp one 8-row
@@ -9,9 +10,9 @@
 //   * a warp owns two octets of COLUMNS for the whole tile and reads their B fragments -- the member values of its 16
 //     points, k-block j = member slots 4j..4j+3 -- from the expansion table into registers ONCE (KB x 2 doubles);
 //   * all warps walk the row blocks in lockstep, RB at a time ("step"); a step's coefficient blocks of all subcells
-//     (prefix packing of fixed k-blocks, plan.py: pack_fixed_stream) are one contiguous run of global memory that the CTA copies into
-//     shared memory with cp.async one step ahead; per block a warp issues one conflict-free LDS.64 and one DMMA
-//     per octet (both octets in the same subcell, the usual case for sorted columns, share the LDS);
+//     (prefix packing of fixed k-blocks, plan.py: pack_fixed_stream) are one contiguous run of global memory that
+//     the CTA copies into shared memory with cp.async one step ahead; per block a warp issues one conflict-free
+//     LDS.64 and one DMMA per octet (both octets in the same subcell, the usual case for sorted columns, share it);
 //   * the 8 x 8 results go through the column permutation into a CTA-wide staging buffer (double-buffered) and the
 //     previous step's RB * 8 rows leave as full-width coalesced row stores while the current step's DMMAs run;
 //   * one block barrier per step.
@@ -32,10 +33,6 @@ struct CellsRegGeom {
     int uoff;      // doubles before the phase union region (column permutation, octet -> subcell)
 };
 
-__device__ __forceinline__ void fb_cp_async16(void* dst_shared, const void* src_global) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst_shared);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src_global));
-}
 __device__ __forceinline__ void fb_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void fb_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
