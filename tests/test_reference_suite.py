@@ -75,8 +75,10 @@ def _run(mode, tmp_path, workers, files=DEFAULT_FILES, min_passed=600, min_repla
     assert replaced >= min_replaced, (replaced, fallback, reasons)
     assert fallback <= replaced // 4, (replaced, fallback, reasons)
     # nothing but what the docstring of the plugin lists is handed back to the reference
+    # (on the device, sizes the library does not take are handed back as well: "fiat_b200 error 3")
     for reason in reasons:
-        assert "symbolic points" in reason or "elements on a point" in reason or "fiat_b200 error 3" in reason, reasons
+        assert "symbolic points" in reason or "elements on a point" in reason or "fiat_b200 error 3" in reason \
+            or (mode == "device" and reason.startswith(("UnsupportedElement", "UnsupportedByLibrary"))), reasons
     return replaced, fallback
 
 
