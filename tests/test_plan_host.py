@@ -92,7 +92,9 @@ def test_alpha_split_reproduces_reference(name):
     assert prog.kpad % 4 == 0 and emu.blocks_to_dense(prog).shape == (prog.nrows, prog.nslots)
 
 
-@pytest.mark.parametrize("name", ["gn_tet_o2", "walkington_tet_o2", "hct4_tri_o2", "hct_o2", "ps12_o2"])
+@pytest.mark.parametrize("name", ["gn_tet_o2", "walkington_tet_o2", "hct4_tri_o2", "hct_o2", "ps12_o2",
+                                  "alfeld_sorokina_tet_adv_o2", "ch_wf_tet_adv_o1", "p2_wf_tet_adv_o2", "p1_ps_tet_adv_o1",
+                                  "hct6_tri_o2", "jm_tri_o2"])
 def test_macro_merged_reproduces_reference(name):
     """Derived order-0 element of a split-cell element (plan.macro_merged): per-subcell stacked matrices on the
     subcell's un-normalised members; its order-0 tabulation (with the reference's binning and multiplicities) is the
