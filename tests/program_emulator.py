@@ -141,5 +141,78 @@ def stream_to_dense(prog, cell=0):
     return out
 
 
+def run_cells_reg(prog, pts, near, nwarps=16):
+    """The tile algorithm of csrc/cells_reg.cuh, statement by statement, on the host: a tile of 16 * nwarps -
+    8 * ncells points; columns sorted by subcell, each subcell's range padded to octets; warp w owns octets 2w, 2w + 1
+    and reads their B fragments (k-block j = slots 4j..4j+3) once; steps of crb row blocks from the prefix stream
+    (int32 records n | first block << 16, blocks 0 .. n - 1); results through the column permutation into rows
+    row_perm[...]; points in several subcells (or none) are finished thread-per-point from the dense matrices.
+    -> out[row, point] of the order-0 derived element (prog.na == 1)."""
+    assert prog.na == 1 and prog.crb > 0
+    ncells, RB, K = prog.ncells, prog.crb, prog.nslots
+    KB = prog.kpad // 4
+    nstep = len(prog.cstep_ptr) - 1
+    hdr = -(-(ncells * RB) // 4) * 2
+    PTS = 16 * nwarps
+    PT = PTS - 8 * ncells
+    npts = len(pts)
+    out = numpy.full((prog.nrows, npts), numpy.nan)
+    mult = near.sum(axis=0)
+    sd = prog.sd
+    for base in range(0, npts, PT):
+        tile = numpy.arange(base, min(base + PT, npts))
+        cell_of = numpy.where(mult[tile] == 1, near[:, tile].argmax(axis=0), -1)
+        # phase 0: columns sorted by subcell, ranges padded to octets
+        perm, octcell = -numpy.ones(PTS, dtype=int), []
+        off = 0
+        for c in range(ncells):
+            mine = numpy.flatnonzero(cell_of == c)
+            perm[off:off + len(mine)] = mine
+            noct = -(-len(mine) // 8)
+            octcell += [c] * noct
+            off += 8 * noct
+        # phase 1: member values of every column in its own subcell's coordinates (padding columns stay zero)
+        T = numpy.zeros((4 * KB, PTS))
+        for c in range(ncells):
+            cols = [j for j in range(off) if perm[j] >= 0 and cell_of[perm[j]] == c]
+            if cols:
+                A = prog.geom[c, :sd * sd].reshape(sd, sd)
+                x = (pts[tile[perm[cols]]] @ A.T + prog.geom[c, 9:9 + sd]).T
+                T[:K, cols] = _jets(prog, c, x, fixups=False)[:, 0, :]
+        # phase 2: warps x steps
+        for w in range(nwarps):
+            for o in (2 * w, 2 * w + 1):
+                if o >= len(octcell):
+                    continue
+                c = octcell[o]
+                B = T[:, 8 * o:8 * o + 8].reshape(KB, 4, 8)              # B fragments, one per k-block
+                for s in range(nstep):
+                    step = numpy.asarray(prog.cstream[prog.cstep_ptr[s]:prog.cstep_ptr[s + 1]])
+                    meta, frags = step[:hdr].view(numpy.int32), step[hdr:].reshape(-1, 8, 4)
+                    for r in range(RB):
+                        m = int(meta[c * RB + r])
+                        n, first = m & 0xFFFF, m >> 16
+                        acc = numpy.zeros((8, 8))
+                        for kb in range(n - 1, -1, -1):                      # the fall-through run: n - 1, ..., 0
+                            acc += frags[first + kb] @ B[kb]
+                        rb = s * RB + r
+                        for g in range(8):
+                            row = prog.row_perm[rb * 8 + g] if rb * 8 + g < prog.nrows else -1
+                            for col in range(8):
+                                p = perm[8 * o + col]
+                                if row >= 0 and p >= 0:
+                                    out[row, tile[p]] = acc[g, col]
+        # phase 3: points in several subcells (tables averaged) or in none (zero column)
+        for i, p in enumerate(tile):
+            if mult[p] == 1:
+                continue
+            out[:, p] = 0.0
+            for c in numpy.flatnonzero(near[:, p]):
+                A = prog.geom[c, :sd * sd].reshape(sd, sd)
+                x = (pts[p:p + 1] @ A.T + prog.geom[c, 9:9 + sd]).T
+                out[:, p] += prog.ccell[c] @ _jets(prog, c, x)[:, 0, 0] / (1.0 if prog.unique else mult[p])
+    return out
+
+
 def keys(prog):
     return alpha_list(prog.sd, prog.order)

@@ -269,3 +269,26 @@ def test_quick_description_builds_only_dense_tables(name):
         if ref.nslots == prog.nslots and len(ref.blk_kb) == 0:
             assert numpy.array_equal(ref.ccell_morton, prog.ccell_morton)
         assert prog.ccell_morton.shape == ref.ccell_morton.shape
+
+
+@pytest.mark.parametrize("name", ["gn_tet_adv_o2", "alfeld_sorokina_tet_adv_o2", "p2_wf_tet_adv_o2", "hct5_tri_o2"])
+def test_cells_reg_tile_algorithm_reproduces_reference(name):
+    """Executable restatement of the register-operand split-cell kernel (program_emulator.run_cells_reg: column sort
+    with octet padding, B fragments per octet, prefix block stream, scatter through the column permutation, points in
+    several subcells) on adversarial point sets, against the reference's derivative tables."""
+    case = load_case(name)
+    desc, order = case["desc"], case["order"]
+    merged = planmod.macro_merged(desc, order)
+    prog = planmod.compile_simplex(merged, 0)
+    assert prog.crb > 0
+    pts = numpy.asarray(case["points"], dtype=float)[:150]
+    near = fiat_oracle.locate_cells(desc, pts, unique=bool(prog.unique))
+    assert (near.sum(axis=0) > 1).any() or name == "hct5_tri_o2"          # interior facets / vertices are in the set
+    nwarps = 4 if prog.ncells <= 4 else 8                                # tile = 16 * nwarps - 8 * ncells points:
+    out = emu.run_cells_reg(prog, pts, near, nwarps=nwarps)              # small tiles, several of them, a ragged last one
+    assert not numpy.isnan(out).any()
+    alphas = planmod.alpha_list(int(desc["sd"]), order)
+    nrows = out.shape[0] // len(alphas)
+    for j, alpha in enumerate(alphas):
+        ref = case["ref"][alpha].reshape(-1, case["ref"][alpha].shape[-1])[:, :150]
+        assert abs(out[j * nrows:(j + 1) * nrows] - ref).max() <= 2e-13 * max(abs(ref).max(), 1e-300), alpha
